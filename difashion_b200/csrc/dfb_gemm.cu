@@ -1,0 +1,435 @@
+// Persistent warp-specialised tcgen05 GEMM / implicit-GEMM convolution for sm_100a.
+//
+//   warp 0      : TMA producer  (A tile 128x64 bf16 via 2-D or 4-D tiled tensor map, OOB = zero
+//                 gives the 3x3 'same' padding for free; B tile block_n x 64)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=block_n, K=16)
+//   warps 2..5  : epilogue (tcgen05.ld -> fp32 registers -> bias / time-embedding row bias /
+//                 residual / GEGLU -> bf16 or fp32 global stores)
+//
+// Pipelines: STAGES-deep smem ring (full/empty mbarriers) between TMA and MMA, and a 2-deep TMEM
+// accumulator ring (tmem_full/tmem_empty) between MMA and epilogue, so the epilogue of tile i
+// overlaps the main loop of tile i+1.  One CTA per SM, grid = min(#tiles, #SMs).
+//
+// Replaces (see include/dfb200.h): every nn.Conv2d / nn.Linear of diffusers'
+// UNet2DConditionModel.forward as called from DiFashion/models/difashion.py:518-523.
+#include "dfb_host.h"
+#include "../../include/dfb200.h"
+
+namespace dfb {
+
+constexpr int GEMM_BLOCK_M = 128;
+constexpr int GEMM_BLOCK_K = 64;                     // one 128-byte swizzle atom of bf16
+constexpr int GEMM_STAGES = 4;
+constexpr int GEMM_MAX_BLOCK_N = 256;
+constexpr int GEMM_A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;          // 16 KB
+constexpr int GEMM_B_BYTES = GEMM_MAX_BLOCK_N * GEMM_BLOCK_K * 2;      // 32 KB (max)
+constexpr int GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES;          // 48 KB
+constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int GEMM_TMEM_COLS = 512;
+
+struct GemmMaps {
+  CUtensorMap a[2];
+  CUtensorMap b;
+};
+
+struct GemmKernelParams {
+  int M, N, block_n, n_tiles_m, n_tiles_n;
+  int conv, TH, TB, tiles_per_img;
+  int nseg;
+  int seg_ntaps[2];
+  int seg_ncblk[2];
+  int tap_dh[18], tap_dw[18], tap_coff[18];
+  const float* bias;
+  const float* rowbias;
+  int rowbias_ld, rows_per_batch;
+  const void* residual;
+  int res_ld, res_fp32;
+  void* out;
+  int out_ld, out_fp32, geglu, vec_ok;
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ GemmKernelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + GEMM_STAGES * GEMM_STAGE_BYTES;
+  // barrier layout (8 bytes each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (GEMM_STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * GEMM_STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * GEMM_STAGES + 2 + s); };
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * GEMM_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.n_tiles_m * p.n_tiles_n;
+  const int nk = p.seg_ntaps[0] * p.seg_ncblk[0] + (p.nseg > 1 ? p.seg_ntaps[1] * p.seg_ncblk[1] : 0);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.a[0]);
+    if (p.nseg > 1) tma_prefetch_desc(&maps.a[1]);
+    tma_prefetch_desc(&maps.b);
+    for (int s = 0; s < GEMM_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);   // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, GEMM_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = GEMM_A_BYTES + (uint32_t)p.block_n * GEMM_BLOCK_K * 2;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int mt = tile / p.n_tiles_n;
+        const int nt = tile - mt * p.n_tiles_n;
+        int b0 = 0, h0 = 0;
+        if (p.conv) {
+          if (p.TB == 1) {
+            b0 = mt / p.tiles_per_img;
+            h0 = (mt - b0 * p.tiles_per_img) * p.TH;
+          } else {
+            b0 = mt * p.TB;
+          }
+        }
+        int kb = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const void* tm = &maps.a[s];
+          for (int tap = 0; tap < p.seg_ntaps[s]; ++tap) {
+            const int ti = s * 9 + tap;
+            const int dh = p.tap_dh[ti], dw = p.tap_dw[ti], coff = p.tap_coff[ti];
+            for (int cb = 0; cb < p.seg_ncblk[s]; ++cb, ++kb) {
+              mbar_wait(empty_bar(stage), phase ^ 1u);
+              const uint32_t sa = smem_base + stage * GEMM_STAGE_BYTES;
+              const uint32_t sb = sa + GEMM_A_BYTES;
+              mbar_expect_tx(full_bar(stage), tx_bytes);
+              if (p.conv)
+                tma_load_4d(tm, sa, full_bar(stage), coff + cb * GEMM_BLOCK_K, dw, h0 + dh, b0);
+              else
+                tma_load_2d(tm, sa, full_bar(stage), coff + cb * GEMM_BLOCK_K, mt * GEMM_BLOCK_M);
+              tma_load_2d(&maps.b, sb, full_bar(stage), kb * GEMM_BLOCK_K, nt * p.block_n);
+              if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t idesc = make_idesc_f16(GEMM_BLOCK_M, (uint32_t)p.block_n, true);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)as * GEMM_MAX_BLOCK_N;
+        for (int kb = 0; kb < nk; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * GEMM_STAGE_BYTES;
+          const uint32_t sb = sa + GEMM_A_BYTES;
+          const uint64_t da = make_smem_desc(sa, 16, 1024, SWZ_128B);
+          const uint64_t db = make_smem_desc(sb, 16, 1024, SWZ_128B);
+#pragma unroll
+          for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in the
+            // (addr >> 4) start-address field
+            umma_f16_ss(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          }
+          umma_commit(empty_bar(stage));       // frees the smem slot when these MMAs retire
+          if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(as));            // accumulator ready for the epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..5) =====================
+    const int quarter = warp & 3;              // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int mt = tile / p.n_tiles_n;
+      const int nt = tile - mt * p.n_tiles_n;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const int m = mt * GEMM_BLOCK_M + row;
+      const bool m_ok = m < p.M;
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * GEMM_MAX_BLOCK_N;
+      const float* rb = (p.rowbias && m_ok) ? p.rowbias + (size_t)(m / p.rows_per_batch) * p.rowbias_ld : nullptr;
+      for (int c = 0; c < p.block_n / 32; ++c) {
+        const int n0 = nt * p.block_n + c * 32;
+        if (n0 >= p.N) break;                  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr0 + (uint32_t)(c * 32), r);
+        tmem_ld_wait();
+        if (!m_ok) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        const int nvalid = min(32, p.N - n0);
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nvalid) v[j] += __ldg(p.bias + n0 + j);
+        }
+        if (rb) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nvalid) v[j] += __ldg(rb + n0 + j);
+        }
+        if (p.geglu) {
+          // columns [0,16) = values, [16,32) = gates of output columns n0/2 .. n0/2+15
+          float o[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[j] = v[j] * gelu_erf_f(v[16 + j]);
+          const size_t off = (size_t)m * p.out_ld + (n0 >> 1);
+          if (p.out_fp32) {
+            float* dst = reinterpret_cast<float*>(p.out) + off;
+            if (p.vec_ok) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) dst[j] = o[j];
+            }
+          } else {
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
+            if (p.vec_ok) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 8)
+                *reinterpret_cast<uint4*>(dst + j) =
+                    make_uint4(pack_bf16x2(o[j], o[j + 1]), pack_bf16x2(o[j + 2], o[j + 3]),
+                               pack_bf16x2(o[j + 4], o[j + 5]), pack_bf16x2(o[j + 6], o[j + 7]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) dst[j] = __float2bfloat16(o[j]);
+            }
+          }
+          continue;
+        }
+        const bool fast = p.vec_ok && nvalid == 32;
+        if (p.residual) {
+          const size_t roff = (size_t)m * p.res_ld + n0;
+          if (p.res_fp32) {
+            const float* rs = reinterpret_cast<const float*>(p.residual) + roff;
+            if (fast) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 t = *reinterpret_cast<const float4*>(rs + j);
+                v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nvalid) v[j] += rs[j];
+            }
+          } else {
+            const __nv_bfloat16* rs = reinterpret_cast<const __nv_bfloat16*>(p.residual) + roff;
+            if (fast) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                const uint4 t = *reinterpret_cast<const uint4*>(rs + j);
+                v[j] += bf16_lo(t.x); v[j + 1] += bf16_hi(t.x);
+                v[j + 2] += bf16_lo(t.y); v[j + 3] += bf16_hi(t.y);
+                v[j + 4] += bf16_lo(t.z); v[j + 5] += bf16_hi(t.z);
+                v[j + 6] += bf16_lo(t.w); v[j + 7] += bf16_hi(t.w);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nvalid) v[j] += __bfloat162float(rs[j]);
+            }
+          }
+        }
+        const size_t off = (size_t)m * p.out_ld + n0;
+        if (p.out_fp32) {
+          float* dst = reinterpret_cast<float*>(p.out) + off;
+          if (fast) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) dst[j] = v[j];
+          }
+        } else {
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
+          if (fast) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8)
+              *reinterpret_cast<uint4*>(dst + j) =
+                  make_uint4(pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]),
+                             pack_bf16x2(v[j + 4], v[j + 5]), pack_bf16x2(v[j + 6], v[j + 7]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) dst[j] = __float2bfloat16(v[j]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, GEMM_TMEM_COLS);
+  }
+}
+
+static int choose_block_n(int N) {
+  static const int cands[] = {256, 224, 192, 160, 128, 96, 64, 32};
+  int best = 32, best_waste = 1 << 30;
+  for (int bn : cands) {
+    const int waste = ((N + bn - 1) / bn) * bn - N;
+    if (waste < best_waste) { best_waste = waste; best = bn; }
+  }
+  return best;
+}
+
+}  // namespace dfb
+
+using namespace dfb;
+
+extern "C" int dfb_gemm(const dfb_gemm_params* q, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  DFB_REQUIRE(q != nullptr, "dfb_gemm: null params");
+  DFB_REQUIRE(q->nseg == 1 || q->nseg == 2, "dfb_gemm: nseg must be 1 or 2");
+  DFB_REQUIRE(q->M > 0 && q->N > 0, "dfb_gemm: empty problem");
+  DFB_REQUIRE(q->w != nullptr && q->out != nullptr && q->a[0] != nullptr, "dfb_gemm: null buffer");
+  DFB_REQUIRE((reinterpret_cast<uintptr_t>(q->w) & 15) == 0 && (q->w_ld % 8) == 0, "dfb_gemm: weights must be 16B aligned");
+
+  GemmKernelParams kp;
+  memset(&kp, 0, sizeof(kp));
+  GemmMaps maps;
+  memset(&maps, 0, sizeof(maps));
+
+  kp.M = q->M;
+  kp.N = q->N;
+  int bn = q->block_n > 0 ? q->block_n : choose_block_n(q->N);
+  DFB_REQUIRE(bn % 32 == 0 && bn >= 32 && bn <= GEMM_MAX_BLOCK_N, "dfb_gemm: block_n must be a multiple of 32 in [32,256]");
+  kp.block_n = bn;
+  kp.n_tiles_n = (q->N + bn - 1) / bn;
+  kp.conv = q->conv ? 1 : 0;
+  kp.nseg = q->nseg;
+
+  uint32_t boxA[4];
+  if (kp.conv) {
+    const int B = q->B, H = q->H, W = q->W;
+    DFB_REQUIRE(B > 0 && H > 0 && W > 0 && (long long)B * H * W == q->M, "dfb_gemm: conv geometry does not match M");
+    DFB_REQUIRE(W <= 128 && (128 % W) == 0, "dfb_gemm: conv width must divide 128");
+    int TH = 128 / W;
+    if (TH > H) TH = H;
+    DFB_REQUIRE(H % TH == 0 && (128 % (W * TH)) == 0, "dfb_gemm: conv height incompatible with 128-pixel tiles");
+    const int TB = 128 / (W * TH);
+    kp.TH = TH;
+    kp.TB = TB;
+    kp.tiles_per_img = H / TH;
+    kp.n_tiles_m = TB == 1 ? B * kp.tiles_per_img : (B + TB - 1) / TB;
+    boxA[0] = GEMM_BLOCK_K; boxA[1] = (uint32_t)W; boxA[2] = (uint32_t)TH; boxA[3] = (uint32_t)TB;
+  } else {
+    kp.n_tiles_m = (q->M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+    boxA[0] = GEMM_BLOCK_K; boxA[1] = GEMM_BLOCK_M;
+  }
+
+  int kp_total = 0;
+  for (int s = 0; s < q->nseg; ++s) {
+    DFB_REQUIRE(q->a[s] != nullptr, "dfb_gemm: null A segment");
+    DFB_REQUIRE(q->ntaps[s] >= 1 && q->ntaps[s] <= 9, "dfb_gemm: 1..9 taps per segment");
+    DFB_REQUIRE(q->a_c[s] > 0, "dfb_gemm: empty A segment");
+    DFB_REQUIRE((reinterpret_cast<uintptr_t>(q->a[s]) & 15) == 0 && (q->a_ld[s] % 8) == 0, "dfb_gemm: A must be 16B aligned with a_ld % 8 == 0");
+    kp.seg_ntaps[s] = q->ntaps[s];
+    kp.seg_ncblk[s] = (q->a_c[s] + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+    int max_coff = 0;
+    for (int t = 0; t < q->ntaps[s]; ++t) {
+      kp.tap_dh[s * 9 + t] = q->tap_dh[s][t];
+      kp.tap_dw[s * 9 + t] = q->tap_dw[s][t];
+      kp.tap_coff[s * 9 + t] = q->tap_coff[s][t];
+      DFB_REQUIRE(q->tap_coff[s][t] >= 0, "dfb_gemm: negative channel offset");
+      if (q->tap_coff[s][t] > max_coff) max_coff = q->tap_coff[s][t];
+      if (!kp.conv) DFB_REQUIRE(q->tap_dh[s][t] == 0 && q->tap_dw[s][t] == 0, "dfb_gemm: shifts need conv addressing");
+    }
+    DFB_REQUIRE(max_coff == 0 || (q->a_c[s] % GEMM_BLOCK_K) == 0, "dfb_gemm: channel offsets need a_c % 64 == 0");
+    const uint64_t cext = (uint64_t)max_coff + (uint64_t)q->a_c[s];
+    DFB_REQUIRE(cext <= (uint64_t)q->a_ld[s], "dfb_gemm: channel extent exceeds the row pitch");
+    kp_total += q->ntaps[s] * kp.seg_ncblk[s] * GEMM_BLOCK_K;
+    int rc;
+    if (kp.conv) {
+      uint64_t dims[4] = {cext, (uint64_t)q->W, (uint64_t)q->H, (uint64_t)q->B};
+      uint64_t str[3] = {(uint64_t)q->a_ld[s] * 2, (uint64_t)q->a_ld[s] * 2 * q->W, (uint64_t)q->a_ld[s] * 2 * q->W * q->H};
+      rc = make_tmap(&maps.a[s], q->a[s], 2, 4, dims, str, boxA, CU_TENSOR_MAP_SWIZZLE_128B);
+    } else {
+      uint64_t dims[2] = {cext, (uint64_t)q->M};
+      uint64_t str[1] = {(uint64_t)q->a_ld[s] * 2};
+      rc = make_tmap(&maps.a[s], q->a[s], 2, 2, dims, str, boxA, CU_TENSOR_MAP_SWIZZLE_128B);
+    }
+    if (rc != DFB_OK) return rc;
+  }
+  DFB_REQUIRE(kp_total <= q->w_ld, "dfb_gemm: packed weight K extent smaller than the A operand implies");
+  {
+    uint64_t dims[2] = {(uint64_t)q->w_ld, (uint64_t)q->N};
+    uint64_t str[1] = {(uint64_t)q->w_ld * 2};
+    uint32_t box[2] = {GEMM_BLOCK_K, (uint32_t)bn};
+    int rc = make_tmap(&maps.b, q->w, 2, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != DFB_OK) return rc;
+  }
+
+  kp.bias = q->bias;
+  kp.rowbias = q->rowbias;
+  kp.rowbias_ld = q->rowbias_ld;
+  kp.rows_per_batch = q->rows_per_batch > 0 ? q->rows_per_batch : 1;
+  kp.residual = q->residual;
+  kp.res_ld = q->res_ld;
+  kp.res_fp32 = q->res_dtype == DFB_DTYPE_F32;
+  kp.out = q->out;
+  kp.out_ld = q->out_ld;
+  kp.out_fp32 = q->out_dtype == DFB_DTYPE_F32;
+  kp.geglu = q->geglu ? 1 : 0;
+  if (kp.geglu) DFB_REQUIRE(q->N % 32 == 0 && q->residual == nullptr, "dfb_gemm: GEGLU needs N % 32 == 0 and no residual");
+  const int out_elem = kp.out_fp32 ? 4 : 2;
+  bool vec_ok = ((reinterpret_cast<uintptr_t>(q->out) & 15) == 0) && (((size_t)q->out_ld * out_elem) % 16 == 0);
+  if (q->residual) {
+    const int res_elem = kp.res_fp32 ? 4 : 2;
+    vec_ok = vec_ok && ((reinterpret_cast<uintptr_t>(q->residual) & 15) == 0) && (((size_t)q->res_ld * res_elem) % 16 == 0);
+  }
+  kp.vec_ok = vec_ok ? 1 : 0;
+
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  DFB_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    attr_done[dev] = true;
+  }
+  const int num_tiles = kp.n_tiles_m * kp.n_tiles_n;
+  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  gemm_tcgen05_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(maps, kp);
+  DFB_CHECK_CUDA(cudaGetLastError());
+  return DFB_OK;
+}

@@ -1,0 +1,140 @@
+"""GPU parity of the tcgen05 GEMM / implicit-GEMM conv kernel against plain PyTorch (fp64 math on
+the same bf16-rounded operands).  Tolerance: fp32 accumulation of bf16 products -> rel-L2 <= 2e-3
+for bf16 outputs (output rounding 2^-9), <= 1e-5 for fp32 outputs."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.util import err_report, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from difashion_b200 import ops
+    return ops
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale)
+
+
+@pytest.mark.parametrize("M,N,K,bn", [
+    (128, 32, 64, 32), (128, 64, 64, 0), (128, 128, 256, 0), (256, 256, 512, 0), (384, 320, 320, 0),
+    (1000, 640, 1280, 0), (4096, 1280, 320, 0), (77, 100, 768, 0), (16, 1280, 320, 0),
+    (4096, 2560, 320, 0), (300, 4, 320, 0), (2048, 1152, 320, 0),
+])
+def test_plain_gemm_fp32_out(M, N, K, bn):
+    ops = _ops()
+    a = _rand((M, K), 1).bfloat16().cuda()
+    w = _rand((N, K), 2, K ** -0.5).cuda()
+    wp = ops.pack_linear(w)
+    out = torch.empty(M, N, dtype=torch.float32, device="cuda")
+    ops.gemm([a], wp, N, out=out, block_n=bn)
+    torch.cuda.synchronize()
+    ref = a.double() @ wp[:, :K].double().t()
+    assert rel_l2(out, ref) < 1e-5, err_report(out, ref, f"gemm {M}x{N}x{K}")
+
+
+def test_gemm_epilogue_bias_residual_bf16():
+    ops = _ops()
+    M, N, K = 1024, 640, 640
+    a = _rand((M, K), 3).bfloat16().cuda()
+    w = _rand((N, K), 4, K ** -0.5).cuda()
+    bias = _rand((N,), 5).cuda()
+    res = _rand((M, N), 6).cuda()
+    wp = ops.pack_linear(w)
+    ref = a.double() @ wp.double().t() + bias.double() + res.double()
+    out = torch.empty(M, N, dtype=torch.float32, device="cuda")
+    ops.gemm([a], wp, N, out=out, bias=bias, residual=res)
+    torch.cuda.synchronize()
+    assert rel_l2(out, ref) < 1e-5, err_report(out, ref, "bias+res fp32")
+    outb = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    resb = res.bfloat16()
+    ops.gemm([a], wp, N, out=outb, bias=bias, residual=resb)
+    torch.cuda.synchronize()
+    refb = a.double() @ wp.double().t() + bias.double() + resb.double()
+    assert rel_l2(outb, refb) < 3e-3, err_report(outb, refb, "bias+res bf16")
+
+
+def test_gemm_rowbias_and_strided_out():
+    ops = _ops()
+    B, S, N, K = 4, 256, 320, 320
+    a = _rand((B * S, K), 7).bfloat16().cuda()
+    w = _rand((N, K), 8, K ** -0.5).cuda()
+    rb = _rand((B, 1000), 9).cuda()[:, 100:100 + N]          # strided row-bias slice
+    wp = ops.pack_linear(w)
+    big = torch.zeros(B * S, 2 * N, dtype=torch.float32, device="cuda")
+    out = big[:, N:]                                           # write into a column slice
+    ops.gemm([a], wp, N, out=out, rowbias=rb, rows_per_batch=S)
+    torch.cuda.synchronize()
+    ref = a.double() @ wp.double().t() + rb.double().repeat_interleave(S, 0)
+    assert rel_l2(out, ref) < 1e-5, err_report(out, ref, "rowbias")
+    assert float(big[:, :N].abs().max()) == 0.0
+
+
+def test_gemm_geglu():
+    ops = _ops()
+    M, C = 512, 320
+    a = _rand((M, C), 10).bfloat16().cuda()
+    w = _rand((8 * C, C), 11, C ** -0.5).cuda()
+    b = _rand((8 * C,), 12, 0.1).cuda()
+    wp, bp = ops.pack_geglu(w, b)
+    out = torch.empty(M, 4 * C, dtype=torch.bfloat16, device="cuda")
+    ops.gemm([a], wp, 8 * C, out=out, bias=bp, geglu=True)
+    torch.cuda.synchronize()
+    y = a.double() @ w.bfloat16().double().t() + b.double()
+    ref = y[:, :4 * C] * F.gelu(y[:, 4 * C:])
+    assert rel_l2(out, ref) < 3e-3, err_report(out, ref, "geglu")
+
+
+def test_gemm_two_segments_concat_k():
+    ops = _ops()
+    M, K1, K2, N = 640, 320, 640, 320
+    a1 = _rand((M, K1), 13).bfloat16().cuda()
+    a2 = _rand((M, K2), 14).bfloat16().cuda()
+    w = _rand((N, K1 + K2), 15, (K1 + K2) ** -0.5).cuda()
+    wp = ops.pack_linear(w)
+    out = torch.empty(M, N, dtype=torch.float32, device="cuda")
+    ops.gemm([a1, a2], wp, N, out=out)
+    torch.cuda.synchronize()
+    ref = torch.cat([a1, a2], 1).double() @ wp.double().t()
+    assert rel_l2(out, ref) < 1e-5, err_report(out, ref, "2seg")
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [
+    (2, 64, 64, 320, 320), (3, 32, 32, 640, 640), (4, 16, 16, 1280, 1280), (5, 8, 8, 1280, 1280),
+    (2, 64, 64, 8, 320), (2, 64, 64, 320, 4), (3, 4, 4, 128, 128), (2, 2, 2, 64, 128),
+])
+def test_conv3x3(B, H, W, Cin, Cout):
+    ops = _ops()
+    x = _rand((B, H, W, Cin), 20).bfloat16().cuda()
+    w = _rand((Cout, Cin, 3, 3), 21, (9 * Cin) ** -0.5).cuda()
+    bias = _rand((Cout,), 22).cuda()
+    wp = ops.pack_conv3x3(w)
+    out = torch.empty(B, H, W, Cout, dtype=torch.float32, device="cuda")
+    ops.gemm([x], wp, Cout, out=out, taps=[ops.TAPS_3X3], conv_geom=(B, H, W), bias=bias)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.double().permute(0, 3, 1, 2), w.bfloat16().double(), bias.double(), padding=1).permute(0, 2, 3, 1)
+    assert rel_l2(out, ref) < 1e-5, err_report(out.reshape(-1, Cout), ref.reshape(-1, Cout), f"conv {B}x{H}x{W} {Cin}->{Cout}")
+
+
+def test_conv3x3_plus_shortcut_segment_and_rowbias():
+    """conv2 of a ResnetBlock2D with the 1x1 shortcut folded in as an extra K segment."""
+    ops = _ops()
+    B, H, W, Cin, Cout = 2, 32, 32, 960, 640
+    hn = _rand((B, H, W, Cout), 30).bfloat16().cuda()
+    xr = _rand((B, H, W, Cin), 31).bfloat16().cuda()
+    w2 = _rand((Cout, Cout, 3, 3), 32, (9 * Cout) ** -0.5).cuda()
+    ws = _rand((Cout, Cin, 1, 1), 33, Cin ** -0.5).cuda()
+    temb = _rand((B, Cout), 34).cuda()
+    wp = torch.cat([ops.pack_conv3x3(w2), ops.pack_linear(ws)], dim=1).contiguous()
+    out = torch.empty(B, H, W, Cout, dtype=torch.float32, device="cuda")
+    ops.gemm([hn, xr], wp, Cout, out=out, taps=[ops.TAPS_3X3, ops.TAP_CENTER], conv_geom=(B, H, W),
+             rowbias=temb, rows_per_batch=H * W)
+    torch.cuda.synchronize()
+    ref = (F.conv2d(hn.double().permute(0, 3, 1, 2), w2.bfloat16().double(), padding=1)
+           + F.conv2d(xr.double().permute(0, 3, 1, 2), ws.bfloat16().double())
+           + temb.double()[:, :, None, None]).permute(0, 2, 3, 1)
+    assert rel_l2(out, ref) < 1e-5, err_report(out.reshape(-1, Cout), ref.reshape(-1, Cout), "conv+shortcut")
