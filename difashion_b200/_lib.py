@@ -46,7 +46,21 @@ class GemmParams(C.Structure):
         ("out_ld", C.c_int32),
         ("out_dtype", C.c_int32),
         ("geglu", C.c_int32),
+        ("act", C.c_int32),
         ("block_n", C.c_int32),
+    ]
+
+
+class AttnParams(C.Structure):
+    """Mirror of ``dfb_attn_params`` (include/dfb200.h)."""
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("out", C.c_void_p),
+        ("q_ld", C.c_int32), ("k_ld", C.c_int32), ("v_ld", C.c_int32), ("out_ld", C.c_int32),
+        ("q_col0", C.c_int32), ("k_col0", C.c_int32), ("v_col0", C.c_int32), ("out_col0", C.c_int32),
+        ("B", C.c_int32), ("heads", C.c_int32), ("Sq", C.c_int32), ("Skv", C.c_int32), ("dp", C.c_int32),
+        ("scale", C.c_float),
+        ("block_kv", C.c_int32),
+        ("dbg_v_lbo", C.c_int32), ("dbg_v_sbo", C.c_int32),
     ]
 
 
@@ -60,6 +74,28 @@ _PROTOTYPES = {
     "dfb_abi_version": (C.c_int, []),
     "dfb_num_sms": (C.c_int, []),
     "dfb_gemm": (C.c_int, [C.POINTER(GemmParams), C.c_void_p]),
+    "dfb_attention": (C.c_int, [C.POINTER(AttnParams), C.c_void_p]),
+    "dfb_groupnorm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "dfb_layernorm": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int,
+                                C.c_int, C.c_int, C.c_void_p]),
+    "dfb_cfg_step": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.c_void_p, C.c_float,
+                               C.POINTER(C.c_float), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
+                               C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "dfb_mutual_gather_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                        C.c_void_p, C.c_void_p]),
+    "dfb_mutual_blend": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int,
+                                   C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_void_p,
+                                   C.c_void_p]),
+    "dfb_nchw_to_nhwc_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "dfb_nhwc_to_nchw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "dfb_pad_cast_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_void_p]),
+    "dfb_upsample2x": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "dfb_space_to_depth": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "dfb_timestep_embedding": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float,
+                                         C.c_void_p]),
 }
 
 

@@ -1,0 +1,339 @@
+// Flash-style attention forward on tcgen05 / TMEM / TMA for sm_100a.
+//
+// Replaces diffusers' Attention processors (XFormersAttnProcessor / AttnProcessor2_0) that run
+// inside UNet2DConditionModel.forward (reference call DiFashion/models/difashion.py:518-523,
+// xformers enabled at :109-118): softmax(Q K^T * scale) V per (batch row, head).
+//
+// One CTA = one 128-row query tile of one (batch, head).  192 threads:
+//   warp 0     : TMA producer (Q once; K/V tiles through a 2-stage ring)
+//   warp 1     : TMEM allocator + single-thread tcgen05.mma issuer
+//   warps 2..5 : softmax (thread <-> query row <-> TMEM lane): S from TMEM, online max/sum in the
+//                exp2 domain with lazy rescaling, P (bf16) -> shared memory, O rescale in TMEM,
+//                final O / l -> bf16 global store.
+// Head dim is padded to a multiple of 16 (d=40 -> 48) by the projection weights' packing; every
+// operand is staged as 16-element (32-byte) column chunks with the 32-byte swizzle:
+//   Q, K : K-major  A / B operands of S = Q K^T        (N = block_kv, K = dp)
+//   P    : K-major  A operand of O += P V              (K = block_kv), written by the softmax warps
+//   V    : MN-major B operand ([kv rows][16 d-cols] chunks; LBO = chunk stride, SBO = 8 kv rows)
+// S occupies TMEM columns [0, block_kv), O columns [block_kv, block_kv + dp).
+// Several CTAs are resident per SM so one CTA's MMAs overlap another's exponentials.
+#include "dfb_host.h"
+#include "../../include/dfb200.h"
+
+namespace dfb {
+
+constexpr int ATT_BLOCK_Q = 128;
+constexpr int ATT_THREADS = 192;
+constexpr int ATT_STAGES = 2;
+
+struct AttnMaps {
+  CUtensorMap q, k, v;
+};
+
+struct AttnKernelParams {
+  int Sq, Skv, dp, block_kv, n_kv_tiles;
+  int q_col0, k_col0, v_col0;     // column of head 0 in each operand (elements)
+  float scale_log2;
+  __nv_bfloat16* out;
+  int out_ld, out_col0;
+  long long out_batch_stride;     // elements
+  uint32_t tmem_cols;
+  uint32_t v_lbo, v_sbo;          // MN-major V descriptor strides (bytes)
+};
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(ATT_THREADS)
+attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnKernelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int dchunks = p.dp >> 4;
+  const uint32_t q_bytes = (uint32_t)dchunks * ATT_BLOCK_Q * 32u;
+  const uint32_t kv_chunk_bytes = (uint32_t)p.block_kv * 32u;
+  const uint32_t kv_tile_bytes = (uint32_t)dchunks * kv_chunk_bytes;       // K (or V) tile
+  const uint32_t p_bytes = (uint32_t)(p.block_kv >> 4) * ATT_BLOCK_Q * 32u;
+  const uint32_t sQ = smem_base;
+  const uint32_t sP = sQ + q_bytes;
+  const uint32_t sKV = sP + p_bytes;                                       // stage s: K then V
+  const uint32_t bar_base = sKV + ATT_STAGES * 2 * kv_tile_bytes;
+  const uint32_t q_full = bar_base;
+  const uint32_t s_full = bar_base + 8;
+  const uint32_t p_full = bar_base + 16;
+  const uint32_t o_done = bar_base + 24;
+  auto kv_full = [&](int s) { return bar_base + 32u + 8u * s; };
+  auto kv_empty = [&](int s) { return bar_base + 32u + 8u * (ATT_STAGES + s); };
+  const uint32_t tmem_ptr_smem = bar_base + 32u + 8u * (2 * ATT_STAGES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  const int n_tiles = p.n_kv_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.q);
+    tma_prefetch_desc(&maps.k);
+    tma_prefetch_desc(&maps.v);
+    mbar_init(q_full, 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_done, 1);
+    for (int s = 0; s < ATT_STAGES; ++s) {
+      mbar_init(kv_full(s), 1);
+      mbar_init(kv_empty(s), 1);
+    }
+    fence_mbar_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+  const uint32_t tmem_S = tmem_base;
+  const uint32_t tmem_O = tmem_base + (uint32_t)p.block_kv;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer ----------------
+      mbar_expect_tx(q_full, q_bytes);
+      for (int c = 0; c < dchunks; ++c)
+        tma_load_3d(&maps.q, sQ + (uint32_t)c * ATT_BLOCK_Q * 32u, q_full, p.q_col0 + head * p.dp + c * 16,
+                    qt * ATT_BLOCK_Q, b);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j % ATT_STAGES;
+        const uint32_t ph = (uint32_t)(j / ATT_STAGES) & 1u;
+        mbar_wait(kv_empty(st), ph ^ 1u);
+        const uint32_t sK = sKV + (uint32_t)st * 2 * kv_tile_bytes;
+        const uint32_t sV = sK + kv_tile_bytes;
+        mbar_expect_tx(kv_full(st), 2 * kv_tile_bytes);
+        for (int c = 0; c < dchunks; ++c)
+          tma_load_3d(&maps.k, sK + (uint32_t)c * kv_chunk_bytes, kv_full(st), p.k_col0 + head * p.dp + c * 16,
+                      j * p.block_kv, b);
+        for (int c = 0; c < dchunks; ++c)
+          tma_load_3d(&maps.v, sV + (uint32_t)c * kv_chunk_bytes, kv_full(st), p.v_col0 + head * p.dp + c * 16,
+                      j * p.block_kv, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer ----------------
+      const uint32_t idesc_qk = make_idesc_f16(ATT_BLOCK_Q, (uint32_t)p.block_kv, true, 0, 0);
+      const uint32_t idesc_pv = make_idesc_f16(ATT_BLOCK_Q, (uint32_t)p.dp, true, 0, 1);
+      auto issue_qk = [&](int st) {
+        const uint32_t sK = sKV + (uint32_t)st * 2 * kv_tile_bytes;
+        for (int c = 0; c < dchunks; ++c) {
+          const uint64_t da = make_smem_desc(sQ + (uint32_t)c * ATT_BLOCK_Q * 32u, 16, 256, SWZ_32B);
+          const uint64_t db = make_smem_desc(sK + (uint32_t)c * kv_chunk_bytes, 16, 256, SWZ_32B);
+          umma_f16_ss(tmem_S, da, db, idesc_qk, c != 0);
+        }
+        umma_commit(s_full);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(kv_full(0), 0);
+      tc_fence_after();
+      issue_qk(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j % ATT_STAGES;
+        mbar_wait(p_full, (uint32_t)j & 1u);
+        tc_fence_after();
+        const uint32_t sV = sKV + (uint32_t)st * 2 * kv_tile_bytes + kv_tile_bytes;
+        for (int k = 0; k < (p.block_kv >> 4); ++k) {
+          const uint64_t da = make_smem_desc(sP + (uint32_t)k * ATT_BLOCK_Q * 32u, 16, 256, SWZ_32B);
+          const uint64_t db = make_smem_desc(sV + (uint32_t)k * 512u, p.v_lbo, p.v_sbo, SWZ_32B);
+          umma_f16_ss(tmem_O, da, db, idesc_pv, (j | k) != 0);
+        }
+        umma_commit(o_done);
+        umma_commit(kv_empty(st));
+        if (j + 1 < n_tiles) {
+          const int st2 = (j + 1) % ATT_STAGES;
+          mbar_wait(kv_full(st2), (uint32_t)((j + 1) / ATT_STAGES) & 1u);
+          tc_fence_after();
+          issue_qk(st2);
+        }
+      }
+    }
+  } else {
+    // ---------------- softmax / correction / epilogue warps ----------------
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const int q_row = qt * ATT_BLOCK_Q + row;
+    float m_ref = -INFINITY, l = 0.f;
+    const int kv_chunks = p.block_kv >> 4;
+    const uint32_t p_row = sP + (uint32_t)row * 32u;
+    const uint32_t flip = (uint32_t)((row >> 2) & 1) << 4;     // 32B-swizzle: 16B halves swap on rows 4..7 of 8
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(s_full, (uint32_t)j & 1u);
+      tc_fence_after();
+      const int kv_valid = min(p.block_kv, p.Skv - j * p.block_kv);
+      float mx = -INFINITY;
+      for (int c = 0; c < kv_chunks; ++c) {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(tmem_S + lane_addr + (uint32_t)(c * 16), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (c * 16 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+      }
+      mx *= p.scale_log2;
+      const bool need = mx > m_ref + 8.0f;
+      const bool need_any = __any_sync(0xffffffffu, need);
+      if (j > 0) {
+        mbar_wait(o_done, (uint32_t)(j - 1) & 1u);   // PV_{j-1} retired: P buffer free, O stable
+        tc_fence_after();
+      }
+      if (need_any) {
+        const float m_new = need ? mx : m_ref;
+        const float alpha = ex2f(m_ref - m_new);     // m_ref = -inf on the first tile -> 0
+        if (j > 0) {
+          for (int c = 0; c < dchunks; ++c) {
+            uint32_t r[16];
+            tmem_ld_32x32b_x16(tmem_O + lane_addr + (uint32_t)(c * 16), r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+            tmem_st_32x32b_x16(tmem_O + lane_addr + (uint32_t)(c * 16), r);
+          }
+          tmem_st_wait();
+        }
+        l *= alpha;
+        m_ref = m_new;
+      }
+      for (int c = 0; c < kv_chunks; ++c) {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(tmem_S + lane_addr + (uint32_t)(c * 16), r);
+        tmem_ld_wait();
+        float pv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float e = ex2f(__uint_as_float(r[i]) * p.scale_log2 - m_ref);
+          pv[i] = (c * 16 + i < kv_valid) ? e : 0.f;
+          l += pv[i];
+        }
+        const uint32_t dst = p_row + (uint32_t)c * ATT_BLOCK_Q * 32u;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (0u ^ flip)), "r"(pack_bf16x2(pv[0], pv[1])),
+                     "r"(pack_bf16x2(pv[2], pv[3])), "r"(pack_bf16x2(pv[4], pv[5])), "r"(pack_bf16x2(pv[6], pv[7]))
+                     : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (16u ^ flip)), "r"(pack_bf16x2(pv[8], pv[9])),
+                     "r"(pack_bf16x2(pv[10], pv[11])), "r"(pack_bf16x2(pv[12], pv[13])), "r"(pack_bf16x2(pv[14], pv[15]))
+                     : "memory");
+      }
+      fence_proxy_async_smem();     // generic-proxy P writes -> visible to the tensor core's async proxy
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    // ---- epilogue: O / l -> bf16 ----
+    mbar_wait(o_done, (uint32_t)(n_tiles - 1) & 1u);
+    tc_fence_after();
+    const float inv_l = 1.0f / l;
+    __nv_bfloat16* orow = p.out + (size_t)b * p.out_batch_stride + (size_t)q_row * p.out_ld + p.out_col0 + head * p.dp;
+    for (int c = 0; c < dchunks; ++c) {
+      uint32_t r[16];
+      tmem_ld_32x32b_x16(tmem_O + lane_addr + (uint32_t)(c * 16), r);
+      tmem_ld_wait();
+      if (q_row < p.Sq) {
+        uint4 a, bq;
+        a.x = pack_bf16x2(__uint_as_float(r[0]) * inv_l, __uint_as_float(r[1]) * inv_l);
+        a.y = pack_bf16x2(__uint_as_float(r[2]) * inv_l, __uint_as_float(r[3]) * inv_l);
+        a.z = pack_bf16x2(__uint_as_float(r[4]) * inv_l, __uint_as_float(r[5]) * inv_l);
+        a.w = pack_bf16x2(__uint_as_float(r[6]) * inv_l, __uint_as_float(r[7]) * inv_l);
+        bq.x = pack_bf16x2(__uint_as_float(r[8]) * inv_l, __uint_as_float(r[9]) * inv_l);
+        bq.y = pack_bf16x2(__uint_as_float(r[10]) * inv_l, __uint_as_float(r[11]) * inv_l);
+        bq.z = pack_bf16x2(__uint_as_float(r[12]) * inv_l, __uint_as_float(r[13]) * inv_l);
+        bq.w = pack_bf16x2(__uint_as_float(r[14]) * inv_l, __uint_as_float(r[15]) * inv_l);
+        *reinterpret_cast<uint4*>(orow + c * 16) = a;
+        *reinterpret_cast<uint4*>(orow + c * 16 + 8) = bq;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+}  // namespace dfb
+
+using namespace dfb;
+
+extern "C" int dfb_attention(const dfb_attn_params* a, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DFB_REQUIRE(a && a->q && a->k && a->v && a->out, "dfb_attention: null buffer");
+  DFB_REQUIRE(a->B > 0 && a->heads > 0 && a->Sq > 0 && a->Skv > 0, "dfb_attention: empty problem");
+  DFB_REQUIRE(a->dp % 16 == 0 && a->dp >= 16 && a->dp <= 256, "dfb_attention: padded head dim must be a multiple of 16 in [16,256]");
+  DFB_REQUIRE(a->q_ld % 8 == 0 && a->k_ld % 8 == 0 && a->v_ld % 8 == 0 && a->out_ld % 8 == 0, "dfb_attention: row pitches must be multiples of 8");
+  DFB_REQUIRE(a->q_col0 % 8 == 0 && a->k_col0 % 8 == 0 && a->v_col0 % 8 == 0 && a->out_col0 % 8 == 0, "dfb_attention: column offsets must be multiples of 8");
+  DFB_REQUIRE(((uintptr_t)a->q | (uintptr_t)a->k | (uintptr_t)a->v | (uintptr_t)a->out) % 16 == 0, "dfb_attention: buffers must be 16B aligned");
+
+  AttnKernelParams kp;
+  memset(&kp, 0, sizeof(kp));
+  int bkv = a->block_kv;
+  if (bkv <= 0) {
+    const int skv16 = (a->Skv + 15) / 16 * 16;
+    const int pref = a->dp <= 48 ? 128 : 64;
+    bkv = skv16 < pref ? skv16 : pref;
+    if (skv16 <= 128 && a->dp <= 80 && skv16 > pref) bkv = skv16;   // short KV (cross-attention): one tile
+  }
+  DFB_REQUIRE(bkv % 16 == 0 && bkv >= 16 && bkv <= 128, "dfb_attention: block_kv must be a multiple of 16 in [16,128]");
+  kp.Sq = a->Sq; kp.Skv = a->Skv; kp.dp = a->dp; kp.block_kv = bkv;
+  kp.n_kv_tiles = (a->Skv + bkv - 1) / bkv;
+  kp.q_col0 = a->q_col0; kp.k_col0 = a->k_col0; kp.v_col0 = a->v_col0;
+  kp.scale_log2 = a->scale * 1.4426950408889634f;
+  kp.out = (__nv_bfloat16*)a->out;
+  kp.out_ld = a->out_ld; kp.out_col0 = a->out_col0;
+  kp.out_batch_stride = (long long)a->Sq * a->out_ld;
+  uint32_t need_cols = (uint32_t)(bkv + a->dp), cols = 32;
+  while (cols < need_cols) cols <<= 1;
+  DFB_REQUIRE(cols <= 512, "dfb_attention: block_kv + dp exceeds TMEM");
+  kp.tmem_cols = cols;
+  kp.v_lbo = a->dbg_v_lbo > 0 ? (uint32_t)a->dbg_v_lbo : (uint32_t)bkv * 32u;
+  kp.v_sbo = a->dbg_v_sbo > 0 ? (uint32_t)a->dbg_v_sbo : 256u;
+
+  AttnMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  {
+    uint64_t dims[3] = {(uint64_t)a->q_ld, (uint64_t)a->Sq, (uint64_t)a->B};
+    uint64_t str[2] = {(uint64_t)a->q_ld * 2, (uint64_t)a->q_ld * 2 * a->Sq};
+    uint32_t box[3] = {16, ATT_BLOCK_Q, 1};
+    int rc = make_tmap(&maps.q, a->q, 2, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_32B);
+    if (rc != DFB_OK) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)a->k_ld, (uint64_t)a->Skv, (uint64_t)a->B};
+    uint64_t str[2] = {(uint64_t)a->k_ld * 2, (uint64_t)a->k_ld * 2 * a->Skv};
+    uint32_t box[3] = {16, (uint32_t)bkv, 1};
+    int rc = make_tmap(&maps.k, a->k, 2, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_32B);
+    if (rc != DFB_OK) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)a->v_ld, (uint64_t)a->Skv, (uint64_t)a->B};
+    uint64_t str[2] = {(uint64_t)a->v_ld * 2, (uint64_t)a->v_ld * 2 * a->Skv};
+    uint32_t box[3] = {16, (uint32_t)bkv, 1};
+    int rc = make_tmap(&maps.v, a->v, 2, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_32B);
+    if (rc != DFB_OK) return rc;
+  }
+
+  const int dch = a->dp / 16;
+  const size_t smem = 1024 + (size_t)dch * ATT_BLOCK_Q * 32 + (size_t)(bkv / 16) * ATT_BLOCK_Q * 32 +
+                      (size_t)ATT_STAGES * 2 * dch * bkv * 32 + 128;
+  DFB_REQUIRE(smem <= 227 * 1024, "dfb_attention: tile configuration exceeds shared memory");
+  static size_t max_set[64] = {0};
+  int dev = 0;
+  DFB_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && smem > max_set[dev]) {
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+    max_set[dev] = 227 * 1024;
+  }
+  dim3 grid((a->Sq + ATT_BLOCK_Q - 1) / ATT_BLOCK_Q, a->heads, a->B);
+  attn_fwd_kernel<<<grid, ATT_THREADS, smem, stream>>>(maps, kp);
+  DFB_CHECK_CUDA(cudaGetLastError());
+  return DFB_OK;
+}

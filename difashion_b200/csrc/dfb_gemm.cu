@@ -46,7 +46,7 @@ struct GemmKernelParams {
   const void* residual;
   int res_ld, res_fp32;
   void* out;
-  int out_ld, out_fp32, geglu, vec_ok;
+  int out_ld, out_fp32, geglu, vec_ok, act;
 };
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -196,6 +196,18 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (j < nvalid) v[j] += __ldg(rb + n0 + j);
+        }
+        if (p.act) {
+          if (p.act == DFB_ACT_SILU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+          } else if (p.act == DFB_ACT_LEAKY_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.01f * v[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+          }
         }
         if (p.geglu) {
           // columns [0,16) = values, [16,32) = gates of output columns n0/2 .. n0/2+15
@@ -411,6 +423,7 @@ extern "C" int dfb_gemm(const dfb_gemm_params* q, void* stream_) {
   kp.out_ld = q->out_ld;
   kp.out_fp32 = q->out_dtype == DFB_DTYPE_F32;
   kp.geglu = q->geglu ? 1 : 0;
+  kp.act = q->act;
   if (kp.geglu) DFB_REQUIRE(q->N % 32 == 0 && q->residual == nullptr, "dfb_gemm: GEGLU needs N % 32 == 0 and no residual");
   const int out_elem = kp.out_fp32 ? 4 : 2;
   bool vec_ok = ((reinterpret_cast<uintptr_t>(q->out) & 15) == 0) && (((size_t)q->out_ld * out_elem) % 16 == 0);

@@ -82,7 +82,7 @@ def gemm(a: Sequence[torch.Tensor], w: torch.Tensor, n: int, *, out: torch.Tenso
          a_c: Optional[Sequence[int]] = None, conv_geom: Optional[Tuple[int, int, int]] = None,
          bias: Optional[torch.Tensor] = None, rowbias: Optional[torch.Tensor] = None,
          rows_per_batch: int = 1, residual: Optional[torch.Tensor] = None, geglu: bool = False,
-         block_n: int = 0) -> torch.Tensor:
+         block_n: int = 0, act: int = 0) -> torch.Tensor:
     """``out = epilogue(A @ w.T)`` on tcgen05 tensor cores (see ``dfb_gemm`` in include/dfb200.h).
 
     a:    1 or 2 bf16 operands; each ``[M, C]`` (plain) or ``[B, H, W, C]`` (conv), last dim
@@ -124,6 +124,170 @@ def gemm(a: Sequence[torch.Tensor], w: torch.Tensor, n: int, *, out: torch.Tenso
     assert out.stride(-1) == 1
     p.out, p.out_ld, p.out_dtype = out.data_ptr(), out.stride(-2), _dt(out)
     p.geglu = 1 if geglu else 0
+    p.act = act
     p.block_n = block_n
     check(_lib.load().dfb_gemm(C.byref(p), _stream()), "dfb_gemm")
+    return out
+
+
+ACT_NONE, ACT_SILU, ACT_LEAKY_RELU, ACT_TANH = 0, 1, 2, 3
+
+
+# ----------------------------------------------------------------------------------------------
+# attention
+# ----------------------------------------------------------------------------------------------
+def pad16(d: int) -> int:
+    return (d + 15) // 16 * 16
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, heads: int, dp: int,
+              scale: float, q_col0: int = 0, k_col0: int = 0, v_col0: int = 0, out_col0: int = 0,
+              block_kv: int = 0, dbg_v_lbo: int = 0, dbg_v_sbo: int = 0) -> torch.Tensor:
+    """softmax(Q K^T * scale) V per (batch, head); q/k/v/out are bf16 ``[B, S, ld]`` views whose head
+    ``h`` lives in columns ``[col0 + h*dp, col0 + (h+1)*dp)`` (``dp`` = head dim padded to 16)."""
+    from ._lib import AttnParams
+    p = AttnParams()
+    for t in (q, k, v, out):
+        assert t.dtype == torch.bfloat16 and t.is_cuda and t.dim() == 3 and t.stride(-1) == 1
+        assert t.stride(0) == t.shape[1] * t.stride(1), "batch stride must be S * row pitch"
+    p.q, p.k, p.v, p.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+    p.q_ld, p.k_ld, p.v_ld, p.out_ld = q.stride(1), k.stride(1), v.stride(1), out.stride(1)
+    p.q_col0, p.k_col0, p.v_col0, p.out_col0 = q_col0, k_col0, v_col0, out_col0
+    p.B, p.heads, p.Sq, p.Skv, p.dp = q.shape[0], heads, q.shape[1], k.shape[1], dp
+    p.scale = scale
+    p.block_kv = block_kv
+    p.dbg_v_lbo, p.dbg_v_sbo = dbg_v_lbo, dbg_v_sbo
+    check(_lib.load().dfb_attention(C.byref(p), _stream()), "dfb_attention")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# norms
+# ----------------------------------------------------------------------------------------------
+def groupnorm(src0: torch.Tensor, src1: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor, *,
+              groups: int, eps: float, silu: bool, stats_ws: torch.Tensor, out: torch.Tensor,
+              raw_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """GroupNorm(+SiLU) over the channel-concat of fp32 NHWC sources ``[B, H, W, C]`` -> bf16 ``out``."""
+    b = src0.shape[0]
+    hw = src0.shape[1] * src0.shape[2] if src0.dim() == 4 else src0.shape[1]
+    c0 = src0.shape[-1]
+    c1 = 0 if src1 is None else src1.shape[-1]
+    assert src0.dtype == torch.float32 and out.dtype == torch.bfloat16
+    assert stats_ws.dtype == torch.float32 and stats_ws.numel() >= b * groups * 2
+    check(_lib.load().dfb_groupnorm(
+        src0.data_ptr(), c0, src0.stride(-2), _ptr(src1), c1, 0 if src1 is None else src1.stride(-2), b, hw,
+        groups, eps, gamma.data_ptr(), beta.data_ptr(), 1 if silu else 0, stats_ws.data_ptr(), out.data_ptr(),
+        out.stride(-2), _ptr(raw_out), 0 if raw_out is None else raw_out.stride(-2), _stream()), "dfb_groupnorm")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: torch.Tensor, eps: float = 1e-5):
+    """LayerNorm over the last dim of fp32 ``[rows, C]`` -> bf16 ``out``."""
+    rows = x.numel() // x.shape[-1]
+    assert x.dtype == torch.float32 and out.dtype == torch.bfloat16
+    check(_lib.load().dfb_layernorm(x.data_ptr(), x.stride(-2), gamma.data_ptr(), beta.data_ptr(), eps,
+                                    out.data_ptr(), out.stride(-2), rows, x.shape[-1], _stream()), "dfb_layernorm")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# streaming kernels
+# ----------------------------------------------------------------------------------------------
+def cfg_step(eps: torch.Tensor, weights: Sequence[float], x_src: torch.Tensor, cx: float, ck: Sequence[float],
+             hist: Sequence[Optional[torch.Tensor]] = (None, None, None), noise: Optional[torch.Tensor] = None,
+             cn: float = 0.0, x_out: Optional[torch.Tensor] = None, eps_out: Optional[torch.Tensor] = None):
+    """Fused CFG combine + scheduler update.  eps: fp32 NHWC ``[nb*N, H, W, 4]``; x: fp32 NCHW."""
+    nb = len(weights)
+    n_items, hw = x_src.shape[0], x_src.shape[2] * x_src.shape[3]
+    assert eps.dtype == torch.float32 and eps.is_contiguous() and eps.numel() == nb * n_items * hw * 4
+    assert x_src.dtype == torch.float32 and x_src.is_contiguous() and x_src.shape[1] == 4
+    if x_out is None:
+        x_out = torch.empty_like(x_src)
+    w = (C.c_float * nb)(*[float(v) for v in weights])
+    ckk = (C.c_float * 4)(*[float(v) for v in (list(ck) + [0.0] * 4)[:4]])
+    h = list(hist) + [None] * 3
+    check(_lib.load().dfb_cfg_step(eps.data_ptr(), nb, w, x_src.data_ptr(), float(cx), ckk, _ptr(h[0]), _ptr(h[1]),
+                                   _ptr(h[2]), _ptr(noise), float(cn), x_out.data_ptr(), _ptr(eps_out), n_items, hw,
+                                   _stream()), "dfb_cfg_step")
+    return x_out
+
+
+def mutual_gather_sum(all_latents: Optional[torch.Tensor], prev_latents: torch.Tensor, idx: torch.Tensor,
+                      out: torch.Tensor):
+    n_items, n_src = idx.shape
+    d = prev_latents[0].numel()
+    assert idx.dtype == torch.int32 and idx.is_contiguous() and out.dtype == torch.bfloat16
+    check(_lib.load().dfb_mutual_gather_sum(_ptr(all_latents), prev_latents.data_ptr(), idx.data_ptr(), n_items,
+                                            n_src, d, out.data_ptr(), _stream()), "dfb_mutual_gather_sum")
+    return out
+
+
+def mutual_blend(x: torch.Tensor, m: Optional[torch.Tensor], hist: Optional[torch.Tensor], null_latent: torch.Tensor,
+                 eta: float, use_m: Sequence[int], use_h: Sequence[int], out: torch.Tensor):
+    nb = len(use_m)
+    n_items, hw = x.shape[0], x.shape[2] * x.shape[3]
+    um = (C.c_int32 * nb)(*[int(v) for v in use_m])
+    uh = (C.c_int32 * nb)(*[int(v) for v in use_h])
+    assert out.dtype == torch.bfloat16 and out.numel() == nb * n_items * hw * 8
+    check(_lib.load().dfb_mutual_blend(x.data_ptr(), _ptr(m), _ptr(hist), null_latent.data_ptr(), float(eta), nb, um,
+                                       uh, n_items, hw, out.data_ptr(), _stream()), "dfb_mutual_blend")
+    return out
+
+
+def nchw_to_nhwc_bf16(x: torch.Tensor, out: torch.Tensor):
+    b, c, h, w = x.shape
+    assert x.is_contiguous()
+    check(_lib.load().dfb_nchw_to_nhwc_bf16(x.data_ptr(), _dt(x), out.data_ptr(), b, c, h * w, _stream()),
+          "dfb_nchw_to_nhwc_bf16")
+    return out
+
+
+def nhwc_to_nchw(x: torch.Tensor, out: torch.Tensor):
+    b, c, h, w = out.shape
+    assert x.dtype == torch.float32 and x.is_contiguous() and out.is_contiguous()
+    check(_lib.load().dfb_nhwc_to_nchw(x.data_ptr(), out.data_ptr(), _dt(out), b, c, h * w, _stream()),
+          "dfb_nhwc_to_nchw")
+    return out
+
+
+def pad_cast_rows(x: torch.Tensor, out: torch.Tensor):
+    b, s, d = x.shape
+    assert x.is_contiguous() and out.is_contiguous() and out.dtype == torch.bfloat16
+    check(_lib.load().dfb_pad_cast_rows(x.data_ptr(), _dt(x), out.data_ptr(), b, s, out.shape[1], d, _stream()),
+          "dfb_pad_cast_rows")
+    return out
+
+
+def upsample2x(x: torch.Tensor, out: torch.Tensor):
+    b, h, w, c = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous() and out.dtype == torch.bfloat16 and out.is_contiguous()
+    check(_lib.load().dfb_upsample2x(x.data_ptr(), out.data_ptr(), b, h, w, c, _stream()), "dfb_upsample2x")
+    return out
+
+
+def space_to_depth(x: torch.Tensor, out: torch.Tensor):
+    b, h, w, c = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous() and out.dtype == torch.bfloat16 and out.is_contiguous()
+    check(_lib.load().dfb_space_to_depth(x.data_ptr(), out.data_ptr(), b, h, w, c, _stream()), "dfb_space_to_depth")
+    return out
+
+
+def s2d_taps(c: int) -> Tuple[Tuple[int, int, int], ...]:
+    """Tap table of a stride-2, pad-1 3x3 conv expressed over the space-to-depth planes (kh-major,
+    matching ``pack_conv3x3``): input row 2*ho + kh - 1 -> (plane parity, shift)."""
+    par = {0: (1, -1), 1: (0, 0), 2: (1, 0)}
+    taps = []
+    for kh in range(3):
+        ph, dh = par[kh]
+        for kw in range(3):
+            pw, dw = par[kw]
+            taps.append((dh, dw, (ph * 2 + pw) * c))
+    return tuple(taps)
+
+
+def timestep_embedding(t: torch.Tensor, out: torch.Tensor, flip_sin_to_cos: bool = True, freq_shift: float = 0.0):
+    assert t.dtype == torch.float32 and t.is_contiguous() and out.dtype == torch.bfloat16 and out.is_contiguous()
+    check(_lib.load().dfb_timestep_embedding(t.data_ptr(), out.data_ptr(), t.shape[0], out.shape[1],
+                                             1 if flip_sin_to_cos else 0, float(freq_shift), _stream()),
+          "dfb_timestep_embedding")
     return out

@@ -1,0 +1,581 @@
+"""``B200UNet2DConditionModel`` — drop-in for diffusers 0.18.2 ``UNet2DConditionModel`` on the DiFashion
+denoising path (reference call site ``DiFashion/models/difashion.py:518-523``; model surgery
+``:82-93``; attributes consumed are listed in SURVEY.md §8b).
+
+* Same module tree / state-dict key names as diffusers: the sub-modules are plain
+  ``nn.Conv2d`` / ``nn.Linear`` / ``nn.GroupNorm`` / ``nn.LayerNorm`` used ONLY as parameter containers
+  (their ``forward`` is never called) so ``load_state_dict`` of a diffusers checkpoint works and
+  ``unet.conv_in = nn.Conv2d(8, 320, ...)`` (DiFashion's 4->8 channel widening) is honoured.
+* ``forward`` has diffusers' signature and runs entirely on the hand-written sm_100a kernels of
+  ``libdfb200.so``: NHWC activations, bf16 tensor-core operands, fp32 residual stream / norm
+  statistics / softmax.  No PyTorch arithmetic, no CPU fallback.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Any, Dict, List, Optional, Tuple, Union
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .attention import Attention, AttnPack, B200AttnProcessor
+from .config import SD15_UNET_CONFIG, FrozenConfig
+
+
+@dataclass
+class UNet2DConditionOutput:
+    sample: torch.Tensor
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter containers (diffusers names)
+# ------------------------------------------------------------------------------------------------
+class TimestepEmbedding(nn.Module):
+    def __init__(self, in_dim, dim):
+        super().__init__()
+        self.linear_1 = nn.Linear(in_dim, dim)
+        self.linear_2 = nn.Linear(dim, dim)
+
+
+class ResnetBlock2D(nn.Module):
+    def __init__(self, cin, cout, temb_dim, groups, eps):
+        super().__init__()
+        self.in_channels, self.out_channels = cin, cout
+        self.norm1 = nn.GroupNorm(groups, cin, eps=eps)
+        self.conv1 = nn.Conv2d(cin, cout, 3, padding=1)
+        self.time_emb_proj = nn.Linear(temb_dim, cout)
+        self.norm2 = nn.GroupNorm(groups, cout, eps=eps)
+        self.conv2 = nn.Conv2d(cout, cout, 3, padding=1)
+        self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
+
+
+class GEGLU(nn.Module):
+    def __init__(self, dim, inner):
+        super().__init__()
+        self.proj = nn.Linear(dim, inner * 2)
+
+
+class FeedForward(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.net = nn.ModuleList([GEGLU(dim, dim * 4), nn.Dropout(0.0), nn.Linear(dim * 4, dim)])
+
+
+class BasicTransformerBlock(nn.Module):
+    def __init__(self, dim, heads, dim_head, cross_dim):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim)
+        self.attn1 = Attention(dim, None, heads, dim_head)
+        self.norm2 = nn.LayerNorm(dim)
+        self.attn2 = Attention(dim, cross_dim, heads, dim_head)
+        self.norm3 = nn.LayerNorm(dim)
+        self.ff = FeedForward(dim)
+
+
+class Transformer2DModel(nn.Module):
+    def __init__(self, channels, heads, cross_dim, groups, use_linear_projection):
+        super().__init__()
+        self.channels = channels
+        self.use_linear_projection = use_linear_projection
+        self.norm = nn.GroupNorm(groups, channels, eps=1e-6)
+        if use_linear_projection:
+            self.proj_in, self.proj_out = nn.Linear(channels, channels), nn.Linear(channels, channels)
+        else:
+            self.proj_in, self.proj_out = nn.Conv2d(channels, channels, 1), nn.Conv2d(channels, channels, 1)
+        self.transformer_blocks = nn.ModuleList([BasicTransformerBlock(channels, heads, channels // heads, cross_dim)])
+
+
+class Downsample2D(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.conv = nn.Conv2d(c, c, 3, stride=2, padding=1)
+
+
+class Upsample2D(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.conv = nn.Conv2d(c, c, 3, padding=1)
+
+
+class _Block(nn.Module):
+    """resnets (+attentions) (+downsamplers | upsamplers): CrossAttnDownBlock2D / DownBlock2D /
+    UNetMidBlock2DCrossAttn / UpBlock2D / CrossAttnUpBlock2D all reduce to this container."""
+
+    def __init__(self, resnets, attentions=None, downsamplers=None, upsamplers=None):
+        super().__init__()
+        self.resnets = nn.ModuleList(resnets)
+        if attentions is not None:
+            self.attentions = nn.ModuleList(attentions)
+        if downsamplers is not None:
+            self.downsamplers = nn.ModuleList(downsamplers)
+        if upsamplers is not None:
+            self.upsamplers = nn.ModuleList(upsamplers)
+
+
+class Workspace:
+    """Caller-owned device scratch, keyed by role tag; sized to the largest request per tag."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs: Dict[Tuple[str, torch.dtype], torch.Tensor] = {}
+
+    def get(self, tag: str, shape, dtype) -> torch.Tensor:
+        n = 1
+        for s in shape:
+            n *= int(s)
+        key = (tag, dtype)
+        buf = self.bufs.get(key)
+        if buf is None or buf.numel() < n:
+            buf = torch.empty(max(n, 1), dtype=dtype, device=self.device)
+            self.bufs[key] = buf
+        return buf[:n].view(*shape)
+
+    def nbytes(self) -> int:
+        return sum(b.numel() * b.element_size() for b in self.bufs.values())
+
+
+def _f32(t, device):
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# the model
+# ------------------------------------------------------------------------------------------------
+class B200UNet2DConditionModel(nn.Module):
+    _supports_gradient_checkpointing = True
+
+    def __init__(self, **config):
+        super().__init__()
+        cfg = dict(SD15_UNET_CONFIG)
+        cfg.update(config)
+        self._config = FrozenConfig(cfg)
+        boc = tuple(cfg["block_out_channels"])
+        groups, eps = cfg["norm_num_groups"], cfg["norm_eps"]
+        temb_dim = boc[0] * 4
+        xdim, lin = cfg["cross_attention_dim"], cfg["use_linear_projection"]
+        ahd = cfg["attention_head_dim"]
+        heads = (lambda i: ahd[i]) if isinstance(ahd, (list, tuple)) else (lambda i: ahd)
+        nl = cfg["layers_per_block"]
+
+        self.conv_in = nn.Conv2d(cfg["in_channels"], boc[0], 3, padding=1)
+        self.time_embedding = TimestepEmbedding(boc[0], temb_dim)
+
+        downs, cin = [], boc[0]
+        for i, c in enumerate(boc):
+            res = [ResnetBlock2D(cin if j == 0 else c, c, temb_dim, groups, eps) for j in range(nl)]
+            att = ([Transformer2DModel(c, heads(i), xdim, groups, lin) for _ in range(nl)]
+                   if cfg["down_block_types"][i] == "CrossAttnDownBlock2D" else None)
+            ds = [Downsample2D(c)] if i < len(boc) - 1 else None
+            downs.append(_Block(res, att, downsamplers=ds))
+            cin = c
+        self.down_blocks = nn.ModuleList(downs)
+
+        c = boc[-1]
+        self.mid_block = _Block([ResnetBlock2D(c, c, temb_dim, groups, eps) for _ in range(2)],
+                                [Transformer2DModel(c, heads(len(boc) - 1), xdim, groups, lin)])
+
+        rev = list(reversed(boc))
+        ups = []
+        for i, out_c in enumerate(rev):
+            prev_c, in_c = rev[max(i - 1, 0)], rev[min(i + 1, len(rev) - 1)]
+            res = []
+            for j in range(nl + 1):
+                skip_c = in_c if j == nl else out_c
+                rin = prev_c if j == 0 else out_c
+                res.append(ResnetBlock2D(rin + skip_c, out_c, temb_dim, groups, eps))
+            att = ([Transformer2DModel(out_c, heads(len(boc) - 1 - i), xdim, groups, lin) for _ in range(nl + 1)]
+                   if cfg["up_block_types"][i] == "CrossAttnUpBlock2D" else None)
+            us = [Upsample2D(out_c)] if i < len(rev) - 1 else None
+            ups.append(_Block(res, att, upsamplers=us))
+        self.up_blocks = nn.ModuleList(ups)
+
+        self.conv_norm_out = nn.GroupNorm(groups, boc[0], eps=eps)
+        self.conv_out = nn.Conv2d(boc[0], cfg["out_channels"], 3, padding=1)
+
+        for p in self.parameters():
+            p.requires_grad_(False)
+        self._pack: Optional[Dict[str, Any]] = None
+        self._pack_key = None
+        self._ws: Dict[Any, Workspace] = {}
+        self._kv_cache: Dict[str, Any] = {}
+
+    # ---------------------------------------------------------------- diffusers-style surface
+    @property
+    def config(self) -> FrozenConfig:
+        return self._config
+
+    def register_to_config(self, **kw):
+        d = dict(self._config)
+        d.update(kw)
+        self._config = FrozenConfig(d)
+
+    @property
+    def dtype(self):
+        return next(self.parameters()).dtype
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    @property
+    def attn_processors(self) -> Dict[str, Any]:
+        return {f"{name}.processor": m.processor for name, m in self.named_modules() if isinstance(m, Attention)}
+
+    def set_attn_processor(self, processor):
+        mods = {f"{name}.processor": m for name, m in self.named_modules() if isinstance(m, Attention)}
+        if isinstance(processor, dict):
+            if len(processor) != len(mods):
+                raise ValueError(f"A dict of processors was passed, but the number of processors {len(processor)} does "
+                                 f"not match the number of attention layers: {len(mods)}.")
+            for k, m in mods.items():
+                m.set_processor(processor[k])
+        else:
+            for m in mods.values():
+                m.set_processor(processor)
+
+    def set_default_attn_processor(self):
+        self.set_attn_processor(B200AttnProcessor())
+
+    def enable_xformers_memory_efficient_attention(self, attention_op=None):
+        """No-op: attention already runs on the fused tcgen05 flash kernel (difashion.py:118)."""
+
+    def disable_xformers_memory_efficient_attention(self):
+        """No-op."""
+
+    def enable_gradient_checkpointing(self):
+        """Accepted for API compatibility (inf4eval.py:587); inference-only module."""
+
+    def save_pretrained(self, save_directory: str, **kw):
+        import json
+        import os
+        os.makedirs(save_directory, exist_ok=True)
+        cfg = dict(self._config)
+        cfg["_class_name"] = "UNet2DConditionModel"
+        with open(os.path.join(save_directory, "config.json"), "w") as f:
+            json.dump(cfg, f, indent=2)
+        torch.save(self.state_dict(), os.path.join(save_directory, "diffusion_pytorch_model.bin"))
+
+    @classmethod
+    def from_pretrained(cls, path: str, subfolder: Optional[str] = None, **kw):
+        import json
+        import os
+        d = os.path.join(path, subfolder) if subfolder else path
+        with open(os.path.join(d, "config.json")) as f:
+            cfg = {k: v for k, v in json.load(f).items() if not k.startswith("_")}
+        known = set(SD15_UNET_CONFIG.keys())
+        m = cls(**{k: (tuple(v) if isinstance(v, list) else v) for k, v in cfg.items() if k in known})
+        m.load_state_dict(torch.load(os.path.join(d, "diffusion_pytorch_model.bin"), map_location="cpu"))
+        return m
+
+    @classmethod
+    def from_diffusers(cls, unet_or_state_dict, config: Optional[dict] = None):
+        """Build from a diffusers ``UNet2DConditionModel`` instance (or its state dict + config)."""
+        if isinstance(unet_or_state_dict, dict):
+            sd, cfg = unet_or_state_dict, dict(config or {})
+        else:
+            sd, cfg = unet_or_state_dict.state_dict(), dict(unet_or_state_dict.config)
+        known = set(SD15_UNET_CONFIG.keys())
+        cfg = {k: (tuple(v) if isinstance(v, list) else v) for k, v in cfg.items() if k in known}
+        cfg["in_channels"] = sd["conv_in.weight"].shape[1]
+        m = cls(**cfg)
+        m.load_state_dict(sd)
+        return m
+
+    # ---------------------------------------------------------------- weight packing
+    def _weights_key(self):
+        return (id(self.conv_in), tuple((p.data_ptr(), p._version) for p in self.parameters()))
+
+    def pack(self, device=None, force: bool = False):
+        """Pre-pack all weights into the kernels' bf16 K-major layouts (once; re-done when weights change)."""
+        device = torch.device(device) if device is not None else self.device
+        if device.type != "cuda":
+            raise RuntimeError("B200UNet2DConditionModel needs a CUDA device: there is no CPU fallback")
+        key = (str(device), self._weights_key())
+        if not force and self._pack is not None and self._pack_key == key:
+            return self._pack
+        P: Dict[str, Any] = {}
+        te = self.time_embedding
+        P["t1"] = (ops.pack_linear(te.linear_1.weight.to(device)), _f32(te.linear_1.bias, device))
+        P["t2"] = (ops.pack_linear(te.linear_2.weight.to(device)), _f32(te.linear_2.bias, device))
+        tp_w, tp_b, off = [], [], 0
+
+        def pack_resnet(rb: ResnetBlock2D):
+            nonlocal off
+            d = dict(cin=rb.conv1.weight.shape[1], cout=rb.conv1.weight.shape[0], temb_off=off)
+            tp_w.append(rb.time_emb_proj.weight.detach().to(device).float())
+            tp_b.append(rb.time_emb_proj.bias.detach().to(device).float())
+            off += d["cout"]
+            d["n1"] = (_f32(rb.norm1.weight, device), _f32(rb.norm1.bias, device), rb.norm1.eps, rb.norm1.num_groups)
+            d["n2"] = (_f32(rb.norm2.weight, device), _f32(rb.norm2.bias, device), rb.norm2.eps, rb.norm2.num_groups)
+            d["w1"], d["b1"] = ops.pack_conv3x3(rb.conv1.weight.to(device)), _f32(rb.conv1.bias, device)
+            w2, b2 = ops.pack_conv3x3(rb.conv2.weight.to(device)), _f32(rb.conv2.bias, device)
+            if rb.conv_shortcut is not None:
+                w2 = torch.cat([w2, ops.pack_linear(rb.conv_shortcut.weight.to(device))], dim=1).contiguous()
+                b2 = (b2 + _f32(rb.conv_shortcut.bias, device)).contiguous()
+                d["shortcut"] = True
+            else:
+                d["shortcut"] = False
+            d["w2"], d["b2"] = w2, b2
+            return d
+
+        def pack_transformer(tr: Transformer2DModel):
+            blk = tr.transformer_blocks[0]
+            d = dict(c=tr.norm.num_channels)
+            d["gn"] = (_f32(tr.norm.weight, device), _f32(tr.norm.bias, device), tr.norm.eps, tr.norm.num_groups)
+            d["pin"] = (ops.pack_linear(tr.proj_in.weight.to(device)), _f32(tr.proj_in.bias, device))
+            d["pout"] = (ops.pack_linear(tr.proj_out.weight.to(device)), _f32(tr.proj_out.bias, device))
+            for i, ln in enumerate((blk.norm1, blk.norm2, blk.norm3), 1):
+                d[f"ln{i}"] = (_f32(ln.weight, device), _f32(ln.bias, device), ln.eps)
+            d["a1"], d["a2"] = AttnPack(blk.attn1, device), AttnPack(blk.attn2, device)
+            d["attn1"], d["attn2"] = blk.attn1, blk.attn2
+            d["geglu"] = ops.pack_geglu(blk.ff.net[0].proj.weight.to(device), blk.ff.net[0].proj.bias.to(device))
+            d["ffo"] = (ops.pack_linear(blk.ff.net[2].weight.to(device)), _f32(blk.ff.net[2].bias, device))
+            return d
+
+        def pack_block(b: _Block):
+            d = dict(resnets=[pack_resnet(r) for r in b.resnets])
+            d["attentions"] = [pack_transformer(t) for t in b.attentions] if hasattr(b, "attentions") else None
+            for nm in ("downsamplers", "upsamplers"):
+                if hasattr(b, nm):
+                    conv = getattr(b, nm)[0].conv
+                    d[nm] = (ops.pack_conv3x3(conv.weight.to(device)), _f32(conv.bias, device), conv.weight.shape[0])
+                else:
+                    d[nm] = None
+            return d
+
+        P["conv_in"] = (ops.pack_conv3x3(self.conv_in.weight.to(device)), _f32(self.conv_in.bias, device))
+        P["down"] = [pack_block(b) for b in self.down_blocks]
+        P["mid"] = pack_block(self.mid_block)
+        P["up"] = [pack_block(b) for b in self.up_blocks]
+        P["norm_out"] = (_f32(self.conv_norm_out.weight, device), _f32(self.conv_norm_out.bias, device),
+                         self.conv_norm_out.eps, self.conv_norm_out.num_groups)
+        P["conv_out"] = (ops.pack_conv3x3(self.conv_out.weight.to(device)), _f32(self.conv_out.bias, device))
+        P["tproj"] = (ops.pack_linear(torch.cat(tp_w, 0)), torch.cat(tp_b, 0).contiguous(), off)
+        P["device"] = device
+        self._pack, self._pack_key = P, key
+        self._kv_cache = {}
+        return P
+
+    # ---------------------------------------------------------------- kernels sequencing
+    def _resnet(self, pk, srcs: List[torch.Tensor], temb_all, ws: Workspace, out_tag: str):
+        x0 = srcs[0]
+        x1 = srcs[1] if len(srcs) > 1 else None
+        B, H, W = x0.shape[0], x0.shape[1], x0.shape[2]
+        cin, cout = pk["cin"], pk["cout"]
+        g, b, eps, groups = pk["n1"]
+        stats = ws.get("gn_stats", (B * groups * 2,), torch.float32)
+        xn = ws.get("xn", (B, H, W, cin), torch.bfloat16)
+        xraw = ws.get("xraw", (B, H, W, cin), torch.bfloat16) if pk["shortcut"] else None
+        ops.groupnorm(x0, x1, g, b, groups=groups, eps=eps, silu=True, stats_ws=stats, out=xn, raw_out=xraw)
+        h1 = ws.get("h1", (B, H, W, cout), torch.float32)
+        ops.gemm([xn], pk["w1"], cout, out=h1, taps=[ops.TAPS_3X3], conv_geom=(B, H, W), bias=pk["b1"],
+                 rowbias=temb_all[:, pk["temb_off"]:pk["temb_off"] + cout], rows_per_batch=H * W)
+        g, b, eps, groups = pk["n2"]
+        hn = ws.get("hn", (B, H, W, cout), torch.bfloat16)
+        ops.groupnorm(h1, None, g, b, groups=groups, eps=eps, silu=True, stats_ws=stats, out=hn)
+        out = ws.get(out_tag, (B, H, W, cout), torch.float32)
+        if pk["shortcut"]:
+            ops.gemm([hn, xraw], pk["w2"], cout, out=out, taps=[ops.TAPS_3X3, ops.TAP_CENTER], conv_geom=(B, H, W),
+                     bias=pk["b2"])
+        else:
+            ops.gemm([hn], pk["w2"], cout, out=out, taps=[ops.TAPS_3X3], conv_geom=(B, H, W), bias=pk["b2"], residual=x0)
+        return out
+
+    def _cross_kv(self, pk_attn: AttnPack, name: str, ctx_bf16: torch.Tensor, ws: Workspace):
+        """K/V of the text tokens are step-invariant: projected once per distinct context tensor."""
+        ent = self._kv_cache.get(name)
+        key = self._ctx_key
+        if ent is not None and ent[0] == key:
+            return ent[1]
+        b, skv, dctx = ctx_bf16.shape
+        kv = torch.empty(b, skv, 2 * pk_attn.cp, dtype=torch.bfloat16, device=ctx_bf16.device)
+        ops.gemm([ctx_bf16.view(b * skv, dctx)], pk_attn.w_kv, 2 * pk_attn.cp, out=kv.view(b * skv, 2 * pk_attn.cp))
+        self._kv_cache[name] = (key, kv)
+        return kv
+
+    def _transformer(self, pk, name: str, x: torch.Tensor, ctx_bf16, ws: Workspace, out_tag: str):
+        B, H, W, C = x.shape
+        S, M = H * W, B * H * W
+        g, b, eps, groups = pk["gn"]
+        stats = ws.get("gn_stats", (B * groups * 2,), torch.float32)
+        xn = ws.get("xn", (M, C), torch.bfloat16)
+        ops.groupnorm(x, None, g, b, groups=groups, eps=eps, silu=False, stats_ws=stats, out=xn.view(B, H, W, C))
+        h = ws.get("tr_h", (M, C), torch.float32)
+        ops.gemm([xn], pk["pin"][0], C, out=h, bias=pk["pin"][1])
+        ln = ws.get("ln", (M, C), torch.bfloat16)
+        a1, a2 = pk["a1"], pk["a2"]
+        fast = isinstance(pk["attn1"].processor, B200AttnProcessor) and isinstance(pk["attn2"].processor, B200AttnProcessor)
+
+        # --- self-attention
+        g, b, eps = pk["ln1"]
+        ops.layernorm(h, g, b, ln, eps)
+        if fast:
+            qkv = ws.get("qkv", (B, S, 3 * a1.cp), torch.bfloat16)
+            ops.gemm([ln], a1.w_qkv, 3 * a1.cp, out=qkv.view(M, 3 * a1.cp))
+            att = ws.get("att", (B, S, a1.cp), torch.bfloat16)
+            ops.attention(qkv[..., :a1.cp], qkv[..., a1.cp:2 * a1.cp], qkv[..., 2 * a1.cp:], att, heads=a1.heads,
+                          dp=a1.dp, scale=a1.scale)
+            ops.gemm([att.view(M, a1.cp)], a1.w_o, C, out=h, bias=a1.b_o, residual=h)
+        else:
+            h.add_(pk["attn1"].processor(pk["attn1"], ln.view(B, S, C)).reshape(M, C).float())
+        # --- cross-attention over the (category prompt [+ history]) tokens
+        g, b, eps = pk["ln2"]
+        ops.layernorm(h, g, b, ln, eps)
+        if fast:
+            q = ws.get("q", (B, S, a2.cp), torch.bfloat16)
+            ops.gemm([ln], a2.w_q, a2.cp, out=q.view(M, a2.cp))
+            kv = self._cross_kv(a2, name, ctx_bf16, ws)
+            att = ws.get("att", (B, S, a2.cp), torch.bfloat16)
+            ops.attention(q, kv[..., :a2.cp], kv[..., a2.cp:], att, heads=a2.heads, dp=a2.dp, scale=a2.scale)
+            ops.gemm([att.view(M, a2.cp)], a2.w_o, C, out=h, bias=a2.b_o, residual=h)
+        else:
+            h.add_(pk["attn2"].processor(pk["attn2"], ln.view(B, S, C), encoder_hidden_states=ctx_bf16).reshape(M, C).float())
+        # --- GEGLU feed-forward
+        g, b, eps = pk["ln3"]
+        ops.layernorm(h, g, b, ln, eps)
+        ff = ws.get("ff", (M, 4 * C), torch.bfloat16)
+        ops.gemm([ln], pk["geglu"][0], 8 * C, out=ff, bias=pk["geglu"][1], geglu=True)
+        hb = ws.get("tr_hb", (M, C), torch.bfloat16)
+        ops.gemm([ff], pk["ffo"][0], C, out=hb, bias=pk["ffo"][1], residual=h)
+        out = ws.get(out_tag, (B, H, W, C), torch.float32)
+        ops.gemm([hb], pk["pout"][0], C, out=out.view(M, C), bias=pk["pout"][1], residual=x.view(M, C))
+        return out
+
+    def _temb(self, P, t_dev: torch.Tensor, ws: Workspace):
+        B = t_dev.shape[0]
+        c0 = self.config.block_out_channels[0]
+        te = ws.get("t_sin", (B, c0), torch.bfloat16)
+        ops.timestep_embedding(t_dev, te, bool(self.config.flip_sin_to_cos), float(self.config.freq_shift))
+        e1 = ws.get("t_e1", (B, c0 * 4), torch.bfloat16)
+        ops.gemm([te], P["t1"][0], c0 * 4, out=e1, bias=P["t1"][1], act=ops.ACT_SILU)
+        # every consumer applies SiLU to emb first (ResnetBlock2D: time_emb_proj(silu(temb))) -> fuse it here
+        e2 = ws.get("t_e2", (B, c0 * 4), torch.bfloat16)
+        ops.gemm([e1], P["t2"][0], c0 * 4, out=e2, bias=P["t2"][1], act=ops.ACT_SILU)
+        ntot = P["tproj"][2]
+        temb_all = ws.get("temb_all", (B, ntot), torch.float32)
+        ops.gemm([e2], P["tproj"][0], ntot, out=temb_all, bias=P["tproj"][1])
+        return temb_all
+
+    def forward_nhwc(self, x_in: torch.Tensor, t_dev: torch.Tensor, ctx_bf16: torch.Tensor, ws: Workspace,
+                     taps: Optional[dict] = None) -> torch.Tensor:
+        """x_in: bf16 NHWC [B,H,W,in_channels]; t_dev: fp32 [B]; ctx: bf16 [B,S_kv,D].  Returns the
+        fp32 NHWC noise prediction [B,H,W,out_channels] (a workspace buffer)."""
+        P = self.pack(x_in.device)
+        B, H, W, cin = x_in.shape
+        temb_all = self._temb(P, t_dev, ws)
+        c0 = self.config.block_out_channels[0]
+        h = ws.get("skip0", (B, H, W, c0), torch.float32)
+        ops.gemm([x_in], P["conv_in"][0], c0, out=h, taps=[ops.TAPS_3X3], conv_geom=(B, H, W), bias=P["conv_in"][1])
+        if taps is not None:
+            taps["conv_in"] = h.clone()
+        skips, ns = [h], 1
+        for i, bp in enumerate(P["down"]):
+            for j, rp in enumerate(bp["resnets"]):
+                has_att = bp["attentions"] is not None
+                r = self._resnet(rp, [h], temb_all, ws, "rtmp" if has_att else f"skip{ns}")
+                h = self._transformer(bp["attentions"][j], f"down{i}.{j}", r, ctx_bf16, ws, f"skip{ns}") if has_att else r
+                skips.append(h)
+                ns += 1
+            if bp["downsamplers"] is not None:
+                w, b, c = bp["downsamplers"]
+                Bh, Hh, Wh = h.shape[0], h.shape[1], h.shape[2]
+                s2d = ws.get("s2d", (Bh, Hh // 2, Wh // 2, 4 * c), torch.bfloat16)
+                ops.space_to_depth(h, s2d)
+                h = ws.get(f"skip{ns}", (Bh, Hh // 2, Wh // 2, c), torch.float32)
+                ops.gemm([s2d], w, c, out=h, taps=[ops.s2d_taps(c)], a_c=[c], conv_geom=(Bh, Hh // 2, Wh // 2), bias=b)
+                skips.append(h)
+                ns += 1
+            if taps is not None:
+                taps[f"down{i}"] = h.clone()
+        mp = P["mid"]
+        r = self._resnet(mp["resnets"][0], [h], temb_all, ws, "mid_r0")
+        a = self._transformer(mp["attentions"][0], "mid", r, ctx_bf16, ws, "mid_a")
+        h = self._resnet(mp["resnets"][1], [a], temb_all, ws, "mid_r1")
+        if taps is not None:
+            taps["mid"] = h.clone()
+        par = 0
+        for i, bp in enumerate(P["up"]):
+            for j, rp in enumerate(bp["resnets"]):
+                skip = skips.pop()
+                par ^= 1
+                r = self._resnet(rp, [h, skip], temb_all, ws, f"up_r{par}")
+                h = (self._transformer(bp["attentions"][j], f"up{i}.{j}", r, ctx_bf16, ws, f"up_a{par}")
+                     if bp["attentions"] is not None else r)
+            if bp["upsamplers"] is not None:
+                w, b, c = bp["upsamplers"]
+                Bh, Hh, Wh = h.shape[0], h.shape[1], h.shape[2]
+                up = ws.get("upx", (Bh, 2 * Hh, 2 * Wh, c), torch.bfloat16)
+                ops.upsample2x(h, up)
+                h = ws.get("up_conv", (Bh, 2 * Hh, 2 * Wh, c), torch.float32)
+                ops.gemm([up], w, c, out=h, taps=[ops.TAPS_3X3], conv_geom=(Bh, 2 * Hh, 2 * Wh), bias=b)
+            if taps is not None:
+                taps[f"up{i}"] = h.clone()
+        g, b, eps, groups = P["norm_out"]
+        stats = ws.get("gn_stats", (B * groups * 2,), torch.float32)
+        xn = ws.get("xn", (B, H, W, c0), torch.bfloat16)
+        ops.groupnorm(h, None, g, b, groups=groups, eps=eps, silu=True, stats_ws=stats, out=xn)
+        cout = self.config.out_channels
+        eps_out = ws.get("eps_out", (B, H, W, cout), torch.float32)
+        ops.gemm([xn], P["conv_out"][0], cout, out=eps_out, taps=[ops.TAPS_3X3], conv_geom=(B, H, W), bias=P["conv_out"][1])
+        return eps_out
+
+    def workspace(self, key, device) -> Workspace:
+        ws = self._ws.get(key)
+        if ws is None or ws.device != device:
+            ws = Workspace(device)
+            self._ws[key] = ws
+        return ws
+
+    def set_context(self, encoder_hidden_states: torch.Tensor) -> torch.Tensor:
+        """Register the cross-attention context; its K/V projections are cached until it changes."""
+        key = (encoder_hidden_states.data_ptr(), encoder_hidden_states._version, tuple(encoder_hidden_states.shape),
+               encoder_hidden_states.dtype)
+        if getattr(self, "_ctx_key", None) != key or getattr(self, "_ctx_bf16", None) is None:
+            self._ctx_key = key
+            self._ctx_bf16 = encoder_hidden_states.detach().to(torch.bfloat16).contiguous()
+            self._kv_cache = {}
+        return self._ctx_bf16
+
+    @torch.no_grad()
+    def forward(self, sample: torch.Tensor, timestep: Union[torch.Tensor, float, int],
+                encoder_hidden_states: torch.Tensor, class_labels=None, timestep_cond=None, attention_mask=None,
+                cross_attention_kwargs=None, added_cond_kwargs=None, down_block_additional_residuals=None,
+                mid_block_additional_residual=None, encoder_attention_mask=None, return_dict: bool = True):
+        for nm, v in (("class_labels", class_labels), ("timestep_cond", timestep_cond), ("attention_mask", attention_mask),
+                      ("cross_attention_kwargs", cross_attention_kwargs), ("added_cond_kwargs", added_cond_kwargs),
+                      ("down_block_additional_residuals", down_block_additional_residuals),
+                      ("mid_block_additional_residual", mid_block_additional_residual),
+                      ("encoder_attention_mask", encoder_attention_mask)):
+            if v is not None:
+                raise NotImplementedError(f"B200UNet2DConditionModel.forward: `{nm}` is not used on the DiFashion path")
+        if not sample.is_cuda:
+            raise RuntimeError("B200UNet2DConditionModel needs CUDA tensors: there is no CPU fallback")
+        B, C, H, W = sample.shape
+        if C != self.conv_in.weight.shape[1]:
+            raise ValueError(f"sample has {C} channels, conv_in expects {self.conv_in.weight.shape[1]}")
+        n_down = len(self.config.block_out_channels) - 1
+        if H % (1 << n_down) or W % (1 << n_down):
+            raise ValueError("sample height/width must be divisible by 2**(num down blocks - 1)")
+        dev = sample.device
+        ws = self.workspace(("fwd", B, H, W), dev)
+        # timestep -> fp32 [B] on device (python number / 0-d tensor / [B] tensor, as in diffusers)
+        t = timestep
+        if not torch.is_tensor(t):
+            t = torch.tensor([float(t)], dtype=torch.float32, device=dev)
+        t = t.to(device=dev, dtype=torch.float32).reshape(-1)
+        t_dev = ws.get("t_in", (B,), torch.float32)
+        t_dev.copy_(t.expand(B))
+        x_in = ws.get("x_in", (B, H, W, C), torch.bfloat16)
+        smp = sample if sample.dtype in (torch.float32, torch.bfloat16) else sample.float()
+        ops.nchw_to_nhwc_bf16(smp.contiguous(), x_in)
+        ctx = self.set_context(encoder_hidden_states)
+        eps = self.forward_nhwc(x_in, t_dev, ctx, ws)
+        out_dtype = sample.dtype if sample.dtype in (torch.float32, torch.bfloat16) else torch.float32
+        out = torch.empty(B, self.config.out_channels, H, W, dtype=out_dtype, device=dev)
+        ops.nhwc_to_nchw(eps, out)
+        if out.dtype != sample.dtype:
+            out = out.to(sample.dtype)
+        if not return_dict:
+            return (out,)
+        return UNet2DConditionOutput(sample=out)

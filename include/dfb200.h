@@ -30,6 +30,11 @@ extern "C" {
 #define DFB_DTYPE_BF16 0
 #define DFB_DTYPE_F32 1
 
+#define DFB_ACT_NONE 0
+#define DFB_ACT_SILU 1
+#define DFB_ACT_LEAKY_RELU 2 /* slope 0.01 (nn.LeakyReLU default, MutualEncoder) */
+#define DFB_ACT_TANH 3
+
 const char* dfb_strerror(int rc);
 const char* dfb_last_error(void);
 int dfb_abi_version(void);
@@ -80,10 +85,82 @@ typedef struct dfb_gemm_params {
   int32_t out_ld;
   int32_t out_dtype;     /* DFB_DTYPE_*                                                    */
   int32_t geglu;         /* 1: columns come in (16 value | 16 gate) groups; N_out = N / 2  */
+  int32_t act;           /* DFB_ACT_* applied after bias/rowbias, before the residual      */
   int32_t block_n;       /* N tile (multiple of 32, <= 256); 0 = choose automatically      */
 } dfb_gemm_params;
 
 int dfb_gemm(const dfb_gemm_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Flash attention forward (tcgen05 QK^T and PV, online softmax, TMA-fed).
+ *
+ * Replaces: the attention processor call `attn.processor(attn, hidden_states,
+ * encoder_hidden_states)` of every diffusers Attention layer (attn1 self / attn2 cross) in
+ * UNet2DConditionModel.forward — xformers.memory_efficient_attention in the reference
+ * (DiFashion/models/difashion.py:109-118) — softmax(Q K^T * scale) V per (batch, head).
+ *
+ * q: bf16 [B, Sq, q_ld], k: [B, Skv, k_ld], v: [B, Skv, v_ld], out: [B, Sq, out_ld]; head h
+ * occupies columns [col0 + h*dp, col0 + (h+1)*dp) of its operand, dp = head dim padded to a
+ * multiple of 16 with zero columns.  Skv needs no padding in memory (TMA zero-fills, the
+ * kernel masks columns >= Skv).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct dfb_attn_params {
+  const void* q; const void* k; const void* v; void* out;
+  int32_t q_ld, k_ld, v_ld, out_ld;
+  int32_t q_col0, k_col0, v_col0, out_col0;
+  int32_t B, heads, Sq, Skv, dp;
+  float scale;            /* softmax scale (true head_dim ** -0.5)                          */
+  int32_t block_kv;       /* KV tile (multiple of 16, <= 128); 0 = automatic                */
+  int32_t dbg_v_lbo, dbg_v_sbo; /* 0 = default; test hooks for the V descriptor strides     */
+} dfb_attn_params;
+
+int dfb_attention(const dfb_attn_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Norm kernels producing bf16 GEMM operands from the fp32 residual stream (NHWC).
+ * dfb_groupnorm replaces nn.GroupNorm(32, C)(+SiLU) of ResnetBlock2D.norm1/norm2,
+ * Transformer2DModel.norm and conv_norm_out; reads the up-block skip concat from its two sources
+ * (torch.cat([h, skip], 1) is never materialised); optional raw bf16 copy of the input (the A
+ * operand of conv_shortcut).  stats_ws: fp32 [B, groups, 2] scratch.
+ * dfb_layernorm replaces BasicTransformerBlock.norm1/2/3.
+ * ------------------------------------------------------------------------------------------ */
+int dfb_groupnorm(const float* src0, int c0, int ld0, const float* src1, int c1, int ld1, int B, int hw,
+                  int groups, float eps, const float* gamma, const float* beta, int silu, float* stats_ws,
+                  void* out_bf16, int ld_out, void* raw_out_bf16, int ld_raw, void* stream);
+int dfb_layernorm(const float* x, int ld_x, const float* gamma, const float* beta, float eps, void* out_bf16,
+                  int ld_out, int rows, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * HBM-streaming kernels of the loop body (DiFashion/models/difashion.py:456-577).
+ * ------------------------------------------------------------------------------------------ */
+/* CFG combine (difashion.py:525-566) fused with the scheduler update (:569; diffusers
+ * DDIMScheduler.step / PNDMScheduler.step_plms):
+ *   e0 = sum_b w[b] * eps[b]   (eps: fp32 NHWC [nb*N, hw, 4], branch-major)
+ *   x_out = cx*x_src + ck[0]*e0 + ck[1]*hist1 + ck[2]*hist2 + ck[3]*hist3 + cn*noise   (fp32 NCHW [N,4,hw])
+ *   eps_out (optional) = e0.   w: host float[nb]; ck: host float[4].                           */
+int dfb_cfg_step(const float* eps, int nb, const float* w, const float* x_src, float cx, const float* ck,
+                 const float* hist1, const float* hist2, const float* hist3, const float* noise, float cn,
+                 float* x_out, float* eps_out, int n_items, int hw, void* stream);
+/* Mutual-condition neighbour sum (difashion.py:475-488): out[n] = sum_s src(idx[n, s]); idx >= 0 ->
+ * all_latents row, idx < 0 -> prev_latents row (-idx-1), INT32_MIN -> skip.  out bf16 [N, d]. */
+int dfb_mutual_gather_sum(const float* all_latents, const float* prev_latents, const int32_t* idx, int n_items,
+                          int n_src, int d, void* out_bf16, void* stream);
+/* Mutual blend + history concat + CFG branch expansion (difashion.py:458-459, :494-515, :388-390):
+ * writes the UNet input NHWC bf16 [nb*N, hw, 8].  use_m / use_h: host int32[nb].              */
+int dfb_mutual_blend(const float* x, const float* m, const float* hist, const float* null_latent, float eta,
+                     int nb, const int32_t* use_m, const int32_t* use_h, int n_items, int hw, void* out_bf16,
+                     void* stream);
+/* Layout conversions at the diffusers API boundary (NCHW tensors in, NHWC inside). */
+int dfb_nchw_to_nhwc_bf16(const void* in, int in_dtype, void* out_bf16, int B, int C, int HW, void* stream);
+int dfb_nhwc_to_nchw(const float* in, void* out, int out_dtype, int B, int C, int HW, void* stream);
+int dfb_pad_cast_rows(const void* in, int in_dtype, void* out_bf16, int B, int S, int S_pad, int D, void* stream);
+/* Upsample2D nearest-2x (fp32 NHWC -> bf16 NHWC) and the space-to-depth feeding Downsample2D's
+ * stride-2 conv (fp32 NHWC [B,H,W,C] -> bf16 [B,H/2,W/2,4C]). */
+int dfb_upsample2x(const float* in, void* out_bf16, int B, int H, int W, int C, void* stream);
+int dfb_space_to_depth(const float* in, void* out_bf16, int B, int H, int W, int C, void* stream);
+/* diffusers Timesteps (get_timestep_embedding): t fp32 [B] -> bf16 [B, dim] = [cos | sin]. */
+int dfb_timestep_embedding(const float* t, void* out_bf16, int B, int dim, int flip_sin_to_cos, float freq_shift,
+                           void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,72 @@
+"""GPU parity of the tcgen05 flash-attention kernel vs plain softmax(QK^T*scale)V in fp64 on the same
+bf16 operands.  Tolerance rel-L2 <= 1e-2 (P and the output are rounded to bf16; measured ~3e-3)."""
+import pytest
+import torch
+
+from tests.util import err_report, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(q, k, v, heads, d, scale):
+    b, sq, _ = q.shape
+    skv = k.shape[1]
+    qh = q.double().reshape(b, sq, heads, d).permute(0, 2, 1, 3)
+    kh = k.double().reshape(b, skv, heads, d).permute(0, 2, 1, 3)
+    vh = v.double().reshape(b, skv, heads, d).permute(0, 2, 1, 3)
+    w = torch.softmax(qh @ kh.transpose(-1, -2) * scale, dim=-1)
+    return (w @ vh).permute(0, 2, 1, 3).reshape(b, sq, heads * d)
+
+
+def _pad_heads(x, heads, d, dp):
+    b, s, _ = x.shape
+    out = torch.zeros(b, s, heads, dp, dtype=x.dtype, device=x.device)
+    out[..., :d] = x.reshape(b, s, heads, d)
+    return out.reshape(b, s, heads * dp)
+
+
+CASES = [
+    (2, 8, 4096, 4096, 40), (2, 8, 1024, 1024, 80), (2, 8, 256, 256, 160), (3, 8, 64, 64, 160),
+    (2, 8, 4096, 77, 40), (2, 8, 1024, 77, 80), (2, 8, 256, 77, 160), (2, 8, 64, 85, 160),
+    (2, 2, 16, 16, 32), (3, 2, 4, 4, 64), (3, 2, 256, 77, 32), (1, 1, 200, 300, 16),
+]
+
+
+@pytest.mark.parametrize("B,H,Sq,Skv,d", CASES)
+def test_attention(B, H, Sq, Skv, d):
+    from difashion_b200 import ops
+    g = torch.Generator().manual_seed(Sq * 7 + Skv + d)
+    q = torch.randn(B, Sq, H * d, generator=g).bfloat16().cuda()
+    k = torch.randn(B, Skv, H * d, generator=g).bfloat16().cuda()
+    v = torch.randn(B, Skv, H * d, generator=g).bfloat16().cuda()
+    dp = ops.pad16(d)
+    scale = d ** -0.5
+    qp, kp, vp = (_pad_heads(t, H, d, dp).contiguous() for t in (q, k, v))
+    out = torch.full((B, Sq, H * dp), float("nan"), dtype=torch.bfloat16, device="cuda")
+    ops.attention(qp, kp, vp, out, heads=H, dp=dp, scale=scale)
+    torch.cuda.synchronize()
+    got = out.reshape(B, Sq, H, dp)[..., :d].reshape(B, Sq, H * d)
+    ref = _ref(q, k, v, H, d, scale)
+    assert rel_l2(got, ref) < 1e-2, err_report(got.reshape(-1, H * d), ref.reshape(-1, H * d), f"attn {B},{H},{Sq},{Skv},{d}")
+
+
+def test_attention_fused_qkv_layout_and_large_logits():
+    """q/k/v as column slices of one [B,S,3*H*dp] buffer (the fused projection output); logits scaled
+    up so the online-softmax rescale path (running max grows across KV tiles) is exercised."""
+    from difashion_b200 import ops
+    B, H, S, d = 2, 8, 1024, 40
+    dp = ops.pad16(d)
+    g = torch.Generator().manual_seed(5)
+    q = (torch.randn(B, S, H * d, generator=g) * 3).bfloat16().cuda()
+    k = (torch.randn(B, S, H * d, generator=g) * 3).bfloat16().cuda()
+    k[:, S // 2:] *= 2.0                       # later KV tiles carry larger logits
+    v = torch.randn(B, S, H * d, generator=g).bfloat16().cuda()
+    qkv = torch.cat([_pad_heads(t, H, d, dp) for t in (q, k, v)], dim=-1).contiguous()
+    C = H * dp
+    out = torch.zeros(B, S, C, dtype=torch.bfloat16, device="cuda")
+    ops.attention(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], out, heads=H, dp=dp, scale=d ** -0.5,
+                  q_col0=0, k_col0=0, v_col0=0)
+    torch.cuda.synchronize()
+    got = out.reshape(B, S, H, dp)[..., :d].reshape(B, S, H * d)
+    ref = _ref(q, k, v, H, d, d ** -0.5)
+    assert rel_l2(got, ref) < 1e-2, err_report(got.reshape(-1, H * d), ref.reshape(-1, H * d), "attn fused")
