@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""Benchmark of the DiFashion conditional denoising step on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--outfits O]
+
+metric : outfits/sec for GOR generation = 4 items x 512 px (4x64x64 latents) x 50-step DDIM x 4-branch CFG.
+step   : one denoising step (mutual gather + MutualEncoder MLP + blend + SD-1.5-shaped UNet over
+         4 branches + fused CFG/DDIM update) for the rank's batch of O outfits (O=16 -> 256 UNet rows).
+value  : whole-job outfits/s = N * O * (K / 50) / t_K, inputs resident in HBM, t_K device-timed (CUDA events),
+         max over ranks.  Outfits are sharded whole across ranks; there is no collective inside the loop.
+e2e    : the same metric through B200DiFashionPipeline.generate() with PINNED HOST inputs and a pinned host
+         output: H2D of latents/prompts/history, text K/V projection, 50 steps, (N>1: NCCL all_gather of the
+         finished latents,) D2H — one full generation per rank.
+roofline: tensor-bound.  `achieved` = algorithmic FLOPs of the tcgen05 GEMM/conv kernel launches of one step
+         (rows x 677.31 GFLOP: F_row 803.37 minus the attention core 126.06) / their summed
+         CUDA-event durations, vs the measured sustained bf16 peak of MEASURED_PEAKS.json.
+cpu_baseline / --impl reference: the CPU oracle (PyTorch fp32 restatement of the reference path; the
+         reference itself needs diffusers, absent here) timed on the box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+F_ROW = 803.37e9            # FLOPs per UNet batch row, S_kv = 77
+F_ROW_ATTN_CORE = 126.06e9  # QK^T + PV of attn1 + attn2
+DDIM_STEPS = 50
+ROWS_PER_OUTFIT = 16        # 4 items x 4 CFG branches
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=d.get("hbm_gbs", 6650.0), burst=d.get("bf16_tflops", 1590.0),
+                    sustained=d.get("bf16_tflops_sustained", 1400.0), src="measured")
+    return dict(hbm=6650.0, burst=1590.0, sustained=1400.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons of one GPU via NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                     "hw_power_brake_slowdown": 0x80, "sw_power_cap": 0x4}
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+                time.sleep(0.05)
+        except Exception as e:  # NVML missing: record that instead of failing the bench
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def synthetic_inputs(n_outfits: int, s_kv: int = 77, seed: int = 123, pin: bool = True):
+    """GOR inputs per SURVEY §8d: every slot is generated; CPU-generated from fixed seeds."""
+    g = torch.Generator().manual_seed(seed)
+    n = n_outfits * 4
+    mk = lambda *shape, scale=1.0: (torch.randn(*shape, generator=g) * scale)
+    d = dict(
+        olists=torch.zeros(n_outfits, 4, dtype=torch.long),
+        all_latents=None,
+        init_latents=mk(n, 4, 64, 64),
+        category_prompts=mk(n, s_kv, 768),
+        null_prompt=mk(1, s_kv, 768),
+        hist_latents=mk(n, 4, 64, 64, scale=0.9),
+        null_latent=mk(4, 64, 64, scale=0.9),
+    )
+    if pin and torch.cuda.is_available():
+        d = {k: (v.pin_memory() if torch.is_tensor(v) and k != "olists" else v) for k, v in d.items()}
+    return d
+
+
+def cpu_oracle_sample(rows: int, threads: int):
+    """Time `rows` UNet rows of one denoising step with the fp32 CPU oracle (all host threads)."""
+    from oracle.unet_oracle import make_oracle_unet
+    torch.set_num_threads(threads)
+    unet = make_oracle_unet(seed=0)
+    g = torch.Generator().manual_seed(123)
+    x = torch.randn(rows, 8, 64, 64, generator=g)
+    ctx = torch.randn(rows, 77, 768, generator=g)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        unet(x, torch.tensor(981), ctx)
+        dt = time.perf_counter() - t0
+    return dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference path's CPU implementation (oracle port) on the host cores."""
+    if rank != 0:
+        return
+    from oracle.generation_oracle import make_oracle_mutual_encoder, oracle_generation
+    from oracle.schedulers_oracle import OracleDDIMScheduler
+    from oracle.unet_oracle import make_oracle_unet
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    unet = make_oracle_unet(seed=0)
+    me = make_oracle_mutual_encoder(seed=1)
+    total_steps = args.steps + args.warmup
+    # bounded sample: one FITB outfit with one blank (4 CFG rows per step) when few steps are asked,
+    # else a single-branch row (guidance scales 1.0 -> 1 UNet row per step)
+    few = total_steps <= 8
+    g = torch.Generator().manual_seed(123)
+    olists = torch.tensor([[11, 0, 7, 9]])
+    inp = dict(olists=olists, all_latents=0.9 * torch.randn(4, 4, 64, 64, generator=g),
+               category_prompts=torch.randn(1, 77, 768, generator=g), null_prompt=torch.randn(1, 77, 768, generator=g),
+               hist_latents=0.9 * torch.randn(1, 4, 64, 64, generator=g), null_latent=0.9 * torch.randn(4, 64, 64, generator=g),
+               init_latents=torch.randn(1, 4, 64, 64, generator=g))
+    scales = dict(category_guidance_scale=12.0, hist_guidance_scale=4.0, mutual_guidance_scale=5.0) if few else \
+        dict(category_guidance_scale=1.0, hist_guidance_scale=1.0, mutual_guidance_scale=1.0)
+    rows_per_step = 4 if few else 1
+    rec = []
+    sched = OracleDDIMScheduler()
+    t_marks = []
+
+    class _Timed:
+        def __call__(self, *a, **k):
+            out = unet(*a, **k)
+            t_marks.append(time.perf_counter())
+            return out
+
+    t_start = time.perf_counter()
+    oracle_generation(_Timed(), me, sched, **inp, num_inference_steps=DDIM_STEPS, max_steps=total_steps, **scales)
+    marks = [t_start] + t_marks
+    dt = marks[-1] - marks[args.warmup]
+    ms_per_step = dt / args.steps * 1e3
+    # a GOR outfit costs 16 rows x 50 steps
+    value = (rows_per_step / ROWS_PER_OUTFIT) * args.steps / DDIM_STEPS / dt
+    line = {
+        "impl": "reference", "metric": "outfits/sec (4x512px, 50-step DDIM+CFG)", "value": value, "unit": "outfits/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "GOR generation, 50-step DDIM + 4-branch CFG, SD-1.5-shaped UNet (in_channels 8), "
+                               "random-init weights; CPU sample extrapolated per UNet row"},
+        "cpu_baseline": {"value": value, "unit": "outfits/s", "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} denoising steps x {rows_per_step} UNet row(s) of one FITB outfit "
+                                   f"(oracle fp32 port of the diffusers path; the reference itself needs diffusers, "
+                                   f"not installable here); outfits/s = rows/16 per step over 50 steps"},
+        "e2e": {"value": value, "unit": "outfits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=DDIM_STEPS)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--outfits", type=int, default=16, help="outfits per GPU (16 -> 256 UNet rows: BASELINE configs[1])")
+    ap.add_argument("--skv", type=int, default=77, help="text tokens (85 = 77 + 8 history tokens, configs[3])")
+    ap.add_argument("--max-rows", type=int, default=256, help="UNet rows per micro-batch")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile-step", action="store_true", help="print per-kernel-kind time of one eager step")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from difashion_b200 import ops
+    from difashion_b200.mutual import MutualEncoder
+    from difashion_b200.pipeline import B200DiFashionPipeline
+    from difashion_b200.schedulers import B200DDIMScheduler
+    from difashion_b200.unet import B200UNet2DConditionModel
+
+    torch.manual_seed(0)                       # identical random-init weights on every rank (weight replica per GPU)
+    unet = B200UNet2DConditionModel()
+    me = MutualEncoder()
+    unet.pack(dev)
+    pipe = B200DiFashionPipeline(unet, me, B200DDIMScheduler(), eta_mutual=0.1, max_rows=args.max_rows)
+    # weak scaling: every rank owns `outfits` whole outfits (distinct seeds = distinct outfits)
+    inp = synthetic_inputs(args.outfits, args.skv, seed=123 + rank)
+    rows = args.outfits * ROWS_PER_OUTFIT
+
+    # ---------------- device-resident throughput (value) ----------------
+    st = pipe.begin(**inp, num_inference_steps=DDIM_STEPS, device=dev)
+    ts = st.timesteps
+    for w in range(args.warmup):
+        pipe.step(st, ts[w % len(ts)])
+    torch.cuda.synchronize()
+    launches_per_step = pipe.last_step_launches
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        pipe.step(st, ts[(args.warmup + k) % len(ts)])
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    t_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    t_ms = float(t_ms.item())
+    ms_per_step = t_ms / args.steps
+    value = world * args.outfits * (args.steps / DDIM_STEPS) / (t_ms / 1e3)
+    step_tflops = rows * (F_ROW if args.skv == 77 else 804.04e9) / (ms_per_step / 1e3) / 1e12
+
+    # ---------------- dominant-kernel roofline: per-launch CUDA events over one eager step ----------------
+    peaks = _peaks()
+    pipe_eager = B200DiFashionPipeline(unet, me, B200DDIMScheduler(), eta_mutual=0.1, max_rows=args.max_rows,
+                                       use_cuda_graph=False)
+    st2 = pipe_eager.begin(**inp, num_inference_steps=DDIM_STEPS, device=dev)
+    pipe_eager.step(st2, ts[0])
+    torch.cuda.synchronize()
+    ops.PROFILE = []
+    es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    es0.record()
+    pipe_eager.step(st2, ts[1])
+    es1.record()
+    torch.cuda.synchronize()
+    prof, ops.PROFILE = ops.PROFILE, None
+    kinds = {}
+    for kind, flops, shape, a, b in prof:
+        d = kinds.setdefault(kind, [0.0, 0.0, 0])
+        d[0] += a.elapsed_time(b)
+        d[1] += flops
+        d[2] += 1
+    eager_ms = es0.elapsed_time(es1)
+    mma_ms = kinds.get("gemm", [0, 0, 0])[0] + kinds.get("conv", [0, 0, 0])[0]
+    mma_launches = kinds.get("gemm", [0, 0, 0])[2] + kinds.get("conv", [0, 0, 0])[2]
+    gemm_alg_flops = rows * (F_ROW - F_ROW_ATTN_CORE)
+    achieved = gemm_alg_flops / (mma_ms / 1e3) / 1e12 if mma_ms > 0 else 0.0
+    roofline = {
+        "bound": "tensor", "kernel": "gemm_tcgen05_kernel (all conv3x3 / 1x1 / linear launches of one step)",
+        "achieved": achieved, "peak": peaks["sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["sustained"],
+        "traffic": None, "peak_source": f"{peaks['src']} (bf16_tflops_sustained; burst {peaks['burst']})",
+        "launches_per_step": mma_launches, "kernel_ms_per_step": mma_ms, "kernel_share_of_step": mma_ms / eager_ms if eager_ms else None,
+        "attention_ms_per_step": kinds.get("attention", [0, 0, 0])[0],
+        "step_achieved": step_tflops, "step_frac": step_tflops / peaks["sustained"], "step_frac_of_burst": step_tflops / peaks["burst"],
+    }
+    if args.profile_step and rank == 0:
+        for kind, (ms, fl, cnt) in sorted(kinds.items()):
+            print(f"# {kind:10s} launches={cnt:4d} ms={ms:9.3f} executed TFLOP/s={fl / (ms / 1e3) / 1e12 if ms else 0:8.1f}", file=sys.stderr)
+        print(f"# eager step {eager_ms:.3f} ms; graph step {ms_per_step:.3f} ms", file=sys.stderr)
+        big = sorted(prof, key=lambda r: -r[3].elapsed_time(r[4]))[:25]
+        for kind, flops, shape, a, b in big:
+            ms = a.elapsed_time(b)
+            print(f"#   {kind:9s} {str(shape):34s} {ms:8.3f} ms {flops / (ms / 1e3) / 1e12:8.1f} TFLOP/s", file=sys.stderr)
+    del pipe_eager, st2
+
+    # ---------------- end-to-end through the public API with host buffers ----------------
+    e2e = None
+    if not args.no_e2e:
+        n_items = args.outfits * 4
+        out_host = torch.empty(n_items, 4, 64, 64, dtype=torch.float32).pin_memory()
+        gathered = torch.empty(world * n_items, 4, 64, 64, dtype=torch.float32, device=dev) if world > 1 else None
+        h2d = sum(v.numel() * v.element_size() for k, v in inp.items() if torch.is_tensor(v) and k != "olists")
+        d2h = out_host.numel() * 4
+
+        def one_generation():
+            if world > 1:
+                lat = pipe.generate(**inp, num_inference_steps=DDIM_STEPS, device=dev)
+                dist.all_gather_into_tensor(gathered, lat)       # NCCL over NVLink: finished latents only
+                out_host.copy_(gathered[rank * n_items:(rank + 1) * n_items], non_blocking=True)
+            else:
+                pipe.generate(**inp, num_inference_steps=DDIM_STEPS, device=dev, out=out_host)
+            torch.cuda.synchronize()
+
+        one_generation()                                          # warm (graphs already captured above)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        one_generation()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dt = float(dt.item())
+        e2e = {"value": world * args.outfits / dt, "unit": "outfits/s", "h2d_bytes_per_step": h2d // DDIM_STEPS,
+               "d2h_bytes_per_step": d2h // DDIM_STEPS, "h2d_bytes_per_generation": h2d, "d2h_bytes_per_generation": d2h,
+               "seconds_per_generation": dt, "finite": bool(torch.isfinite(out_host).all())}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- CPU baseline (oracle port) on this box's host cores, bounded sample ----------------
+    cpu = None
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sample_rows = 2
+        dt = cpu_oracle_sample(sample_rows, threads)
+        cpu = {"value": sample_rows / ROWS_PER_OUTFIT / DDIM_STEPS / dt, "unit": "outfits/s", "cores": threads, "kind": "port",
+               "sample": f"one fp32 UNet forward over {sample_rows} of the 256 rows of one denoising step ({dt:.2f} s); "
+                         f"outfits/s extrapolated as rows/16/50 (oracle = PyTorch restatement of the diffusers path)"}
+
+    line = {
+        "metric": "outfits/sec (4x512px, 50-step DDIM+CFG)", "value": value, "unit": "outfits/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"GOR generation: 50-step DDIM + 4-branch CFG, {args.outfits} outfits x 4 items per GPU "
+                               f"({rows} UNet rows/step), SD-1.5-shaped UNet (in_channels 8, S_kv {args.skv}), random-init weights",
+                   "outfits_per_gpu": args.outfits, "unet_rows_per_step": rows, "ddim_steps": DDIM_STEPS,
+                   "parallelism": f"outfit-sharded replicas x{world}, no in-loop collective",
+                   "l2": "inputs larger than L2: each step streams 1.7 GB of weights + multi-GB activations (126 MB L2)",
+                   "unet_step_ms": ms_per_step},
+        "clocks": sampler.summary(), "gpu_launches": launches_per_step * args.steps,
+        "launches_per_step": launches_per_step, "roofline": roofline,
+    }
+    if e2e is not None:
+        line["e2e"] = e2e
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -75,12 +75,13 @@ _PROTOTYPES = {
     "dfb_num_sms": (C.c_int, []),
     "dfb_gemm": (C.c_int, [C.POINTER(GemmParams), C.c_void_p]),
     "dfb_attention": (C.c_int, [C.POINTER(AttnParams), C.c_void_p]),
+    "dfb_groupnorm_ws_floats": (C.c_size_t, [C.c_int, C.c_int]),
     "dfb_groupnorm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                 C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "dfb_layernorm": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int,
                                 C.c_int, C.c_int, C.c_void_p]),
-    "dfb_cfg_step": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.c_void_p, C.c_float,
+    "dfb_cfg_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_void_p, C.c_float,
                                C.POINTER(C.c_float), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
                                C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "dfb_mutual_gather_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,

@@ -37,6 +37,7 @@ struct CfgStepParams {
   float* x_out;
   float* eps_out;
   int n_items, hw;
+  int eps_nchw;
 };
 
 __global__ void __launch_bounds__(256) cfg_step_kernel(const CfgStepParams p) {
@@ -52,12 +53,21 @@ __global__ void __launch_bounds__(256) cfg_step_kernel(const CfgStepParams p) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) e[a][c] = 0.f;
     for (int b = 0; b < p.nb; ++b) {
-      const float* src = p.eps + (((size_t)b * p.n_items + n) * p.hw + px) * 4;
       const float wb = p.w[b];
+      if (p.eps_nchw) {
+        const float* src = p.eps + (((size_t)b * p.n_items + n) * 4) * p.hw + px;
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const float4 v = ldg4(src + a * 4);
-        e[a][0] += wb * v.x; e[a][1] += wb * v.y; e[a][2] += wb * v.z; e[a][3] += wb * v.w;
+        for (int c = 0; c < 4; ++c) {
+          const float4 v = ldg4(src + (size_t)c * p.hw);
+          e[0][c] += wb * v.x; e[1][c] += wb * v.y; e[2][c] += wb * v.z; e[3][c] += wb * v.w;
+        }
+      } else {
+        const float* src = p.eps + (((size_t)b * p.n_items + n) * p.hw + px) * 4;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const float4 v = ldg4(src + a * 4);
+          e[a][0] += wb * v.x; e[a][1] += wb * v.y; e[a][2] += wb * v.z; e[a][3] += wb * v.w;
+        }
       }
     }
 #pragma unroll
@@ -278,7 +288,7 @@ using namespace dfb;
 
 extern "C" {
 
-int dfb_cfg_step(const float* eps, int nb, const float* w, const float* x_src, float cx, const float* ck,
+int dfb_cfg_step(const float* eps, int eps_nchw, int nb, const float* w, const float* x_src, float cx, const float* ck,
                  const float* hist1, const float* hist2, const float* hist3, const float* noise, float cn,
                  float* x_out, float* eps_out, int n_items, int hw, void* stream) {
   DFB_REQUIRE(eps && w && x_src && ck && x_out, "dfb_cfg_step: null buffer");
@@ -293,7 +303,7 @@ int dfb_cfg_step(const float* eps, int nb, const float* w, const float* x_src, f
   for (int k = 0; k < 4; ++k) p.ck[k] = ck[k];
   p.hist[0] = hist1; p.hist[1] = hist2; p.hist[2] = hist3;
   p.noise = noise; p.cn = cn; p.x_out = x_out; p.eps_out = eps_out;
-  p.n_items = n_items; p.hw = hw;
+  p.n_items = n_items; p.hw = hw; p.eps_nchw = eps_nchw ? 1 : 0;
   const long long work = (long long)n_items * (hw / 4);
   cfg_step_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>(p);
   DFB_CHECK_CUDA(cudaGetLastError());

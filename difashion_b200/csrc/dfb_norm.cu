@@ -8,54 +8,100 @@
 namespace dfb {
 
 // ---------------------------------------------------------------------------------------------
-// GroupNorm statistics: stats[b][g] = (sum, sumsq) accumulated with fp32 atomics.
-// grid = (pixel chunks, B); each thread owns fixed float4 channel-vectors (coalesced across the
-// warp) and walks the chunk's pixels.  Channels-per-group is even, so a float4 spans <= 2 groups.
+// GroupNorm statistics, deterministic (no atomics, fixed reduction order -> bitwise reproducible):
+//   stage 1: grid = (pixel chunks, B); each thread owns fixed float4 channel-vectors (coalesced
+//            across the warp) and walks its share of the chunk's pixels; per-thread partials go to
+//            shared memory and one thread per group folds them in thread order; the block writes
+//            partial[b][chunk][g] = (sum, sumsq).
+//   stage 2: one warp per (b, g) folds the chunks in order -> stats[b][g] = (mean, rstd).
+// Channels-per-group is even, so a float4 spans <= 2 groups.
 // ---------------------------------------------------------------------------------------------
 constexpr int GN_THREADS = 256;
 constexpr int GN_MAX_VEC_PER_THREAD = 4;   // supports C <= 4096
+constexpr int GN_MAX_CHUNKS = 256;         // partial sums per image (workspace sizing)
 
 __global__ void __launch_bounds__(GN_THREADS)
 groupnorm_stats_kernel(const float* __restrict__ src0, int c0, int ld0, const float* __restrict__ src1, int c1, int ld1,
-                       int hw, int groups, int pix_per_block, float* __restrict__ stats) {
-  __shared__ float s_sum[64], s_sq[64];
+                       int hw, int groups, int pix_per_block, float* __restrict__ partial) {
+  __shared__ float s_part[GN_THREADS * GN_MAX_VEC_PER_THREAD][4];   // (sum_a, sq_a, sum_b, sq_b) per thread-vector
+  __shared__ short s_ga[GN_THREADS * GN_MAX_VEC_PER_THREAD], s_gb[GN_THREADS * GN_MAX_VEC_PER_THREAD];
   const int b = blockIdx.y;
   const int C = c0 + c1;
   const int cg = C / groups;
   const int nvec = C >> 2;
   const int p_begin = blockIdx.x * pix_per_block;
   const int p_end = min(hw, p_begin + pix_per_block);
-  if (threadIdx.x < groups) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
-  __syncthreads();
   // thread -> (channel vector, pixel lane): with few channels several pixel lanes share a block
   const int vlanes = nvec < GN_THREADS ? nvec : GN_THREADS;
   const int plane_cnt = GN_THREADS / vlanes;            // >= 1
   const int tv = threadIdx.x % vlanes;
   const int tp = threadIdx.x / vlanes;
-  for (int v = tv; v < nvec && tp < plane_cnt; v += GN_THREADS) {
-    const int c = v << 2;
-    const float* base;
-    int ld, cc;
-    if (c < c0) { base = src0; ld = ld0; cc = c; } else { base = src1; ld = ld1; cc = c - c0; }
-    base += (size_t)b * hw * ld + cc;
+  int slot = threadIdx.x;
+#pragma unroll
+  for (int it = 0; it < GN_MAX_VEC_PER_THREAD; ++it, slot += GN_THREADS) {
+    const int v = tv + it * GN_THREADS;
     float sa = 0.f, qa = 0.f, sb = 0.f, qb = 0.f;
-    for (int px = p_begin + tp; px < p_end; px += plane_cnt) {
-      const float4 x = __ldg(reinterpret_cast<const float4*>(base + (size_t)px * ld));
-      sa += x.x + x.y; qa += x.x * x.x + x.y * x.y;
-      sb += x.z + x.w; qb += x.z * x.z + x.w * x.w;
+    int ga = -1, gb = -1;
+    if (v < nvec && tp < plane_cnt) {
+      const int c = v << 2;
+      const float* base;
+      int ld, cc;
+      if (c < c0) { base = src0; ld = ld0; cc = c; } else { base = src1; ld = ld1; cc = c - c0; }
+      base += (size_t)b * hw * ld + cc;
+      for (int px = p_begin + tp; px < p_end; px += plane_cnt) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(base + (size_t)px * ld));
+        sa += x.x + x.y; qa += x.x * x.x + x.y * x.y;
+        sb += x.z + x.w; qb += x.z * x.z + x.w * x.w;
+      }
+      ga = c / cg; gb = (c + 2) / cg;
     }
-    const int ga = c / cg, gb = (c + 2) / cg;
-    if (ga == gb) {
-      atomicAdd(&s_sum[ga], sa + sb); atomicAdd(&s_sq[ga], qa + qb);
-    } else {
-      atomicAdd(&s_sum[ga], sa); atomicAdd(&s_sq[ga], qa);
-      atomicAdd(&s_sum[gb], sb); atomicAdd(&s_sq[gb], qb);
-    }
+    s_part[slot][0] = sa; s_part[slot][1] = qa; s_part[slot][2] = sb; s_part[slot][3] = qb;
+    s_ga[slot] = (short)ga; s_gb[slot] = (short)gb;
   }
   __syncthreads();
-  if (threadIdx.x < groups) {
-    atomicAdd(&stats[((size_t)b * groups + threadIdx.x) * 2 + 0], s_sum[threadIdx.x]);
-    atomicAdd(&stats[((size_t)b * groups + threadIdx.x) * 2 + 1], s_sq[threadIdx.x]);
+  // fixed-order fold: warp w handles groups w, w+8, ...; lanes stride the slots, then a shuffle tree
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nslots = GN_THREADS * ((nvec + GN_THREADS - 1) / GN_THREADS);
+  for (int g = warp; g < groups; g += GN_THREADS / 32) {
+    float s = 0.f, q = 0.f;
+    for (int i = lane; i < nslots; i += 32) {
+      if (s_ga[i] == g) { s += s_part[i][0]; q += s_part[i][1]; }
+      if (s_gb[i] == g) { s += s_part[i][2]; q += s_part[i][3]; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (lane == 0) {
+      float* dst = partial + (((size_t)b * gridDim.x + blockIdx.x) * groups + g) * 2;
+      dst[0] = s; dst[1] = q;
+    }
+  }
+}
+
+__global__ void groupnorm_finalize_kernel(const float* __restrict__ partial, int chunks, int groups, int B, float inv_n,
+                                          float eps, float* __restrict__ stats) {
+  // one warp per (b, g)
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int b = w / groups, g = w - b * groups;
+  if (b >= B) return;
+  float s = 0.f, q = 0.f;
+  for (int c = lane; c < chunks; c += 32) {
+    const float* src = partial + (((size_t)b * chunks + c) * groups + g) * 2;
+    s += src[0]; q += src[1];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (lane == 0) {
+    const float mean = s * inv_n;
+    const float var = fmaxf(q * inv_n - mean * mean, 0.f);
+    stats[((size_t)b * groups + g) * 2 + 0] = mean;
+    stats[((size_t)b * groups + g) * 2 + 1] = rsqrtf(var + eps);
   }
 }
 
@@ -69,7 +115,6 @@ groupnorm_apply_kernel(const float* __restrict__ src0, int c0, int ld0, const fl
   const int C = c0 + c1;
   const int cg = C / groups;
   const int nvec = C >> 2;
-  const float inv_n = 1.f / ((float)cg * (float)hw);
   const long long total = (long long)B * hw * nvec;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -85,13 +130,9 @@ groupnorm_apply_kernel(const float* __restrict__ src0, int c0, int ld0, const fl
     const float4 bt = __ldg(reinterpret_cast<const float4*>(beta + c));
     const int ga = c / cg, gb = (c + 2) / cg;
     const float* st = stats + (size_t)b * groups * 2;
-    const float ma = st[ga * 2] * inv_n;
-    const float ra = rsqrtf(fmaxf(st[ga * 2 + 1] * inv_n - ma * ma, 0.f) + eps);
+    const float ma = st[ga * 2], ra = st[ga * 2 + 1];
     float mb = ma, rb = ra;
-    if (gb != ga) {
-      mb = st[gb * 2] * inv_n;
-      rb = rsqrtf(fmaxf(st[gb * 2 + 1] * inv_n - mb * mb, 0.f) + eps);
-    }
+    if (gb != ga) { mb = st[gb * 2]; rb = st[gb * 2 + 1]; }
     float y0 = (x.x - ma) * ra * g.x + bt.x;
     float y1 = (x.y - ma) * ra * g.y + bt.y;
     float y2 = (x.z - mb) * rb * g.z + bt.z;
@@ -165,6 +206,10 @@ using namespace dfb;
 
 extern "C" {
 
+size_t dfb_groupnorm_ws_floats(int B, int groups) {
+  return (size_t)B * groups * 2 * (1 + GN_MAX_CHUNKS);
+}
+
 int dfb_groupnorm(const float* src0, int c0, int ld0, const float* src1, int c1, int ld1, int B, int hw, int groups,
                   float eps, const float* gamma, const float* beta, int silu, float* stats_ws, void* out_bf16, int ld_out,
                   void* raw_out_bf16, int ld_raw, void* stream_) {
@@ -176,20 +221,30 @@ int dfb_groupnorm(const float* src0, int c0, int ld0, const float* src1, int c1,
   DFB_REQUIRE((Cch / groups) % 2 == 0 && c0 % 4 == 0 && c1 % 4 == 0, "dfb_groupnorm: channels/group must be even, sources multiple of 4");
   DFB_REQUIRE(Cch / 4 <= GN_THREADS * GN_MAX_VEC_PER_THREAD, "dfb_groupnorm: too many channels");
   DFB_REQUIRE(ld0 % 4 == 0 && ld1 % 4 == 0 && ld_out % 4 == 0 && ld_raw % 4 == 0, "dfb_groupnorm: pitches must be multiples of 4");
-  DFB_CHECK_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(float) * 2 * groups * B, stream));
-  // enough blocks to fill the machine: ~4 waves of CTAs over (B x pixel chunks)
+  // enough blocks to fill the machine: ~4 waves of CTAs over (B x pixel chunks), <= GN_MAX_CHUNKS per image
   int chunks = (num_sms() * 4 + B - 1) / B;
   if (chunks > hw) chunks = hw;
+  if (chunks > GN_MAX_CHUNKS) chunks = GN_MAX_CHUNKS;
   if (chunks < 1) chunks = 1;
   const int ppb = (hw + chunks - 1) / chunks;
   chunks = (hw + ppb - 1) / ppb;
-  groupnorm_stats_kernel<<<dim3(chunks, B), GN_THREADS, 0, stream>>>(src0, c0, ld0, src1, c1, ld1, hw, groups, ppb, stats_ws);
+  float* stats = stats_ws;                                   // [B, groups, 2] (mean, rstd)
+  float* partial = stats_ws + (size_t)B * groups * 2;        // [B, chunks, groups, 2]
+  groupnorm_stats_kernel<<<dim3(chunks, B), GN_THREADS, 0, stream>>>(src0, c0, ld0, src1, c1, ld1, hw, groups, ppb, partial);
   DFB_CHECK_CUDA(cudaGetLastError());
+  {
+    const int warps = B * groups;
+    const int threads = 128;
+    const int blocks = (warps * 32 + threads - 1) / threads;
+    const float inv_n = 1.f / ((float)(Cch / groups) * (float)hw);
+    groupnorm_finalize_kernel<<<blocks, threads, 0, stream>>>(partial, chunks, groups, B, inv_n, eps, stats);
+    DFB_CHECK_CUDA(cudaGetLastError());
+  }
   const long long total = (long long)B * hw * (Cch / 4);
   long long blocks = (total + GN_THREADS - 1) / GN_THREADS;
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  groupnorm_apply_kernel<<<(int)blocks, GN_THREADS, 0, stream>>>(src0, c0, ld0, src1, c1, ld1, hw, groups, eps, stats_ws, gamma,
+  groupnorm_apply_kernel<<<(int)blocks, GN_THREADS, 0, stream>>>(src0, c0, ld0, src1, c1, ld1, hw, groups, eps, stats, gamma,
                                                                 beta, silu, (__nv_bfloat16*)out_bf16, ld_out,
                                                                 (__nv_bfloat16*)raw_out_bf16, ld_raw, B);
   DFB_CHECK_CUDA(cudaGetLastError());

@@ -17,6 +17,36 @@ TAPS_3X3: Tuple[Tuple[int, int, int], ...] = tuple((kh - 1, kw - 1, 0) for kh in
 TAP_CENTER: Tuple[Tuple[int, int, int], ...] = ((0, 0, 0),)
 
 
+_LAUNCHES = 0
+PROFILE = None      # bench.py sets this to a list: every tensor-core launch is then bracketed by CUDA events
+
+
+def _prof_begin():
+    if PROFILE is None:
+        return None
+    e0 = torch.cuda.Event(enable_timing=True)
+    e0.record(torch.cuda.current_stream())
+    return e0
+
+
+def _prof_end(e0, kind: str, flops: float, shape):
+    if e0 is None:
+        return
+    e1 = torch.cuda.Event(enable_timing=True)
+    e1.record(torch.cuda.current_stream())
+    PROFILE.append((kind, flops, shape, e0, e1))
+
+
+def launch_count() -> int:
+    """Kernels of libdfb200.so launched so far by this process (bench.py's ``gpu_launches`` evidence)."""
+    return _LAUNCHES
+
+
+def _count(k: int = 1) -> None:
+    global _LAUNCHES
+    _LAUNCHES += k
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -126,7 +156,12 @@ def gemm(a: Sequence[torch.Tensor], w: torch.Tensor, n: int, *, out: torch.Tenso
     p.geglu = 1 if geglu else 0
     p.act = act
     p.block_n = block_n
+    e0 = _prof_begin()
     check(_lib.load().dfb_gemm(C.byref(p), _stream()), "dfb_gemm")
+    if e0 is not None:
+        k_exec = sum(int(p.ntaps[s]) * ceil64(int(p.a_c[s])) for s in range(nseg))
+        _prof_end(e0, "conv" if conv_geom is not None else "gemm", 2.0 * m_rows * n * k_exec, (m_rows, n, k_exec))
+    _count(1)
     return out
 
 
@@ -157,13 +192,21 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
     p.scale = scale
     p.block_kv = block_kv
     p.dbg_v_lbo, p.dbg_v_sbo = dbg_v_lbo, dbg_v_sbo
+    e0 = _prof_begin()
     check(_lib.load().dfb_attention(C.byref(p), _stream()), "dfb_attention")
+    if e0 is not None:
+        _prof_end(e0, "attention", 4.0 * q.shape[0] * heads * q.shape[1] * k.shape[1] * dp, (q.shape[0], heads, q.shape[1], k.shape[1], dp))
+    _count(1)
     return out
 
 
 # ----------------------------------------------------------------------------------------------
 # norms
 # ----------------------------------------------------------------------------------------------
+def groupnorm_ws_floats(b: int, groups: int) -> int:
+    return int(_lib.load().dfb_groupnorm_ws_floats(b, groups))
+
+
 def groupnorm(src0: torch.Tensor, src1: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor, *,
               groups: int, eps: float, silu: bool, stats_ws: torch.Tensor, out: torch.Tensor,
               raw_out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -173,11 +216,12 @@ def groupnorm(src0: torch.Tensor, src1: Optional[torch.Tensor], gamma: torch.Ten
     c0 = src0.shape[-1]
     c1 = 0 if src1 is None else src1.shape[-1]
     assert src0.dtype == torch.float32 and out.dtype == torch.bfloat16
-    assert stats_ws.dtype == torch.float32 and stats_ws.numel() >= b * groups * 2
+    assert stats_ws.dtype == torch.float32 and stats_ws.numel() >= groupnorm_ws_floats(b, groups)
     check(_lib.load().dfb_groupnorm(
         src0.data_ptr(), c0, src0.stride(-2), _ptr(src1), c1, 0 if src1 is None else src1.stride(-2), b, hw,
         groups, eps, gamma.data_ptr(), beta.data_ptr(), 1 if silu else 0, stats_ws.data_ptr(), out.data_ptr(),
         out.stride(-2), _ptr(raw_out), 0 if raw_out is None else raw_out.stride(-2), _stream()), "dfb_groupnorm")
+    _count(3)
     return out
 
 
@@ -187,6 +231,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: tor
     assert x.dtype == torch.float32 and out.dtype == torch.bfloat16
     check(_lib.load().dfb_layernorm(x.data_ptr(), x.stride(-2), gamma.data_ptr(), beta.data_ptr(), eps,
                                     out.data_ptr(), out.stride(-2), rows, x.shape[-1], _stream()), "dfb_layernorm")
+    _count(1)
     return out
 
 
@@ -195,8 +240,10 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: tor
 # ----------------------------------------------------------------------------------------------
 def cfg_step(eps: torch.Tensor, weights: Sequence[float], x_src: torch.Tensor, cx: float, ck: Sequence[float],
              hist: Sequence[Optional[torch.Tensor]] = (None, None, None), noise: Optional[torch.Tensor] = None,
-             cn: float = 0.0, x_out: Optional[torch.Tensor] = None, eps_out: Optional[torch.Tensor] = None):
-    """Fused CFG combine + scheduler update.  eps: fp32 NHWC ``[nb*N, H, W, 4]``; x: fp32 NCHW."""
+             cn: float = 0.0, x_out: Optional[torch.Tensor] = None, eps_out: Optional[torch.Tensor] = None,
+             eps_nchw: bool = False):
+    """Fused CFG combine + scheduler update.  eps: fp32 NHWC ``[nb*N, H, W, 4]`` (or NCHW ``[nb*N, 4, H, W]``
+    with ``eps_nchw``); x: fp32 NCHW."""
     nb = len(weights)
     n_items, hw = x_src.shape[0], x_src.shape[2] * x_src.shape[3]
     assert eps.dtype == torch.float32 and eps.is_contiguous() and eps.numel() == nb * n_items * hw * 4
@@ -206,9 +253,10 @@ def cfg_step(eps: torch.Tensor, weights: Sequence[float], x_src: torch.Tensor, c
     w = (C.c_float * nb)(*[float(v) for v in weights])
     ckk = (C.c_float * 4)(*[float(v) for v in (list(ck) + [0.0] * 4)[:4]])
     h = list(hist) + [None] * 3
-    check(_lib.load().dfb_cfg_step(eps.data_ptr(), nb, w, x_src.data_ptr(), float(cx), ckk, _ptr(h[0]), _ptr(h[1]),
+    check(_lib.load().dfb_cfg_step(eps.data_ptr(), 1 if eps_nchw else 0, nb, w, x_src.data_ptr(), float(cx), ckk, _ptr(h[0]), _ptr(h[1]),
                                    _ptr(h[2]), _ptr(noise), float(cn), x_out.data_ptr(), _ptr(eps_out), n_items, hw,
                                    _stream()), "dfb_cfg_step")
+    _count(1)
     return x_out
 
 
@@ -219,6 +267,7 @@ def mutual_gather_sum(all_latents: Optional[torch.Tensor], prev_latents: torch.T
     assert idx.dtype == torch.int32 and idx.is_contiguous() and out.dtype == torch.bfloat16
     check(_lib.load().dfb_mutual_gather_sum(_ptr(all_latents), prev_latents.data_ptr(), idx.data_ptr(), n_items,
                                             n_src, d, out.data_ptr(), _stream()), "dfb_mutual_gather_sum")
+    _count(1)
     return out
 
 
@@ -231,6 +280,7 @@ def mutual_blend(x: torch.Tensor, m: Optional[torch.Tensor], hist: Optional[torc
     assert out.dtype == torch.bfloat16 and out.numel() == nb * n_items * hw * 8
     check(_lib.load().dfb_mutual_blend(x.data_ptr(), _ptr(m), _ptr(hist), null_latent.data_ptr(), float(eta), nb, um,
                                        uh, n_items, hw, out.data_ptr(), _stream()), "dfb_mutual_blend")
+    _count(1)
     return out
 
 
@@ -239,6 +289,7 @@ def nchw_to_nhwc_bf16(x: torch.Tensor, out: torch.Tensor):
     assert x.is_contiguous()
     check(_lib.load().dfb_nchw_to_nhwc_bf16(x.data_ptr(), _dt(x), out.data_ptr(), b, c, h * w, _stream()),
           "dfb_nchw_to_nhwc_bf16")
+    _count(1)
     return out
 
 
@@ -247,6 +298,7 @@ def nhwc_to_nchw(x: torch.Tensor, out: torch.Tensor):
     assert x.dtype == torch.float32 and x.is_contiguous() and out.is_contiguous()
     check(_lib.load().dfb_nhwc_to_nchw(x.data_ptr(), out.data_ptr(), _dt(out), b, c, h * w, _stream()),
           "dfb_nhwc_to_nchw")
+    _count(1)
     return out
 
 
@@ -255,6 +307,7 @@ def pad_cast_rows(x: torch.Tensor, out: torch.Tensor):
     assert x.is_contiguous() and out.is_contiguous() and out.dtype == torch.bfloat16
     check(_lib.load().dfb_pad_cast_rows(x.data_ptr(), _dt(x), out.data_ptr(), b, s, out.shape[1], d, _stream()),
           "dfb_pad_cast_rows")
+    _count(1)
     return out
 
 
@@ -262,6 +315,7 @@ def upsample2x(x: torch.Tensor, out: torch.Tensor):
     b, h, w, c = x.shape
     assert x.dtype == torch.float32 and x.is_contiguous() and out.dtype == torch.bfloat16 and out.is_contiguous()
     check(_lib.load().dfb_upsample2x(x.data_ptr(), out.data_ptr(), b, h, w, c, _stream()), "dfb_upsample2x")
+    _count(1)
     return out
 
 
@@ -269,6 +323,7 @@ def space_to_depth(x: torch.Tensor, out: torch.Tensor):
     b, h, w, c = x.shape
     assert x.dtype == torch.float32 and x.is_contiguous() and out.dtype == torch.bfloat16 and out.is_contiguous()
     check(_lib.load().dfb_space_to_depth(x.data_ptr(), out.data_ptr(), b, h, w, c, _stream()), "dfb_space_to_depth")
+    _count(1)
     return out
 
 
@@ -290,4 +345,5 @@ def timestep_embedding(t: torch.Tensor, out: torch.Tensor, flip_sin_to_cos: bool
     check(_lib.load().dfb_timestep_embedding(t.data_ptr(), out.data_ptr(), t.shape[0], out.shape[1],
                                              1 if flip_sin_to_cos else 0, float(freq_shift), _stream()),
           "dfb_timestep_embedding")
+    _count(1)
     return out

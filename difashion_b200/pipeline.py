@@ -33,3 +33,247 @@ def mutual_index_table(olists: torch.Tensor) -> torch.Tensor:
                 row.append(-int(gen_row[o, s]) - 1 if gen[o, s] else o * olen + s)
             rows.append(row)
     return torch.tensor(rows, dtype=torch.int32).reshape(len(rows), olen - 1)
+
+
+# --------------------------------------------------------------------------------------------------
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+from . import ops
+from .mutual import MutualEncoder
+from .schedulers import B200DDIMScheduler, B200PNDMScheduler
+from .unet import B200UNet2DConditionModel, Workspace
+
+
+def guidance_plan(use_history: bool, use_mutual: bool, s_cate: float, s_hist: float, s_mutual: float):
+    """CFG branch layout of ``fashion_generation`` (difashion.py:309-325, :388-431, :494-512, :525-566).
+
+    Returns (ctx_is_cat[b], use_m[b], use_h[b], weights[b]) per branch b, so that
+    ``eps = sum_b weights[b] * eps_b`` equals the reference's nested guidance formula."""
+    do_h = bool(use_history and s_hist > 1.0)
+    do_m = bool(use_mutual and s_mutual > 1.0)
+    do_c = bool(s_cate > 1.0)
+    if do_h and do_m and do_c:
+        return [1, 1, 1, 0], [1, 1, 0, 0], [1, 0, 0, 0], [s_hist, s_mutual - s_hist, s_cate - s_mutual, 1.0 - s_cate]
+    if do_c:
+        if do_h:
+            return [1, 1, 0], [1, 1, 1], [1, 0, 0], [s_hist, s_cate - s_hist, 1.0 - s_cate]
+        if do_m:
+            return [1, 1, 0], [1, 0, 0], [1, 1, 1], [s_mutual, s_cate - s_mutual, 1.0 - s_cate]
+        return [1, 0], [1, 1], [1, 1], [s_cate, 1.0 - s_cate]
+    if do_h:
+        return [1, 1], [1, 1], [1, 0], [s_hist, 1.0 - s_hist]
+    if do_m:
+        return [1, 1], [1, 0], [1, 1], [s_mutual, 1.0 - s_mutual]
+    return [1], [1], [1], [1.0]
+
+
+@dataclass
+class _Chunk:
+    n0: int
+    n1: int
+    ctx: torch.Tensor                          # fp32/any [nb*(n1-n0), S, D] static buffer (refilled per generation)
+    ctx_bf16: torch.Tensor
+    kv_store: dict = field(default_factory=dict)
+    graph: Optional[torch.cuda.CUDAGraph] = None
+    eps: Optional[torch.Tensor] = None
+
+
+class _State:
+    """Static device buffers + captured graphs for one problem shape (reused across ``generate`` calls)."""
+    pass
+
+
+class B200DiFashionPipeline:
+    """Denoising loop of ``DiFashion.fashion_generation`` (difashion.py:456-577) on the B200 kernels.
+
+    One step = [mutual gather-sum -> MutualEncoder MLP] for all items, then per row chunk
+    [blend/concat/branch-expand -> UNet] (one CUDA graph per chunk) + one fused CFG-combine/scheduler kernel.
+    Whole outfits are the unit of work: all items of an outfit must be in the same call (they couple
+    through the mutual condition); different outfits never interact — which multi-GPU sharding relies on."""
+
+    def __init__(self, unet: B200UNet2DConditionModel, mutual_encoder: Optional[MutualEncoder], scheduler,
+                 eta_mutual: float = 0.1, use_history: bool = True, use_mutual_guidance: bool = True,
+                 max_rows: int = 256, use_cuda_graph: bool = True):
+        self.unet, self.mutual_encoder, self.scheduler = unet, mutual_encoder, scheduler
+        self.eta_mutual = float(eta_mutual)
+        self.use_history, self.use_mutual_guidance = use_history, use_mutual_guidance
+        self.max_rows = int(max_rows)
+        self.use_cuda_graph = use_cuda_graph
+        self._states = {}
+        self.last_step_launches = 0          # kernels launched per denoising step (counted at capture / eager run)
+
+    # ---------------------------------------------------------------------------------------------
+    def _chunk_forward(self, ch: _Chunk, st) -> torch.Tensor:
+        """blend -> UNet over the rows of one chunk, on the current stream."""
+        n = ch.n1 - ch.n0
+        x = st.latents[ch.n0:ch.n1]
+        m = st.m[ch.n0:ch.n1] if st.m is not None else None
+        hist = st.hist[ch.n0:ch.n1] if st.hist is not None else None
+        x_in = st.ws.get("pipe_x_in", (st.nb * n, st.size, st.size, 8), torch.bfloat16)
+        ops.mutual_blend(x, m, hist, st.null, self.eta_mutual, st.use_m, st.use_h, x_in)
+        return self.unet.forward_nhwc(x_in, st.t_dev[: st.nb * n], ch.ctx_bf16, ch.kv_store, st.ws)
+
+    def _mutual(self, st):
+        if st.m is None:
+            return
+        ops.mutual_gather_sum(st.all_latents, st.latents, st.idx, st.msum)
+        self.mutual_encoder.encode_bf16(st.msum, st.m.view(st.n, -1), st.mhid)
+
+    def _state(self, dev, n, n_given, olen, size, nb, S, D, plan) -> "_State":
+        key = (str(dev), n, n_given, olen, size, nb, S, D, tuple(map(tuple, plan[:3])), self.use_history,
+               self.use_mutual_guidance, self.max_rows)
+        st = self._states.get(key)
+        if st is not None:
+            return st
+        st = _State()
+        hw = size * size
+        st.n, st.size, st.hw, st.nb = n, size, hw, nb
+        st.ctx_cat, st.use_m, st.use_h = plan[0], plan[1], plan[2]
+        f = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
+        st.latents = f(n, 4, size, size)
+        st.null = f(4, size, size)
+        st.hist = f(n, 4, size, size) if self.use_history else None
+        st.all_latents = f(max(n_given, 1), 4, size, size)
+        st.m = None
+        if self.use_mutual_guidance:
+            if self.mutual_encoder is None:
+                raise ValueError("use_mutual_guidance=True needs a MutualEncoder")
+            st.idx = torch.empty(n, max(olen - 1, 1), dtype=torch.int32, device=dev)
+            st.msum = torch.empty(n, 4 * hw, dtype=torch.bfloat16, device=dev)
+            st.mhid = torch.empty(n, self.mutual_encoder.hid_dim, dtype=torch.bfloat16, device=dev)
+            st.m = f(n, 4, size, size)
+        per = max(1, self.max_rows // nb)
+        st.t_dev = torch.zeros(nb * min(n, per), dtype=torch.float32, device=dev)
+        st.ws = self.unet.workspace(("pipe", nb, min(n, per), size), dev)
+        st.chunks = []
+        for n0 in range(0, n, per):
+            n1 = min(n, n0 + per)
+            rows = nb * (n1 - n0)
+            st.chunks.append(_Chunk(n0, n1, torch.empty(rows, S, D, dtype=torch.float32, device=dev),
+                                    torch.empty(rows, S, D, dtype=torch.bfloat16, device=dev)))
+        st.warm = False
+        self._states[key] = st
+        return st
+
+    @torch.no_grad()
+    def begin(self, *, olists: torch.Tensor, all_latents: Optional[torch.Tensor], category_prompts: torch.Tensor,
+              null_prompt: torch.Tensor, hist_latents: Optional[torch.Tensor], null_latent: torch.Tensor,
+              init_latents: torch.Tensor, num_inference_steps: int = 50, category_guidance_scale: float = 12.0,
+              hist_guidance_scale: float = 4.0, mutual_guidance_scale: float = 5.0, device=None) -> "_State":
+        """Stage one generation: copy the inputs (host or device) into the static device buffers, project the
+        step-invariant text K/V, reset the scheduler.  Returns the state to pass to ``step``."""
+        dev = torch.device(device) if device is not None else (init_latents.device if init_latents.is_cuda
+                                                               else torch.device("cuda", torch.cuda.current_device()))
+        if dev.type != "cuda":
+            raise RuntimeError("B200DiFashionPipeline needs a CUDA device: there is no CPU fallback")
+        n, size = init_latents.shape[0], init_latents.shape[-1]
+        bsz, olen = olists.shape
+        if int((olists == 0).sum()) != n:
+            raise ValueError("init_latents must have one row per blank (olists == 0) slot")
+        plan = guidance_plan(self.use_history, self.use_mutual_guidance, category_guidance_scale, hist_guidance_scale,
+                             mutual_guidance_scale)
+        ctx_cat, use_m, use_h, weights = plan
+        nb = len(weights)
+        S, D = category_prompts.shape[1], category_prompts.shape[2]
+        n_given = 0 if all_latents is None else all_latents.shape[0]
+        st = self._state(dev, n, n_given, olen, size, nb, S, D, plan)
+        st.weights = weights
+        sched = self.scheduler
+        sched.set_timesteps(num_inference_steps)
+        st.timesteps = [int(t) for t in sched.timesteps]
+
+        st.latents.copy_(init_latents, non_blocking=True)
+        if float(sched.init_noise_sigma) != 1.0:
+            st.latents.mul_(float(sched.init_noise_sigma))
+        st.null.copy_(null_latent, non_blocking=True)
+        if st.hist is not None:
+            if hist_latents is None:
+                st.hist.copy_(st.null.unsqueeze(0).expand_as(st.hist))
+            else:
+                st.hist.copy_(hist_latents, non_blocking=True)
+        if all_latents is not None:
+            st.all_latents.copy_(all_latents, non_blocking=True)
+        if st.m is not None:
+            st.idx.copy_(mutual_index_table(olists), non_blocking=True)
+        for ch in st.chunks:
+            k = ch.n1 - ch.n0
+            for b, c in enumerate(ctx_cat):
+                dst = ch.ctx[b * k:(b + 1) * k]
+                if c:
+                    dst.copy_(category_prompts[ch.n0:ch.n1], non_blocking=True)
+                else:
+                    dst.copy_(null_prompt.expand(k, -1, -1), non_blocking=True)
+            ch.ctx_bf16.copy_(ch.ctx)
+            self.unet.project_context(ch.ctx_bf16, ch.kv_store)     # step-invariant text K/V: once per generation
+        return st
+
+    @torch.no_grad()
+    def step(self, st: "_State", t: int, ddim_eta: float = 0.0, generator=None, record: Optional[list] = None):
+        """One denoising step (difashion.py:456-577 loop body) for every item of the staged batch."""
+        sched = self.scheduler
+        latents = st.latents
+        st.t_dev.fill_(float(t))
+        c0 = ops.launch_count()
+        self._mutual(st)
+        step_launches = ops.launch_count() - c0
+        eps_all = []
+        for ch in st.chunks:
+            if self.use_cuda_graph and ch.graph is None:
+                # warm-up (allocates workspaces, sets kernel attributes), then capture this chunk's step
+                self._chunk_forward(ch, st)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                c1 = ops.launch_count()
+                with torch.cuda.graph(g):
+                    ch.eps = self._chunk_forward(ch, st)
+                ch.graph, ch.launches = g, ops.launch_count() - c1
+            if ch.graph is not None:
+                ch.graph.replay()
+                eps = ch.eps
+                step_launches += ch.launches
+            else:
+                c1 = ops.launch_count()
+                eps = self._chunk_forward(ch, st)
+                step_launches += ops.launch_count() - c1
+            x = latents[ch.n0:ch.n1]
+            if record is not None:
+                eps_all.append(eps.clone())
+            if isinstance(sched, B200DDIMScheduler):
+                sched.cfg_step(eps, st.weights, t, x, eta=ddim_eta, generator=generator, out=x)
+            else:
+                if len(st.chunks) != 1:
+                    raise NotImplementedError("PLMS keeps per-call history: run it with a single row chunk")
+                sched.cfg_step(eps, st.weights, t, x, out=x)
+            step_launches += 1
+        self.last_step_launches = step_launches
+        if record is not None:
+            record.append(dict(t=t, eps_branches=[e for e in eps_all], latents=latents.clone()))
+
+    @torch.no_grad()
+    def generate(self, *, num_inference_steps: int = 50, ddim_eta: float = 0.0, generator=None,
+                 max_steps: Optional[int] = None, record: Optional[list] = None, out: Optional[torch.Tensor] = None,
+                 **inputs) -> torch.Tensor:
+        """Arguments mirror what ``fashion_generation`` has at hand when the loop starts (difashion.py:332-453):
+        olists [bsz, olen] (0 = slot to generate), all_latents [bsz*olen,4,h,w] (VAE latents of the given
+        items), category_prompts [N,S,D] / null_prompt [1,S,D] (CLIP hidden states), hist_latents [N,4,h,w]
+        (null_latent where the user has no history), null_latent [4,h,w], init_latents [N,4,h,w], the three
+        guidance scales.  Inputs may live on the host (pinned or not): they are copied into static device
+        buffers.  Returns the final latents [N,4,h,w] fp32 on the device, or copies them into ``out``."""
+        st = self.begin(num_inference_steps=num_inference_steps, **inputs)
+        for i, t in enumerate(st.timesteps):
+            if max_steps is not None and i >= max_steps:
+                break
+            self.step(st, t, ddim_eta=ddim_eta, generator=generator, record=record)
+        if out is not None:
+            out.copy_(st.latents, non_blocking=True)
+            return out
+        return st.latents
+
+
+def shard_outfits(n_outfits: int, rank: int, world_size: int):
+    """Whole-outfit sharding: contiguous block of outfits for ``rank``; no outfit is ever split.
+    Returns ``range`` of outfit indices."""
+    base, rem = divmod(n_outfits, world_size)
+    start = rank * base + min(rank, rem)
+    return range(start, start + base + (1 if rank < rem else 0))

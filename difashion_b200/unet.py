@@ -198,7 +198,6 @@ class B200UNet2DConditionModel(nn.Module):
         self._pack: Optional[Dict[str, Any]] = None
         self._pack_key = None
         self._ws: Dict[Any, Workspace] = {}
-        self._kv_cache: Dict[str, Any] = {}
 
     # ---------------------------------------------------------------- diffusers-style surface
     @property
@@ -354,7 +353,7 @@ class B200UNet2DConditionModel(nn.Module):
         P["tproj"] = (ops.pack_linear(torch.cat(tp_w, 0)), torch.cat(tp_b, 0).contiguous(), off)
         P["device"] = device
         self._pack, self._pack_key = P, key
-        self._kv_cache = {}
+        self.clear_context_cache()
         return P
 
     # ---------------------------------------------------------------- kernels sequencing
@@ -364,7 +363,7 @@ class B200UNet2DConditionModel(nn.Module):
         B, H, W = x0.shape[0], x0.shape[1], x0.shape[2]
         cin, cout = pk["cin"], pk["cout"]
         g, b, eps, groups = pk["n1"]
-        stats = ws.get("gn_stats", (B * groups * 2,), torch.float32)
+        stats = ws.get("gn_stats", (ops.groupnorm_ws_floats(B, groups),), torch.float32)
         xn = ws.get("xn", (B, H, W, cin), torch.bfloat16)
         xraw = ws.get("xraw", (B, H, W, cin), torch.bfloat16) if pk["shortcut"] else None
         ops.groupnorm(x0, x1, g, b, groups=groups, eps=eps, silu=True, stats_ws=stats, out=xn, raw_out=xraw)
@@ -382,23 +381,37 @@ class B200UNet2DConditionModel(nn.Module):
             ops.gemm([hn], pk["w2"], cout, out=out, taps=[ops.TAPS_3X3], conv_geom=(B, H, W), bias=pk["b2"], residual=x0)
         return out
 
-    def _cross_kv(self, pk_attn: AttnPack, name: str, ctx_bf16: torch.Tensor, ws: Workspace):
-        """K/V of the text tokens are step-invariant: projected once per distinct context tensor."""
-        ent = self._kv_cache.get(name)
-        key = self._ctx_key
-        if ent is not None and ent[0] == key:
-            return ent[1]
-        b, skv, dctx = ctx_bf16.shape
-        kv = torch.empty(b, skv, 2 * pk_attn.cp, dtype=torch.bfloat16, device=ctx_bf16.device)
-        ops.gemm([ctx_bf16.view(b * skv, dctx)], pk_attn.w_kv, 2 * pk_attn.cp, out=kv.view(b * skv, 2 * pk_attn.cp))
-        self._kv_cache[name] = (key, kv)
-        return kv
+    def cross_attention_layers(self, P=None):
+        """(name, AttnPack) of every cross-attention layer, in execution order."""
+        P = P or self._pack
+        out = []
+        for i, bp in enumerate(P["down"]):
+            for j, tp in enumerate(bp["attentions"] or []):
+                out.append((f"down{i}.{j}", tp["a2"]))
+        out.append(("mid", P["mid"]["attentions"][0]["a2"]))
+        for i, bp in enumerate(P["up"]):
+            for j, tp in enumerate(bp["attentions"] or []):
+                out.append((f"up{i}.{j}", tp["a2"]))
+        return out
 
-    def _transformer(self, pk, name: str, x: torch.Tensor, ctx_bf16, ws: Workspace, out_tag: str):
+    def project_context(self, ctx_bf16: torch.Tensor, store: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """K/V projections of the text tokens for all cross-attention layers (step-invariant: done once per
+        generation, outside the per-step graph).  ``store`` buffers are reused in place when present."""
+        P = self.pack(ctx_bf16.device)
+        b, skv, dctx = ctx_bf16.shape
+        for name, a2 in self.cross_attention_layers(P):
+            kv = store.get(name)
+            if kv is None or kv.shape != (b, skv, 2 * a2.cp):
+                kv = torch.empty(b, skv, 2 * a2.cp, dtype=torch.bfloat16, device=ctx_bf16.device)
+                store[name] = kv
+            ops.gemm([ctx_bf16.view(b * skv, dctx)], a2.w_kv, 2 * a2.cp, out=kv.view(b * skv, 2 * a2.cp))
+        return store
+
+    def _transformer(self, pk, name: str, x: torch.Tensor, ctx_bf16, kv_store, ws: Workspace, out_tag: str):
         B, H, W, C = x.shape
         S, M = H * W, B * H * W
         g, b, eps, groups = pk["gn"]
-        stats = ws.get("gn_stats", (B * groups * 2,), torch.float32)
+        stats = ws.get("gn_stats", (ops.groupnorm_ws_floats(B, groups),), torch.float32)
         xn = ws.get("xn", (M, C), torch.bfloat16)
         ops.groupnorm(x, None, g, b, groups=groups, eps=eps, silu=False, stats_ws=stats, out=xn.view(B, H, W, C))
         h = ws.get("tr_h", (M, C), torch.float32)
@@ -425,7 +438,7 @@ class B200UNet2DConditionModel(nn.Module):
         if fast:
             q = ws.get("q", (B, S, a2.cp), torch.bfloat16)
             ops.gemm([ln], a2.w_q, a2.cp, out=q.view(M, a2.cp))
-            kv = self._cross_kv(a2, name, ctx_bf16, ws)
+            kv = kv_store[name]
             att = ws.get("att", (B, S, a2.cp), torch.bfloat16)
             ops.attention(q, kv[..., :a2.cp], kv[..., a2.cp:], att, heads=a2.heads, dp=a2.dp, scale=a2.scale)
             ops.gemm([att.view(M, a2.cp)], a2.w_o, C, out=h, bias=a2.b_o, residual=h)
@@ -457,10 +470,10 @@ class B200UNet2DConditionModel(nn.Module):
         ops.gemm([e2], P["tproj"][0], ntot, out=temb_all, bias=P["tproj"][1])
         return temb_all
 
-    def forward_nhwc(self, x_in: torch.Tensor, t_dev: torch.Tensor, ctx_bf16: torch.Tensor, ws: Workspace,
-                     taps: Optional[dict] = None) -> torch.Tensor:
-        """x_in: bf16 NHWC [B,H,W,in_channels]; t_dev: fp32 [B]; ctx: bf16 [B,S_kv,D].  Returns the
-        fp32 NHWC noise prediction [B,H,W,out_channels] (a workspace buffer)."""
+    def forward_nhwc(self, x_in: torch.Tensor, t_dev: torch.Tensor, ctx_bf16: torch.Tensor, kv_store: Dict[str, torch.Tensor],
+                     ws: Workspace, taps: Optional[dict] = None) -> torch.Tensor:
+        """x_in: bf16 NHWC [B,H,W,in_channels]; t_dev: fp32 [B]; ctx: bf16 [B,S_kv,D]; kv_store: the result of
+        ``project_context(ctx)``.  Returns the fp32 NHWC noise prediction [B,H,W,out_channels] (a workspace buffer)."""
         P = self.pack(x_in.device)
         B, H, W, cin = x_in.shape
         temb_all = self._temb(P, t_dev, ws)
@@ -474,7 +487,7 @@ class B200UNet2DConditionModel(nn.Module):
             for j, rp in enumerate(bp["resnets"]):
                 has_att = bp["attentions"] is not None
                 r = self._resnet(rp, [h], temb_all, ws, "rtmp" if has_att else f"skip{ns}")
-                h = self._transformer(bp["attentions"][j], f"down{i}.{j}", r, ctx_bf16, ws, f"skip{ns}") if has_att else r
+                h = self._transformer(bp["attentions"][j], f"down{i}.{j}", r, ctx_bf16, kv_store, ws, f"skip{ns}") if has_att else r
                 skips.append(h)
                 ns += 1
             if bp["downsamplers"] is not None:
@@ -490,7 +503,7 @@ class B200UNet2DConditionModel(nn.Module):
                 taps[f"down{i}"] = h.clone()
         mp = P["mid"]
         r = self._resnet(mp["resnets"][0], [h], temb_all, ws, "mid_r0")
-        a = self._transformer(mp["attentions"][0], "mid", r, ctx_bf16, ws, "mid_a")
+        a = self._transformer(mp["attentions"][0], "mid", r, ctx_bf16, kv_store, ws, "mid_a")
         h = self._resnet(mp["resnets"][1], [a], temb_all, ws, "mid_r1")
         if taps is not None:
             taps["mid"] = h.clone()
@@ -500,7 +513,7 @@ class B200UNet2DConditionModel(nn.Module):
                 skip = skips.pop()
                 par ^= 1
                 r = self._resnet(rp, [h, skip], temb_all, ws, f"up_r{par}")
-                h = (self._transformer(bp["attentions"][j], f"up{i}.{j}", r, ctx_bf16, ws, f"up_a{par}")
+                h = (self._transformer(bp["attentions"][j], f"up{i}.{j}", r, ctx_bf16, kv_store, ws, f"up_a{par}")
                      if bp["attentions"] is not None else r)
             if bp["upsamplers"] is not None:
                 w, b, c = bp["upsamplers"]
@@ -512,7 +525,7 @@ class B200UNet2DConditionModel(nn.Module):
             if taps is not None:
                 taps[f"up{i}"] = h.clone()
         g, b, eps, groups = P["norm_out"]
-        stats = ws.get("gn_stats", (B * groups * 2,), torch.float32)
+        stats = ws.get("gn_stats", (ops.groupnorm_ws_floats(B, groups),), torch.float32)
         xn = ws.get("xn", (B, H, W, c0), torch.bfloat16)
         ops.groupnorm(h, None, g, b, groups=groups, eps=eps, silu=True, stats_ws=stats, out=xn)
         cout = self.config.out_channels
@@ -527,15 +540,26 @@ class B200UNet2DConditionModel(nn.Module):
             self._ws[key] = ws
         return ws
 
-    def set_context(self, encoder_hidden_states: torch.Tensor) -> torch.Tensor:
-        """Register the cross-attention context; its K/V projections are cached until it changes."""
+    MAX_CACHED_CONTEXTS = 8
+
+    def set_context(self, encoder_hidden_states: torch.Tensor):
+        """(bf16 context, K/V store) for ``encoder_hidden_states``; cached per distinct tensor (identity + version)
+        so the 16 layers' K/V projections are computed once per generation, not once per step."""
         key = (encoder_hidden_states.data_ptr(), encoder_hidden_states._version, tuple(encoder_hidden_states.shape),
                encoder_hidden_states.dtype)
-        if getattr(self, "_ctx_key", None) != key or getattr(self, "_ctx_bf16", None) is None:
-            self._ctx_key = key
-            self._ctx_bf16 = encoder_hidden_states.detach().to(torch.bfloat16).contiguous()
-            self._kv_cache = {}
-        return self._ctx_bf16
+        ctxs = self.__dict__.setdefault("_ctxs", {})
+        ent = ctxs.get(key)
+        if ent is None:
+            while len(ctxs) >= self.MAX_CACHED_CONTEXTS:
+                ctxs.pop(next(iter(ctxs)))
+            ctx_bf16 = encoder_hidden_states.detach().to(torch.bfloat16).contiguous()
+            # keep the source tensor alive so its address cannot be recycled under the same key
+            ent = (ctx_bf16, self.project_context(ctx_bf16, {}), encoder_hidden_states)
+            ctxs[key] = ent
+        return ent[0], ent[1]
+
+    def clear_context_cache(self):
+        self.__dict__["_ctxs"] = {}
 
     @torch.no_grad()
     def forward(self, sample: torch.Tensor, timestep: Union[torch.Tensor, float, int],
@@ -569,8 +593,8 @@ class B200UNet2DConditionModel(nn.Module):
         x_in = ws.get("x_in", (B, H, W, C), torch.bfloat16)
         smp = sample if sample.dtype in (torch.float32, torch.bfloat16) else sample.float()
         ops.nchw_to_nhwc_bf16(smp.contiguous(), x_in)
-        ctx = self.set_context(encoder_hidden_states)
-        eps = self.forward_nhwc(x_in, t_dev, ctx, ws)
+        ctx, kv_store = self.set_context(encoder_hidden_states)
+        eps = self.forward_nhwc(x_in, t_dev, ctx, kv_store, ws)
         out_dtype = sample.dtype if sample.dtype in (torch.float32, torch.bfloat16) else torch.float32
         out = torch.empty(B, self.config.out_channels, H, W, dtype=out_dtype, device=dev)
         ops.nhwc_to_nchw(eps, out)

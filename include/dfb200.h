@@ -121,9 +121,11 @@ int dfb_attention(const dfb_attn_params* p, void* stream);
  * dfb_groupnorm replaces nn.GroupNorm(32, C)(+SiLU) of ResnetBlock2D.norm1/norm2,
  * Transformer2DModel.norm and conv_norm_out; reads the up-block skip concat from its two sources
  * (torch.cat([h, skip], 1) is never materialised); optional raw bf16 copy of the input (the A
- * operand of conv_shortcut).  stats_ws: fp32 [B, groups, 2] scratch.
+ * operand of conv_shortcut).  stats_ws: fp32 scratch of dfb_groupnorm_ws_floats(B, groups) elements.
+ * Deterministic (fixed-order reductions, no atomics).
  * dfb_layernorm replaces BasicTransformerBlock.norm1/2/3.
  * ------------------------------------------------------------------------------------------ */
+size_t dfb_groupnorm_ws_floats(int B, int groups);
 int dfb_groupnorm(const float* src0, int c0, int ld0, const float* src1, int c1, int ld1, int B, int hw,
                   int groups, float eps, const float* gamma, const float* beta, int silu, float* stats_ws,
                   void* out_bf16, int ld_out, void* raw_out_bf16, int ld_raw, void* stream);
@@ -135,10 +137,11 @@ int dfb_layernorm(const float* x, int ld_x, const float* gamma, const float* bet
  * ------------------------------------------------------------------------------------------ */
 /* CFG combine (difashion.py:525-566) fused with the scheduler update (:569; diffusers
  * DDIMScheduler.step / PNDMScheduler.step_plms):
- *   e0 = sum_b w[b] * eps[b]   (eps: fp32 NHWC [nb*N, hw, 4], branch-major)
+ *   e0 = sum_b w[b] * eps[b]   (eps: fp32, branch-major [nb*N, ...]; NHWC [hw,4] from the UNet kernels, or
+ *                               NCHW [4,hw] when eps_nchw != 0 — the public scheduler.step() path)
  *   x_out = cx*x_src + ck[0]*e0 + ck[1]*hist1 + ck[2]*hist2 + ck[3]*hist3 + cn*noise   (fp32 NCHW [N,4,hw])
  *   eps_out (optional) = e0.   w: host float[nb]; ck: host float[4].                           */
-int dfb_cfg_step(const float* eps, int nb, const float* w, const float* x_src, float cx, const float* ck,
+int dfb_cfg_step(const float* eps, int eps_nchw, int nb, const float* w, const float* x_src, float cx, const float* ck,
                  const float* hist1, const float* hist2, const float* hist3, const float* noise, float cn,
                  float* x_out, float* eps_out, int n_items, int hw, void* stream);
 /* Mutual-condition neighbour sum (difashion.py:475-488): out[n] = sum_s src(idx[n, s]); idx >= 0 ->

@@ -97,6 +97,8 @@ def oracle_generation(unet, mutual_encoder, scheduler, *, olists, all_latents, c
     latents = init_latents.clone() * scheduler.init_noise_sigma
 
     null_stack = torch.stack([null_latent] * n)
+    if not use_history:                      # difashion.py:381-385: without history every item gets the null latent
+        hist_latents = null_stack
     if do_all:
         hist = torch.cat([hist_latents, null_stack, null_stack, null_stack], 0)
         ctx = torch.cat([category_prompts, category_prompts, category_prompts, null_prompts], 0)

@@ -25,7 +25,7 @@ def test_groupnorm(B, H, W, c0, c1, silu, raw):
     eps = 1e-5 if silu else 1e-6
     out = torch.empty(B, H, W, C, dtype=torch.bfloat16, device="cuda")
     rawo = torch.empty(B, H, W, C, dtype=torch.bfloat16, device="cuda") if raw else None
-    ws = torch.empty(B * 32 * 2, dtype=torch.float32, device="cuda")
+    ws = torch.empty(ops.groupnorm_ws_floats(B, 32), dtype=torch.float32, device="cuda")
     ops.groupnorm(x0, x1, gamma, beta, groups=32, eps=eps, silu=silu, stats_ws=ws, out=out, raw_out=rawo)
     torch.cuda.synchronize()
     x = x0 if x1 is None else torch.cat([x0, x1], -1)

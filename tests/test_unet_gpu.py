@@ -1,0 +1,157 @@
+"""GPU parity of the full UNet forward and of the generation loop against the CPU oracle
+(oracle/unet_oracle.py, oracle/generation_oracle.py) on identical random-init weights / inputs.
+Tolerances are BASELINE.json's: per-step noise-prediction rel-L2 <= 1e-2 (bf16 tensor-core operands,
+fp32 accumulate / residual stream), final-latent cosine >= 0.999."""
+import pytest
+import torch
+
+from tests.util import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(cfg_kw, seed=0):
+    from oracle.unet_oracle import UNetConfig, make_oracle_unet, tiny_config
+    from difashion_b200.unet import B200UNet2DConditionModel
+    ocfg = tiny_config() if cfg_kw == "tiny" else UNetConfig()
+    oracle = make_oracle_unet(ocfg, seed=seed)
+    kw = dict(sample_size=ocfg.sample_size, in_channels=ocfg.in_channels, out_channels=ocfg.out_channels,
+              block_out_channels=tuple(ocfg.block_out_channels), cross_attention_dim=ocfg.cross_attention_dim,
+              attention_head_dim=ocfg.attention_head_dim)
+    unet = B200UNet2DConditionModel(**kw)
+    missing = unet.load_state_dict(oracle.state_dict(), strict=True)
+    return oracle, unet.cuda()
+
+
+def _block_report(taps_o, taps_g):
+    out = []
+    for k, v in taps_o.items():
+        if k in taps_g:
+            out.append(f"{k}: {rel_l2(taps_g[k].permute(0, 3, 1, 2).cpu(), v):.2e}")
+    return " | ".join(out)
+
+
+@pytest.mark.parametrize("which,B,S", [("tiny", 4, 77), ("tiny", 3, 85), ("full", 2, 77)])
+def test_unet_forward_matches_oracle(which, B, S):
+    oracle, unet = _mk(which)
+    cfg = oracle.cfg
+    g = torch.Generator().manual_seed(123)
+    x = torch.randn(B, cfg.in_channels, cfg.sample_size, cfg.sample_size, generator=g)
+    ctx = torch.randn(B, S, cfg.cross_attention_dim, generator=g)
+    t = torch.tensor(981)
+    taps_o = {}
+    ref = oracle(x, t, ctx, taps=taps_o)
+    # block-level taps through the NHWC entry point
+    from difashion_b200 import ops
+    ws = unet.workspace(("test", B), torch.device("cuda"))
+    x_in = torch.empty(B, cfg.sample_size, cfg.sample_size, cfg.in_channels, dtype=torch.bfloat16, device="cuda")
+    ops.nchw_to_nhwc_bf16(x.cuda(), x_in)
+    taps_g = {}
+    ctx_dev = ctx.cuda()
+    unet.forward_nhwc(x_in, torch.full((B,), 981.0, device="cuda"), *unet.set_context(ctx_dev), ws, taps=taps_g)
+    torch.cuda.synchronize()
+    report = _block_report(taps_o, taps_g)
+    # public diffusers-style call
+    got = unet(x.cuda(), t.cuda(), encoder_hidden_states=ctx_dev, return_dict=False)[0]
+    out2 = unet(x.cuda(), 981, ctx_dev).sample
+    torch.cuda.synchronize()
+    e = rel_l2(got.cpu(), ref)
+    print(f"\n[{which} B={B}] eps rel-L2 {e:.3e}; per-block: {report}")
+    assert got.shape == ref.shape and got.dtype == torch.float32
+    assert e <= 1e-2, report
+    assert torch.equal(got, out2)
+    for i in range(B):
+        assert rel_l2(got[i].cpu(), ref[i]) <= 1e-2
+
+
+def _gen_inputs(cfg, olists, S=77, seed=123):
+    g = torch.Generator().manual_seed(seed)
+    bsz, olen = olists.shape
+    n = int((olists == 0).sum())
+    s = cfg.sample_size
+    return dict(
+        olists=olists,
+        all_latents=0.9 * torch.randn(bsz * olen, 4, s, s, generator=g),
+        category_prompts=torch.randn(n, S, cfg.cross_attention_dim, generator=g),
+        null_prompt=torch.randn(1, S, cfg.cross_attention_dim, generator=g),
+        hist_latents=0.9 * torch.randn(n, 4, s, s, generator=g),
+        null_latent=0.9 * torch.randn(4, s, s, generator=g),
+        init_latents=torch.randn(n, 4, s, s, generator=g),
+    )
+
+
+def _run_both(which, olists, steps, sched_name, scales=(12.0, 4.0, 5.0), total_steps=None, use_graph=True, flags=(True, True)):
+    from oracle.generation_oracle import make_oracle_mutual_encoder, oracle_generation
+    from oracle.schedulers_oracle import OracleDDIMScheduler, OraclePNDMScheduler
+    from difashion_b200.mutual import MutualEncoder
+    from difashion_b200.pipeline import B200DiFashionPipeline
+    from difashion_b200.schedulers import B200DDIMScheduler, B200PNDMScheduler
+    oracle, unet = _mk(which)
+    cfg = oracle.cfg
+    hid = 64 if which == "tiny" else 256
+    ome = make_oracle_mutual_encoder(seed=1, latent_size=cfg.sample_size, hid_dim=hid)
+    me = MutualEncoder(latent_size=cfg.sample_size, hid_dim=hid)
+    me.load_state_dict(ome.state_dict())
+    inp = _gen_inputs(cfg, olists)
+    total = total_steps or steps
+    osched = OracleDDIMScheduler() if sched_name == "ddim" else OraclePNDMScheduler()
+    rec_o = []
+    lat_o = oracle_generation(oracle, ome, osched, **inp, num_inference_steps=total, category_guidance_scale=scales[0],
+                              hist_guidance_scale=scales[1], mutual_guidance_scale=scales[2], use_history=flags[0],
+                              use_mutual_guidance=flags[1], record=rec_o, max_steps=steps)
+    sched = B200DDIMScheduler() if sched_name == "ddim" else B200PNDMScheduler()
+    pipe = B200DiFashionPipeline(unet, me.cuda(), sched, eta_mutual=0.1, use_history=flags[0], use_mutual_guidance=flags[1],
+                                 use_cuda_graph=use_graph)
+    rec_g = []
+    dev_inp = {k: (v.cuda() if k != "olists" else v) for k, v in inp.items()}
+    lat_g = pipe.generate(**dev_inp, num_inference_steps=total, category_guidance_scale=scales[0],
+                          hist_guidance_scale=scales[1], mutual_guidance_scale=scales[2], record=rec_g, max_steps=steps)
+    torch.cuda.synchronize()
+    return lat_o, lat_g.cpu(), rec_o, rec_g
+
+
+def _cos(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a @ b) / (a.norm() * b.norm()))
+
+
+@pytest.mark.parametrize("sched,use_graph", [("ddim", True), ("ddim", False), ("pndm", True)])
+def test_generation_gor_tiny_50_steps(sched, use_graph):
+    """GOR: 2 outfits x 4 generated items, 50 steps, 4-branch CFG: final-latent cosine >= 0.999."""
+    olists = torch.zeros(2, 4, dtype=torch.long)
+    lat_o, lat_g, rec_o, rec_g = _run_both("tiny", olists, 51 if sched == "pndm" else 50, sched, total_steps=50, use_graph=use_graph)
+    # first step: identical inputs -> per-branch eps parity
+    e0 = rel_l2(rec_g[0]["eps_branches"][0].permute(0, 3, 1, 2).cpu(), rec_o[0]["noise_pred_branches"])
+    c = _cos(lat_g, lat_o)
+    print(f"\n[{sched} graph={use_graph}] step-0 eps rel-L2 {e0:.3e}; final cosine {c:.6f}; final rel-L2 {rel_l2(lat_g, lat_o):.3e}")
+    assert e0 <= 1e-2
+    assert c >= 0.999
+
+
+@pytest.mark.parametrize("scales,flags", [((12.0, 4.0, 5.0), (True, True)), ((12.0, 1.0, 5.0), (True, True)),
+                                          ((12.0, 4.0, 1.0), (True, True)), ((12.0, 1.0, 1.0), (True, True)),
+                                          ((1.0, 4.0, 1.0), (True, True)), ((1.0, 1.0, 5.0), (True, True)),
+                                          ((1.0, 1.0, 1.0), (True, True)), ((12.0, 4.0, 5.0), (False, True)),
+                                          ((12.0, 4.0, 5.0), (True, False))])
+def test_generation_fitb_and_degenerate_cfg_variants(scales, flags):
+    """FITB-style outfits (given items + blanks) through every CFG branch layout of difashion.py:533-566."""
+    olists = torch.tensor([[3, 0, 7, 9], [0, 5, 0, 2], [4, 4, 4, 0]])
+    lat_o, lat_g, rec_o, rec_g = _run_both("tiny", olists, 3, "ddim", scales=scales, flags=flags)
+    e0 = rel_l2(rec_g[0]["eps_branches"][0].permute(0, 3, 1, 2).cpu(), rec_o[0]["noise_pred_branches"])
+    el = rel_l2(lat_g, lat_o)
+    print(f"\n[scales={scales} flags={flags}] step-0 eps rel-L2 {e0:.3e}; latents rel-L2 after 3 steps {el:.3e}")
+    assert e0 <= 1e-2
+    assert _cos(lat_g, lat_o) >= 0.999
+
+
+def test_generation_full_size_two_steps():
+    """SD-1.5-shaped UNet, one FITB outfit (1 blank, 3 given items) -> 4 UNet rows, 2 DDIM steps of 50."""
+    olists = torch.tensor([[11, 0, 7, 9]])
+    lat_o, lat_g, rec_o, rec_g = _run_both("full", olists, 2, "ddim", total_steps=50)
+    for i in range(2):
+        if i == 0:
+            e = rel_l2(rec_g[0]["eps_branches"][0].permute(0, 3, 1, 2).cpu(), rec_o[0]["noise_pred_branches"])
+            print(f"\n[full] step-0 per-branch eps rel-L2 {e:.3e}")
+            assert e <= 1e-2
+    print(f"[full] latents rel-L2 after 2 steps {rel_l2(lat_g, lat_o):.3e} cosine {_cos(lat_g, lat_o):.6f}")
+    assert _cos(lat_g, lat_o) >= 0.999

@@ -10,7 +10,7 @@ ids = [l.strip() for l in ids if "::" in l]
 summary = []
 for tid in ids:
     try:
-        r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "--no-header", "-p", "no:cacheprovider", tid],
+        r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-s", "--no-header", "-p", "no:cacheprovider", tid],
                            capture_output=True, text=True, timeout=300)
         ok = r.returncode == 0
         tail = "" if ok else (r.stdout[-3000:] + r.stderr[-1500:])
@@ -18,6 +18,9 @@ for tid in ids:
         ok, tail = False, "TIMEOUT"
     summary.append((tid, ok))
     print(("PASS " if ok else "FAIL ") + tid, flush=True)
+    for line in r.stdout.splitlines() if ok else []:
+        if line.startswith("["):
+            print("    " + line, flush=True)
     if not ok:
         print(tail, flush=True)
 print("\n==== summary: %d/%d passed" % (sum(1 for _, o in summary if o), len(summary)))
