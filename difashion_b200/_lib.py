@@ -73,6 +73,8 @@ _PROTOTYPES = {
     "dfb_last_error": (C.c_char_p, []),
     "dfb_abi_version": (C.c_int, []),
     "dfb_num_sms": (C.c_int, []),
+    "dfb_sizeof_gemm_params": (C.c_size_t, []),
+    "dfb_sizeof_attn_params": (C.c_size_t, []),
     "dfb_gemm": (C.c_int, [C.POINTER(GemmParams), C.c_void_p]),
     "dfb_attention": (C.c_int, [C.POINTER(AttnParams), C.c_void_p]),
     "dfb_groupnorm_ws_floats": (C.c_size_t, [C.c_int, C.c_int]),

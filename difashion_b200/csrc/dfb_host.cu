@@ -101,4 +101,7 @@ int dfb_abi_version(void) { return DFB200_ABI_VERSION; }
 
 int dfb_num_sms(void) { return dfb::num_sms(); }
 
+size_t dfb_sizeof_gemm_params(void) { return sizeof(dfb_gemm_params); }
+size_t dfb_sizeof_attn_params(void) { return sizeof(dfb_attn_params); }
+
 }  // extern "C"

