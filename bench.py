@@ -285,10 +285,14 @@ def main():
         for kind, (ms, fl, cnt) in sorted(kinds.items()):
             print(f"# {kind:10s} launches={cnt:4d} ms={ms:9.3f} executed TFLOP/s={fl / (ms / 1e3) / 1e12 if ms else 0:8.1f}", file=sys.stderr)
         print(f"# eager step {eager_ms:.3f} ms; graph step {ms_per_step:.3f} ms", file=sys.stderr)
-        big = sorted(prof, key=lambda r: -r[3].elapsed_time(r[4]))[:25]
-        for kind, flops, shape, a, b in big:
-            ms = a.elapsed_time(b)
-            print(f"#   {kind:9s} {str(shape):34s} {ms:8.3f} ms {flops / (ms / 1e3) / 1e12:8.1f} TFLOP/s", file=sys.stderr)
+        agg = {}
+        for kind, flops, shape, a, b in prof:
+            d = agg.setdefault((kind, shape), [0.0, 0.0, 0])
+            d[0] += a.elapsed_time(b)
+            d[1] += flops
+            d[2] += 1
+        for (kind, shape), (ms, fl, cnt) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:40]:
+            print(f"#   {kind:9s} {str(shape):34s} x{cnt:<3d} {ms:8.3f} ms {fl / (ms / 1e3) / 1e12:8.1f} TFLOP/s", file=sys.stderr)
     del pipe_eager, st2
 
     # ---------------- end-to-end through the public API with host buffers ----------------

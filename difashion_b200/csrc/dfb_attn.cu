@@ -47,7 +47,10 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(ATT_THREADS)
+// KV_STATIC > 0: block_kv == KV_STATIC, the score row is held in registers (one TMEM pass);
+// KV_STATIC == 0: any block_kv (multiple of 16), two TMEM passes (max, then exponentials).
+template <int KV_STATIC>
+__global__ void __launch_bounds__(ATT_THREADS, KV_STATIC == 0 ? 1 : 2)
 attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -171,6 +174,66 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ A
       mbar_wait(s_full, (uint32_t)j & 1u);
       tc_fence_after();
       const int kv_valid = min(p.block_kv, p.Skv - j * p.block_kv);
+      if constexpr (KV_STATIC > 0) {
+        // ---- single pass: whole score row in registers ----
+        uint32_t sreg[KV_STATIC];
+#pragma unroll
+        for (int c = 0; c < KV_STATIC / 32; ++c)
+          tmem_ld_32x32b_x32(tmem_S + lane_addr + (uint32_t)(c * 32), *reinterpret_cast<uint32_t(*)[32]>(&sreg[c * 32]));
+        tmem_ld_wait();
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        if (kv_valid == KV_STATIC) {
+#pragma unroll
+          for (int i = 0; i < KV_STATIC; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(sreg[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < KV_STATIC; ++i)
+            if (i < kv_valid) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(sreg[i]));
+        }
+        const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * p.scale_log2;
+        const bool need = mx > m_ref + 8.0f;
+        const bool need_any = __any_sync(0xffffffffu, need);
+        if (j > 0) {
+          mbar_wait(o_done, (uint32_t)(j - 1) & 1u);   // PV_{j-1} retired: P buffer free, O stable
+          tc_fence_after();
+        }
+        if (need_any) {
+          const float m_new = need ? mx : m_ref;
+          const float alpha = ex2f(m_ref - m_new);     // m_ref = -inf on the first tile -> 0
+          if (j > 0) {
+            for (int c = 0; c < dchunks; ++c) {
+              uint32_t r[16];
+              tmem_ld_32x32b_x16(tmem_O + lane_addr + (uint32_t)(c * 16), r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+              tmem_st_32x32b_x16(tmem_O + lane_addr + (uint32_t)(c * 16), r);
+            }
+            tmem_st_wait();
+          }
+          l *= alpha;
+          m_ref = m_new;
+        }
+        float l4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < KV_STATIC / 16; ++c) {
+          float pv[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float e = ex2f(fmaf(__uint_as_float(sreg[c * 16 + i]), p.scale_log2, -m_ref));
+            pv[i] = (kv_valid == KV_STATIC || c * 16 + i < kv_valid) ? e : 0.f;
+            l4[i & 3] += pv[i];
+          }
+          const uint32_t dst = p_row + (uint32_t)c * ATT_BLOCK_Q * 32u;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (0u ^ flip)), "r"(pack_bf16x2(pv[0], pv[1])),
+                       "r"(pack_bf16x2(pv[2], pv[3])), "r"(pack_bf16x2(pv[4], pv[5])), "r"(pack_bf16x2(pv[6], pv[7]))
+                       : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (16u ^ flip)), "r"(pack_bf16x2(pv[8], pv[9])),
+                       "r"(pack_bf16x2(pv[10], pv[11])), "r"(pack_bf16x2(pv[12], pv[13])), "r"(pack_bf16x2(pv[14], pv[15]))
+                       : "memory");
+        }
+        l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+      } else {
       float mx = -INFINITY;
       for (int c = 0; c < kv_chunks; ++c) {
         uint32_t r[16];
@@ -222,6 +285,7 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ A
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (16u ^ flip)), "r"(pack_bf16x2(pv[8], pv[9])),
                      "r"(pack_bf16x2(pv[10], pv[11])), "r"(pack_bf16x2(pv[12], pv[13])), "r"(pack_bf16x2(pv[14], pv[15]))
                      : "memory");
+      }
       }
       fence_proxy_async_smem();     // generic-proxy P writes -> visible to the tensor core's async proxy
       tc_fence_before();
@@ -329,11 +393,18 @@ extern "C" int dfb_attention(const dfb_attn_params* a, void* stream_) {
   int dev = 0;
   DFB_CHECK_CUDA(cudaGetDevice(&dev));
   if (dev >= 0 && dev < 64 && smem > max_set[dev]) {
-    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
     max_set[dev] = 227 * 1024;
   }
   dim3 grid((a->Sq + ATT_BLOCK_Q - 1) / ATT_BLOCK_Q, a->heads, a->B);
-  attn_fwd_kernel<<<grid, ATT_THREADS, smem, stream>>>(maps, kp);
+  if (bkv == 128)
+    attn_fwd_kernel<128><<<grid, ATT_THREADS, smem, stream>>>(maps, kp);
+  else if (bkv == 64)
+    attn_fwd_kernel<64><<<grid, ATT_THREADS, smem, stream>>>(maps, kp);
+  else
+    attn_fwd_kernel<0><<<grid, ATT_THREADS, smem, stream>>>(maps, kp);
   DFB_CHECK_CUDA(cudaGetLastError());
   return DFB_OK;
 }

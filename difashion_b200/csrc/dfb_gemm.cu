@@ -3,8 +3,9 @@
 //   warp 0      : TMA producer  (A tile 128x64 bf16 via 2-D or 4-D tiled tensor map, OOB = zero
 //                 gives the 3x3 'same' padding for free; B tile block_n x 64)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=block_n, K=16)
-//   warps 2..5  : epilogue (tcgen05.ld -> fp32 registers -> bias / time-embedding row bias /
-//                 residual / GEGLU -> bf16 or fp32 global stores)
+//   warps 2..9  : epilogue (tcgen05.ld -> registers -> swizzled smem transpose -> row-coalesced
+//                 bias / time-embedding row bias / activation / residual / GEGLU -> bf16 or fp32
+//                 global stores touching full 128-byte rows)
 //
 // Pipelines: STAGES-deep smem ring (full/empty mbarriers) between TMA and MMA, and a 2-deep TMEM
 // accumulator ring (tmem_full/tmem_empty) between MMA and epilogue, so the epilogue of tile i
@@ -24,8 +25,10 @@ constexpr int GEMM_MAX_BLOCK_N = 256;
 constexpr int GEMM_A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;          // 16 KB
 constexpr int GEMM_B_BYTES = GEMM_MAX_BLOCK_N * GEMM_BLOCK_K * 2;      // 32 KB (max)
 constexpr int GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES;          // 48 KB
-constexpr int GEMM_THREADS = 192;
-constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_EPI_STAGE_BYTES = 4096;                              // per-warp 32x32 fp32 transpose tile
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
+constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int GEMM_TMEM_COLS = 512;
 
 struct GemmMaps {
@@ -53,7 +56,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ GemmKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + GEMM_STAGES * GEMM_STAGE_BYTES;
+  const uint32_t bar_base = smem_base + GEMM_STAGES * GEMM_STAGE_BYTES + GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES;
   // barrier layout (8 bytes each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (GEMM_STAGES + s); };
@@ -76,7 +79,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);   // one arrive per epilogue warp
+      mbar_init(tempty_bar(s), GEMM_EPI_WARPS);   // one arrive per epilogue warp
     }
     fence_mbar_init();
     fence_proxy_async_smem();
@@ -161,9 +164,15 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
       }
     }
   } else {
-    // ===================== epilogue warps (2..5) =====================
+    // ===================== epilogue warps (2..9) =====================
+    // Two warps per TMEM lane quarter; each takes every other 32-column chunk.  Accumulators go
+    // TMEM -> registers (thread = row) -> a per-warp swizzled smem tile -> registers in a
+    // row-coalesced layout (8 lanes x 16 B per row), where bias / time-embedding row bias /
+    // activation / residual are applied and global memory is touched with full 128-byte rows.
+    const int ew = warp - 2;
     const int quarter = warp & 3;              // TMEM lane quarter this warp may access
-    const int row = quarter * 32 + lane;
+    const int half = ew >> 2;
+    const uint32_t stg = smem_base + GEMM_STAGES * GEMM_STAGE_BYTES + (uint32_t)ew * GEMM_EPI_STAGE_BYTES;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int mt = tile / p.n_tiles_n;
@@ -172,134 +181,142 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
-      const int m = mt * GEMM_BLOCK_M + row;
-      const bool m_ok = m < p.M;
+      const int row0 = mt * GEMM_BLOCK_M + quarter * 32;
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * GEMM_MAX_BLOCK_N;
-      const float* rb = (p.rowbias && m_ok) ? p.rowbias + (size_t)(m / p.rows_per_batch) * p.rowbias_ld : nullptr;
-      for (int c = 0; c < p.block_n / 32; ++c) {
+      for (int c = half; c < p.block_n / 32; c += 2) {
         const int n0 = nt * p.block_n + c * 32;
         if (n0 >= p.N) break;                  // warp-uniform
         uint32_t r[32];
         tmem_ld_32x32b_x32(taddr0 + (uint32_t)(c * 32), r);
         tmem_ld_wait();
-        if (!m_ok) continue;
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        const int nvalid = min(32, p.N - n0);
-        if (p.bias) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < nvalid) v[j] += __ldg(p.bias + n0 + j);
-        }
-        if (rb) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < nvalid) v[j] += __ldg(rb + n0 + j);
-        }
-        if (p.act) {
-          if (p.act == DFB_ACT_SILU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
-          } else if (p.act == DFB_ACT_LEAKY_RELU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.01f * v[j];
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
-          }
-        }
         if (p.geglu) {
-          // columns [0,16) = values, [16,32) = gates of output columns n0/2 .. n0/2+15
+          // row layout: columns [0,16) = values, [16,32) = gates of output columns n0/2 .. n0/2+15
           float o[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) o[j] = v[j] * gelu_erf_f(v[16 + j]);
-          const size_t off = (size_t)m * p.out_ld + (n0 >> 1);
+          for (int j = 0; j < 16; ++j) {
+            const float a = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + n0 + j) : 0.f);
+            const float g = __uint_as_float(r[16 + j]) + (p.bias ? __ldg(p.bias + n0 + 16 + j) : 0.f);
+            o[j] = a * gelu_fast_f(g);
+          }
+          // staging tile [32 rows][64 B], 64-byte swizzle
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t dst = stg + (uint32_t)lane * 64u + (uint32_t)((u ^ ((lane >> 1) & 3)) << 4);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(o[4 * u]), "f"(o[4 * u + 1]),
+                         "f"(o[4 * u + 2]), "f"(o[4 * u + 3]) : "memory");
+          }
+          __syncwarp();
+          const int u = lane & 3;
+          const int colo = (n0 >> 1) + 4 * u;
+#pragma unroll
+          for (int itr = 0; itr < 4; ++itr) {
+            const int rr = itr * 8 + (lane >> 2);
+            const int m = row0 + rr;
+            float4 x;
+            const uint32_t src = stg + (uint32_t)rr * 64u + (uint32_t)((u ^ ((rr >> 1) & 3)) << 4);
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(src));
+            if (m < p.M) {
+              const size_t off = (size_t)m * p.out_ld + colo;
+              if (p.out_fp32) {
+                float* dst = reinterpret_cast<float*>(p.out) + off;
+                if (p.vec_ok) *reinterpret_cast<float4*>(dst) = x;
+                else { dst[0] = x.x; dst[1] = x.y; dst[2] = x.z; dst[3] = x.w; }
+              } else {
+                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
+                if (p.vec_ok) *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
+                else { dst[0] = __float2bfloat16(x.x); dst[1] = __float2bfloat16(x.y); dst[2] = __float2bfloat16(x.z); dst[3] = __float2bfloat16(x.w); }
+              }
+            }
+          }
+          __syncwarp();
+          continue;
+        }
+        // staging tile [32 rows][128 B], 128-byte swizzle
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const uint32_t dst = stg + (uint32_t)lane * 128u + (uint32_t)((u ^ (lane & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(r[4 * u]), "r"(r[4 * u + 1]),
+                       "r"(r[4 * u + 2]), "r"(r[4 * u + 3]) : "memory");
+        }
+        __syncwarp();
+        const int u = lane & 7;
+        const int col = n0 + 4 * u;
+        const int nval = p.N - col;             // > 0 valid columns of this lane's 4
+        float b4[4] = {0.f, 0.f, 0.f, 0.f};
+        if (p.bias && nval > 0) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (e < nval) b4[e] = __ldg(p.bias + col + e);
+        }
+        const bool vec = p.vec_ok && nval >= 4;
+#pragma unroll
+        for (int itr = 0; itr < 8; ++itr) {
+          const int rr = itr * 4 + (lane >> 3);
+          const int m = row0 + rr;
+          float x[4];
+          const uint32_t src = stg + (uint32_t)rr * 128u + (uint32_t)((u ^ (rr & 7)) << 4);
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[0]), "=f"(x[1]), "=f"(x[2]), "=f"(x[3]) : "r"(src));
+          if (m >= p.M || nval <= 0) continue;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) x[e] += b4[e];
+          if (p.rowbias) {
+            const float* rb = p.rowbias + (size_t)(m / p.rows_per_batch) * p.rowbias_ld + col;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (e < nval) x[e] += __ldg(rb + e);
+          }
+          if (p.act) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (p.act == DFB_ACT_SILU) x[e] = silu_f(x[e]);
+              else if (p.act == DFB_ACT_LEAKY_RELU) x[e] = x[e] > 0.f ? x[e] : 0.01f * x[e];
+              else x[e] = tanhf(x[e]);
+            }
+          }
+          if (p.residual) {
+            const size_t roff = (size_t)m * p.res_ld + col;
+            if (p.res_fp32) {
+              const float* rs = reinterpret_cast<const float*>(p.residual) + roff;
+              if (vec) {
+                const float4 t = *reinterpret_cast<const float4*>(rs);
+                x[0] += t.x; x[1] += t.y; x[2] += t.z; x[3] += t.w;
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (e < nval) x[e] += rs[e];
+              }
+            } else {
+              const __nv_bfloat16* rs = reinterpret_cast<const __nv_bfloat16*>(p.residual) + roff;
+              if (vec) {
+                const uint2 t = *reinterpret_cast<const uint2*>(rs);
+                x[0] += bf16_lo(t.x); x[1] += bf16_hi(t.x); x[2] += bf16_lo(t.y); x[3] += bf16_hi(t.y);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (e < nval) x[e] += __bfloat162float(rs[e]);
+              }
+            }
+          }
+          const size_t off = (size_t)m * p.out_ld + col;
           if (p.out_fp32) {
             float* dst = reinterpret_cast<float*>(p.out) + off;
-            if (p.vec_ok) {
+            if (vec) *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
+            else {
 #pragma unroll
-              for (int j = 0; j < 16; j += 4)
-                *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) dst[j] = o[j];
+              for (int e = 0; e < 4; ++e)
+                if (e < nval) dst[e] = x[e];
             }
           } else {
             __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
-            if (p.vec_ok) {
+            if (vec) *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]));
+            else {
 #pragma unroll
-              for (int j = 0; j < 16; j += 8)
-                *reinterpret_cast<uint4*>(dst + j) =
-                    make_uint4(pack_bf16x2(o[j], o[j + 1]), pack_bf16x2(o[j + 2], o[j + 3]),
-                               pack_bf16x2(o[j + 4], o[j + 5]), pack_bf16x2(o[j + 6], o[j + 7]));
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) dst[j] = __float2bfloat16(o[j]);
-            }
-          }
-          continue;
-        }
-        const bool fast = p.vec_ok && nvalid == 32;
-        if (p.residual) {
-          const size_t roff = (size_t)m * p.res_ld + n0;
-          if (p.res_fp32) {
-            const float* rs = reinterpret_cast<const float*>(p.residual) + roff;
-            if (fast) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 t = *reinterpret_cast<const float4*>(rs + j);
-                v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < nvalid) v[j] += rs[j];
-            }
-          } else {
-            const __nv_bfloat16* rs = reinterpret_cast<const __nv_bfloat16*>(p.residual) + roff;
-            if (fast) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                const uint4 t = *reinterpret_cast<const uint4*>(rs + j);
-                v[j] += bf16_lo(t.x); v[j + 1] += bf16_hi(t.x);
-                v[j + 2] += bf16_lo(t.y); v[j + 3] += bf16_hi(t.y);
-                v[j + 4] += bf16_lo(t.z); v[j + 5] += bf16_hi(t.z);
-                v[j + 6] += bf16_lo(t.w); v[j + 7] += bf16_hi(t.w);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < nvalid) v[j] += __bfloat162float(rs[j]);
+              for (int e = 0; e < 4; ++e)
+                if (e < nval) dst[e] = __float2bfloat16(x[e]);
             }
           }
         }
-        const size_t off = (size_t)m * p.out_ld + n0;
-        if (p.out_fp32) {
-          float* dst = reinterpret_cast<float*>(p.out) + off;
-          if (fast) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < nvalid) dst[j] = v[j];
-          }
-        } else {
-          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
-          if (fast) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8)
-              *reinterpret_cast<uint4*>(dst + j) =
-                  make_uint4(pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]),
-                             pack_bf16x2(v[j + 4], v[j + 5]), pack_bf16x2(v[j + 6], v[j + 7]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < nvalid) dst[j] = __float2bfloat16(v[j]);
-          }
-        }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();

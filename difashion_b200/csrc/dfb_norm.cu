@@ -106,41 +106,49 @@ __global__ void groupnorm_finalize_kernel(const float* __restrict__ partial, int
 }
 
 // y = (x - mean) * rstd * gamma + beta (optionally SiLU) -> bf16 [B, HW, C] (ld_out), optional raw
-// bf16 copy of x (A operand of the 1x1 shortcut folded into conv2).
+// bf16 copy of x (A operand of the 1x1 shortcut folded into conv2).  Same thread mapping as the
+// statistics kernel: a thread owns fixed channel vectors, so gamma/beta/mean/rstd are folded into a
+// per-thread (scale, shift) once and the pixel loop is load -> FMA -> SiLU -> store (no index math).
 __global__ void __launch_bounds__(GN_THREADS)
 groupnorm_apply_kernel(const float* __restrict__ src0, int c0, int ld0, const float* __restrict__ src1, int c1, int ld1,
-                       int hw, int groups, float eps, const float* __restrict__ stats, const float* __restrict__ gamma,
-                       const float* __restrict__ beta, int silu, __nv_bfloat16* __restrict__ out, int ld_out,
-                       __nv_bfloat16* __restrict__ raw_out, int ld_raw, int B) {
+                       int hw, int groups, int pix_per_block, const float* __restrict__ stats,
+                       const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
+                       __nv_bfloat16* __restrict__ out, int ld_out, __nv_bfloat16* __restrict__ raw_out, int ld_raw) {
+  const int b = blockIdx.y;
   const int C = c0 + c1;
   const int cg = C / groups;
   const int nvec = C >> 2;
-  const long long total = (long long)B * hw * nvec;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int v = (int)(i % nvec);
-    const long long r = i / nvec;          // b * hw + px
-    const int b = (int)(r / hw);
+  const int p_begin = blockIdx.x * pix_per_block;
+  const int p_end = min(hw, p_begin + pix_per_block);
+  const int vlanes = nvec < GN_THREADS ? nvec : GN_THREADS;
+  const int plane_cnt = GN_THREADS / vlanes;
+  const int tv = threadIdx.x % vlanes;
+  const int tp = threadIdx.x / vlanes;
+  if (tp >= plane_cnt) return;
+  const float* st = stats + (size_t)b * groups * 2;
+  for (int v = tv; v < nvec; v += GN_THREADS) {
     const int c = v << 2;
     const float* base;
     int ld, cc;
     if (c < c0) { base = src0; ld = ld0; cc = c; } else { base = src1; ld = ld1; cc = c - c0; }
-    const float4 x = __ldg(reinterpret_cast<const float4*>(base + (size_t)r * ld + cc));
+    base += (size_t)b * hw * ld + cc;
     const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
     const float4 bt = __ldg(reinterpret_cast<const float4*>(beta + c));
     const int ga = c / cg, gb = (c + 2) / cg;
-    const float* st = stats + (size_t)b * groups * 2;
     const float ma = st[ga * 2], ra = st[ga * 2 + 1];
-    float mb = ma, rb = ra;
-    if (gb != ga) { mb = st[gb * 2]; rb = st[gb * 2 + 1]; }
-    float y0 = (x.x - ma) * ra * g.x + bt.x;
-    float y1 = (x.y - ma) * ra * g.y + bt.y;
-    float y2 = (x.z - mb) * rb * g.z + bt.z;
-    float y3 = (x.w - mb) * rb * g.w + bt.w;
-    if (silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
-    *reinterpret_cast<uint2*>(out + (size_t)r * ld_out + c) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
-    if (raw_out)
-      *reinterpret_cast<uint2*>(raw_out + (size_t)r * ld_raw + c) = make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
+    const float mb = st[gb * 2], rb = st[gb * 2 + 1];
+    const float s0 = ra * g.x, s1 = ra * g.y, s2 = rb * g.z, s3 = rb * g.w;
+    const float h0 = bt.x - ma * s0, h1 = bt.y - ma * s1, h2 = bt.z - mb * s2, h3 = bt.w - mb * s3;
+    __nv_bfloat16* o = out + (size_t)b * hw * ld_out + c;
+    __nv_bfloat16* ro = raw_out ? raw_out + (size_t)b * hw * ld_raw + c : nullptr;
+#pragma unroll 4
+    for (int px = p_begin + tp; px < p_end; px += plane_cnt) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(base + (size_t)px * ld));
+      float y0 = fmaf(x.x, s0, h0), y1 = fmaf(x.y, s1, h1), y2 = fmaf(x.z, s2, h2), y3 = fmaf(x.w, s3, h3);
+      if (silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
+      *reinterpret_cast<uint2*>(o + (size_t)px * ld_out) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+      if (ro) *reinterpret_cast<uint2*>(ro + (size_t)px * ld_raw) = make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
+    }
   }
 }
 
@@ -148,8 +156,7 @@ groupnorm_apply_kernel(const float* __restrict__ src0, int c0, int ld0, const fl
 // LayerNorm over the last dim: one warp per row, row held in registers (C <= 2048), two-pass
 // (mean, then centred variance) in fp32; bf16 output.
 // ---------------------------------------------------------------------------------------------
-constexpr int LN_MAX_VEC = 16;   // float4 per lane -> C <= 2048
-
+template <int LN_MAX_VEC>   // float4 per lane -> C <= 128 * LN_MAX_VEC
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, int ld_x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  float eps, __nv_bfloat16* __restrict__ out, int ld_out, int rows, int C) {
@@ -240,26 +247,35 @@ int dfb_groupnorm(const float* src0, int c0, int ld0, const float* src1, int c1,
     groupnorm_finalize_kernel<<<blocks, threads, 0, stream>>>(partial, chunks, groups, B, inv_n, eps, stats);
     DFB_CHECK_CUDA(cudaGetLastError());
   }
-  const long long total = (long long)B * hw * (Cch / 4);
-  long long blocks = (total + GN_THREADS - 1) / GN_THREADS;
-  const long long cap = (long long)num_sms() * 16;
-  if (blocks > cap) blocks = cap;
-  groupnorm_apply_kernel<<<(int)blocks, GN_THREADS, 0, stream>>>(src0, c0, ld0, src1, c1, ld1, hw, groups, eps, stats, gamma,
-                                                                beta, silu, (__nv_bfloat16*)out_bf16, ld_out,
-                                                                (__nv_bfloat16*)raw_out_bf16, ld_raw, B);
-  DFB_CHECK_CUDA(cudaGetLastError());
+  {
+    // apply: ~8 resident CTAs per SM over (B x pixel chunks)
+    int ach = (num_sms() * 16 + B - 1) / B;
+    if (ach > hw) ach = hw;
+    if (ach < 1) ach = 1;
+    const int appb = (hw + ach - 1) / ach;
+    ach = (hw + appb - 1) / appb;
+    groupnorm_apply_kernel<<<dim3(ach, B), GN_THREADS, 0, stream>>>(src0, c0, ld0, src1, c1, ld1, hw, groups, appb, stats, gamma,
+                                                                    beta, silu, (__nv_bfloat16*)out_bf16, ld_out,
+                                                                    (__nv_bfloat16*)raw_out_bf16, ld_raw);
+    DFB_CHECK_CUDA(cudaGetLastError());
+  }
   return DFB_OK;
 }
 
 int dfb_layernorm(const float* x, int ld_x, const float* gamma, const float* beta, float eps, void* out_bf16, int ld_out,
                   int rows, int Cch, void* stream) {
   DFB_REQUIRE(x && gamma && beta && out_bf16, "dfb_layernorm: null buffer");
-  DFB_REQUIRE(rows > 0 && Cch > 0 && Cch % 4 == 0 && Cch <= LN_MAX_VEC * 128, "dfb_layernorm: C must be a multiple of 4, <= 2048");
+  DFB_REQUIRE(rows > 0 && Cch > 0 && Cch % 4 == 0 && Cch <= 2048, "dfb_layernorm: C must be a multiple of 4, <= 2048");
   DFB_REQUIRE(ld_x % 4 == 0 && ld_out % 4 == 0, "dfb_layernorm: pitches must be multiples of 4");
   long long blocks = ((long long)rows + 7) / 8;
-  const long long cap = (long long)num_sms() * 8;
+  const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  layernorm_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, ld_x, gamma, beta, eps, (__nv_bfloat16*)out_bf16, ld_out, rows, Cch);
+  cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16* o = (__nv_bfloat16*)out_bf16;
+  if (Cch <= 384) layernorm_kernel<3><<<(int)blocks, 256, 0, st>>>(x, ld_x, gamma, beta, eps, o, ld_out, rows, Cch);
+  else if (Cch <= 640) layernorm_kernel<5><<<(int)blocks, 256, 0, st>>>(x, ld_x, gamma, beta, eps, o, ld_out, rows, Cch);
+  else if (Cch <= 1280) layernorm_kernel<10><<<(int)blocks, 256, 0, st>>>(x, ld_x, gamma, beta, eps, o, ld_out, rows, Cch);
+  else layernorm_kernel<16><<<(int)blocks, 256, 0, st>>>(x, ld_x, gamma, beta, eps, o, ld_out, rows, Cch);
   DFB_CHECK_CUDA(cudaGetLastError());
   return DFB_OK;
 }
