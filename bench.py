@@ -115,6 +115,14 @@ def cpu_oracle_sample(rows: int, threads: int):
     return dt
 
 
+def workload_config(args, world):
+    rows = args.outfits * ROWS_PER_OUTFIT
+    return {"workload": f"GOR generation: 50-step DDIM + 4-branch CFG, {args.outfits} outfits x 4 items per GPU "
+                        f"({rows} UNet rows/step), SD-1.5-shaped UNet (in_channels 8, S_kv {args.skv}), random-init weights",
+            "outfits_per_gpu": args.outfits, "unet_rows_per_step": rows, "ddim_steps": DDIM_STEPS,
+            "parallelism": f"outfit-sharded replicas x{world}, no in-loop collective"}
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference path's CPU implementation (oracle port) on the host cores."""
     if rank != 0:
@@ -150,7 +158,7 @@ def run_reference(args, rank, world):
             return out
 
     t_start = time.perf_counter()
-    oracle_generation(_Timed(), me, sched, **inp, num_inference_steps=DDIM_STEPS, max_steps=total_steps, **scales)
+    oracle_generation(_Timed(), me, sched, **inp, num_inference_steps=max(DDIM_STEPS, total_steps), max_steps=total_steps, **scales)
     marks = [t_start] + t_marks
     dt = marks[-1] - marks[args.warmup]
     ms_per_step = dt / args.steps * 1e3
@@ -160,8 +168,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "outfits/sec (4x512px, 50-step DDIM+CFG)", "value": value, "unit": "outfits/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "GOR generation, 50-step DDIM + 4-branch CFG, SD-1.5-shaped UNet (in_channels 8), "
-                               "random-init weights; CPU sample extrapolated per UNet row"},
+        "config": dict(workload_config(args, world), reference_note="CPU arm runs a bounded per-row sample of this workload"),
         "cpu_baseline": {"value": value, "unit": "outfits/s", "cores": threads, "kind": "port",
                          "sample": f"{args.steps} denoising steps x {rows_per_step} UNet row(s) of one FITB outfit "
                                    f"(oracle fp32 port of the diffusers path; the reference itself needs diffusers, "
@@ -346,12 +353,9 @@ def main():
         "metric": "outfits/sec (4x512px, 50-step DDIM+CFG)", "value": value, "unit": "outfits/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"GOR generation: 50-step DDIM + 4-branch CFG, {args.outfits} outfits x 4 items per GPU "
-                               f"({rows} UNet rows/step), SD-1.5-shaped UNet (in_channels 8, S_kv {args.skv}), random-init weights",
-                   "outfits_per_gpu": args.outfits, "unet_rows_per_step": rows, "ddim_steps": DDIM_STEPS,
-                   "parallelism": f"outfit-sharded replicas x{world}, no in-loop collective",
-                   "l2": "inputs larger than L2: each step streams 1.7 GB of weights + multi-GB activations (126 MB L2)",
-                   "unet_step_ms": ms_per_step},
+        "config": dict(workload_config(args, world),
+                       l2="inputs larger than L2: each step streams 1.7 GB of weights + multi-GB activations (126 MB L2)",
+                       unet_step_ms=ms_per_step),
         "clocks": sampler.summary(), "gpu_launches": launches_per_step * args.steps,
         "launches_per_step": launches_per_step, "roofline": roofline,
     }

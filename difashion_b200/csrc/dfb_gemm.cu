@@ -186,6 +186,48 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
       for (int c = half; c < p.block_n / 32; c += 2) {
         const int n0 = nt * p.block_n + c * 32;
         if (n0 >= p.N) break;                  // warp-uniform
+        // ---- prefetch everything this chunk reads from global memory (row-coalesced layout) ----
+        const int u = lane & 7;
+        const int col = n0 + 4 * u;
+        const int nval = p.N - col;             // > 0: valid columns among this lane's 4
+        const bool vec = p.vec_ok && nval >= 4;
+        float4 resv[8];
+        float b4[4] = {0.f, 0.f, 0.f, 0.f};
+        float rb4[4] = {0.f, 0.f, 0.f, 0.f};
+        bool rb_uniform = false;
+        if (!p.geglu) {
+          if (p.residual && vec) {
+#pragma unroll
+            for (int itr = 0; itr < 8; ++itr) {
+              const int m = row0 + itr * 4 + (lane >> 3);
+              resv[itr] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (m < p.M) {
+                const size_t roff = (size_t)m * p.res_ld + col;
+                if (p.res_fp32) {
+                  resv[itr] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + roff));
+                } else {
+                  const uint2 t = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) + roff));
+                  resv[itr] = make_float4(bf16_lo(t.x), bf16_hi(t.x), bf16_lo(t.y), bf16_hi(t.y));
+                }
+              }
+            }
+          }
+          if (p.bias && nval > 0) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (e < nval) b4[e] = __ldg(p.bias + col + e);
+          }
+          if (p.rowbias && nval > 0) {
+            const int mlast = min(row0 + 31, p.M - 1);
+            rb_uniform = row0 < p.M && (row0 / p.rows_per_batch) == (mlast / p.rows_per_batch);   // warp-uniform
+            if (rb_uniform) {
+              const float* rb = p.rowbias + (size_t)(row0 / p.rows_per_batch) * p.rowbias_ld + col;
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (e < nval) rb4[e] = __ldg(rb + e);
+            }
+          }
+        }
         uint32_t r[32];
         tmem_ld_32x32b_x32(taddr0 + (uint32_t)(c * 32), r);
         tmem_ld_wait();
@@ -200,20 +242,20 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
           }
           // staging tile [32 rows][64 B], 64-byte swizzle
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const uint32_t dst = stg + (uint32_t)lane * 64u + (uint32_t)((u ^ ((lane >> 1) & 3)) << 4);
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(o[4 * u]), "f"(o[4 * u + 1]),
-                         "f"(o[4 * u + 2]), "f"(o[4 * u + 3]) : "memory");
+          for (int u2 = 0; u2 < 4; ++u2) {
+            const uint32_t dst = stg + (uint32_t)lane * 64u + (uint32_t)((u2 ^ ((lane >> 1) & 3)) << 4);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(o[4 * u2]), "f"(o[4 * u2 + 1]),
+                         "f"(o[4 * u2 + 2]), "f"(o[4 * u2 + 3]) : "memory");
           }
           __syncwarp();
-          const int u = lane & 3;
-          const int colo = (n0 >> 1) + 4 * u;
+          const int ug = lane & 3;
+          const int colo = (n0 >> 1) + 4 * ug;
 #pragma unroll
           for (int itr = 0; itr < 4; ++itr) {
             const int rr = itr * 8 + (lane >> 2);
             const int m = row0 + rr;
             float4 x;
-            const uint32_t src = stg + (uint32_t)rr * 64u + (uint32_t)((u ^ ((rr >> 1) & 3)) << 4);
+            const uint32_t src = stg + (uint32_t)rr * 64u + (uint32_t)((ug ^ ((rr >> 1) & 3)) << 4);
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(src));
             if (m < p.M) {
               const size_t off = (size_t)m * p.out_ld + colo;
@@ -231,24 +273,16 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
           __syncwarp();
           continue;
         }
+        // (reached only for the non-GEGLU path; the residual / bias prefetch for this chunk was issued
+        //  above, before the TMEM load, so its HBM latency overlaps the TMEM read and the transpose)
         // staging tile [32 rows][128 B], 128-byte swizzle
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const uint32_t dst = stg + (uint32_t)lane * 128u + (uint32_t)((u ^ (lane & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(r[4 * u]), "r"(r[4 * u + 1]),
-                       "r"(r[4 * u + 2]), "r"(r[4 * u + 3]) : "memory");
+        for (int u2 = 0; u2 < 8; ++u2) {
+          const uint32_t dst = stg + (uint32_t)lane * 128u + (uint32_t)((u2 ^ (lane & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(r[4 * u2]), "r"(r[4 * u2 + 1]),
+                       "r"(r[4 * u2 + 2]), "r"(r[4 * u2 + 3]) : "memory");
         }
         __syncwarp();
-        const int u = lane & 7;
-        const int col = n0 + 4 * u;
-        const int nval = p.N - col;             // > 0 valid columns of this lane's 4
-        float b4[4] = {0.f, 0.f, 0.f, 0.f};
-        if (p.bias && nval > 0) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (e < nval) b4[e] = __ldg(p.bias + col + e);
-        }
-        const bool vec = p.vec_ok && nval >= 4;
 #pragma unroll
         for (int itr = 0; itr < 8; ++itr) {
           const int rr = itr * 4 + (lane >> 3);
@@ -260,10 +294,15 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
 #pragma unroll
           for (int e = 0; e < 4; ++e) x[e] += b4[e];
           if (p.rowbias) {
-            const float* rb = p.rowbias + (size_t)(m / p.rows_per_batch) * p.rowbias_ld + col;
+            if (rb_uniform) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (e < nval) x[e] += __ldg(rb + e);
+              for (int e = 0; e < 4; ++e) x[e] += rb4[e];
+            } else {
+              const float* rb = p.rowbias + (size_t)(m / p.rows_per_batch) * p.rowbias_ld + col;
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (e < nval) x[e] += __ldg(rb + e);
+            }
           }
           if (p.act) {
 #pragma unroll
@@ -274,27 +313,15 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
             }
           }
           if (p.residual) {
-            const size_t roff = (size_t)m * p.res_ld + col;
-            if (p.res_fp32) {
-              const float* rs = reinterpret_cast<const float*>(p.residual) + roff;
-              if (vec) {
-                const float4 t = *reinterpret_cast<const float4*>(rs);
-                x[0] += t.x; x[1] += t.y; x[2] += t.z; x[3] += t.w;
-              } else {
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                  if (e < nval) x[e] += rs[e];
-              }
+            if (vec) {
+              x[0] += resv[itr].x; x[1] += resv[itr].y; x[2] += resv[itr].z; x[3] += resv[itr].w;
             } else {
-              const __nv_bfloat16* rs = reinterpret_cast<const __nv_bfloat16*>(p.residual) + roff;
-              if (vec) {
-                const uint2 t = *reinterpret_cast<const uint2*>(rs);
-                x[0] += bf16_lo(t.x); x[1] += bf16_hi(t.x); x[2] += bf16_lo(t.y); x[3] += bf16_hi(t.y);
-              } else {
+              const size_t roff = (size_t)m * p.res_ld + col;
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                  if (e < nval) x[e] += __bfloat162float(rs[e]);
-              }
+              for (int e = 0; e < 4; ++e)
+                if (e < nval)
+                  x[e] += p.res_fp32 ? reinterpret_cast<const float*>(p.residual)[roff + e]
+                                     : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.residual)[roff + e]);
             }
           }
           const size_t off = (size_t)m * p.out_ld + col;
