@@ -175,64 +175,101 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ A
       tc_fence_after();
       const int kv_valid = min(p.block_kv, p.Skv - j * p.block_kv);
       if constexpr (KV_STATIC > 0) {
-        // ---- single pass: whole score row in registers ----
+        // ---- score row in registers.  Fast path: exponentials are computed OPTIMISTICALLY against the
+        // running reference max m_ref while the TMEM load of the next 32-column chunk is in flight
+        // (TMEM->RF bandwidth and the MUFU are both ~1 tile-time resources, so they must overlap);
+        // the tile max is tracked on the side and, when it exceeds m_ref by more than 2^8 (always on
+        // the first tile, rarely afterwards), the tile is redone from the registers with a new
+        // reference (careful path: O and l rescaled). ----
         uint32_t sreg[KV_STATIC];
-#pragma unroll
-        for (int c = 0; c < KV_STATIC / 32; ++c)
-          tmem_ld_32x32b_x32(tmem_S + lane_addr + (uint32_t)(c * 32), *reinterpret_cast<uint32_t(*)[32]>(&sreg[c * 32]));
-        tmem_ld_wait();
-        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        if (kv_valid == KV_STATIC) {
-#pragma unroll
-          for (int i = 0; i < KV_STATIC; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(sreg[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < KV_STATIC; ++i)
-            if (i < kv_valid) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(sreg[i]));
-        }
-        const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * p.scale_log2;
-        const bool need = mx > m_ref + 8.0f;
-        const bool need_any = __any_sync(0xffffffffu, need);
         if (j > 0) {
           mbar_wait(o_done, (uint32_t)(j - 1) & 1u);   // PV_{j-1} retired: P buffer free, O stable
           tc_fence_after();
         }
-        if (need_any) {
-          const float m_new = need ? mx : m_ref;
-          const float alpha = ex2f(m_ref - m_new);     // m_ref = -inf on the first tile -> 0
-          if (j > 0) {
-            for (int c = 0; c < dchunks; ++c) {
-              uint32_t r[16];
-              tmem_ld_32x32b_x16(tmem_O + lane_addr + (uint32_t)(c * 16), r);
-              tmem_ld_wait();
+        bool careful = (kv_valid != KV_STATIC) || (j == 0);
+        float mx = -INFINITY;
+        if (!careful) {
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+          float l4[4] = {0.f, 0.f, 0.f, 0.f};
+          tmem_ld_32x32b_x32(tmem_S + lane_addr, *reinterpret_cast<uint32_t(*)[32]>(&sreg[0]));
 #pragma unroll
-              for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-              tmem_st_32x32b_x16(tmem_O + lane_addr + (uint32_t)(c * 16), r);
+          for (int c = 0; c < KV_STATIC / 32; ++c) {
+            tmem_ld_wait();                                  // chunk c has landed
+            if (c + 1 < KV_STATIC / 32)
+              tmem_ld_32x32b_x32(tmem_S + lane_addr + (uint32_t)((c + 1) * 32),
+                                 *reinterpret_cast<uint32_t(*)[32]>(&sreg[(c + 1) * 32]));
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              float pv[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float sv = __uint_as_float(sreg[c * 32 + h * 16 + i]);
+                m4[i & 3] = fmaxf(m4[i & 3], sv);
+                pv[i] = ex2f(fmaf(sv, p.scale_log2, -m_ref));
+                l4[i & 3] += pv[i];
+              }
+              const uint32_t dst = p_row + (uint32_t)(c * 2 + h) * ATT_BLOCK_Q * 32u;
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (0u ^ flip)), "r"(pack_bf16x2(pv[0], pv[1])),
+                           "r"(pack_bf16x2(pv[2], pv[3])), "r"(pack_bf16x2(pv[4], pv[5])), "r"(pack_bf16x2(pv[6], pv[7]))
+                           : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (16u ^ flip)), "r"(pack_bf16x2(pv[8], pv[9])),
+                           "r"(pack_bf16x2(pv[10], pv[11])), "r"(pack_bf16x2(pv[12], pv[13])), "r"(pack_bf16x2(pv[14], pv[15]))
+                           : "memory");
             }
-            tmem_st_wait();
           }
-          l *= alpha;
-          m_ref = m_new;
+          mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * p.scale_log2;
+          careful = __any_sync(0xffffffffu, mx > m_ref + 8.0f);
+          if (!careful) l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < KV_STATIC / 32; ++c)
+            tmem_ld_32x32b_x32(tmem_S + lane_addr + (uint32_t)(c * 32), *reinterpret_cast<uint32_t(*)[32]>(&sreg[c * 32]));
+          tmem_ld_wait();
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int i = 0; i < KV_STATIC; ++i)
+            if (i < kv_valid) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(sreg[i]));
+          mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * p.scale_log2;
         }
-        float l4[4] = {0.f, 0.f, 0.f, 0.f};
+        if (careful) {
+          const bool need = mx > m_ref + 8.0f;
+          if (__any_sync(0xffffffffu, need)) {
+            const float m_new = need ? mx : m_ref;
+            const float alpha = ex2f(m_ref - m_new);     // m_ref = -inf on the first tile -> 0
+            if (j > 0) {
+              for (int c = 0; c < dchunks; ++c) {
+                uint32_t r[16];
+                tmem_ld_32x32b_x16(tmem_O + lane_addr + (uint32_t)(c * 16), r);
+                tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < KV_STATIC / 16; ++c) {
-          float pv[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float e = ex2f(fmaf(__uint_as_float(sreg[c * 16 + i]), p.scale_log2, -m_ref));
-            pv[i] = (kv_valid == KV_STATIC || c * 16 + i < kv_valid) ? e : 0.f;
-            l4[i & 3] += pv[i];
+                for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+                tmem_st_32x32b_x16(tmem_O + lane_addr + (uint32_t)(c * 16), r);
+              }
+              tmem_st_wait();
+            }
+            l *= alpha;
+            m_ref = m_new;
           }
-          const uint32_t dst = p_row + (uint32_t)c * ATT_BLOCK_Q * 32u;
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (0u ^ flip)), "r"(pack_bf16x2(pv[0], pv[1])),
-                       "r"(pack_bf16x2(pv[2], pv[3])), "r"(pack_bf16x2(pv[4], pv[5])), "r"(pack_bf16x2(pv[6], pv[7]))
-                       : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (16u ^ flip)), "r"(pack_bf16x2(pv[8], pv[9])),
-                       "r"(pack_bf16x2(pv[10], pv[11])), "r"(pack_bf16x2(pv[12], pv[13])), "r"(pack_bf16x2(pv[14], pv[15]))
-                       : "memory");
+          float l4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int c = 0; c < KV_STATIC / 16; ++c) {
+            float pv[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float e = ex2f(fmaf(__uint_as_float(sreg[c * 16 + i]), p.scale_log2, -m_ref));
+              pv[i] = (c * 16 + i < kv_valid) ? e : 0.f;
+              l4[i & 3] += pv[i];
+            }
+            const uint32_t dst = p_row + (uint32_t)c * ATT_BLOCK_Q * 32u;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (0u ^ flip)), "r"(pack_bf16x2(pv[0], pv[1])),
+                         "r"(pack_bf16x2(pv[2], pv[3])), "r"(pack_bf16x2(pv[4], pv[5])), "r"(pack_bf16x2(pv[6], pv[7]))
+                         : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (16u ^ flip)), "r"(pack_bf16x2(pv[8], pv[9])),
+                         "r"(pack_bf16x2(pv[10], pv[11])), "r"(pack_bf16x2(pv[12], pv[13])), "r"(pack_bf16x2(pv[14], pv[15]))
+                         : "memory");
+          }
+          l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
         }
-        l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
       } else {
       float mx = -INFINITY;
       for (int c = 0; c < kv_chunks; ++c) {

@@ -52,8 +52,14 @@ struct GemmKernelParams {
   int out_ld, out_fp32, geglu, vec_ok, act;
 };
 
+// Epilogue specialisations (compile-time, so the hot epilogue loop carries no runtime flag tests and the
+// kernel image stays small enough for the instruction cache); EPI_GENERIC keeps every option at run time.
+enum : int { EPI_OUT_F32 = 1, EPI_RES_F32 = 2, EPI_ROWBIAS = 4, EPI_GEGLU = 8, EPI_GENERIC = 16 };
+
+template <int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ GemmKernelParams p) {
+  constexpr bool kGeneric = (MODE & EPI_GENERIC) != 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + GEMM_STAGES * GEMM_STAGE_BYTES + GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES;
@@ -173,65 +179,32 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
     const int quarter = warp & 3;              // TMEM lane quarter this warp may access
     const int half = ew >> 2;
     const uint32_t stg = smem_base + GEMM_STAGES * GEMM_STAGE_BYTES + (uint32_t)ew * GEMM_EPI_STAGE_BYTES;
+    // run-time flags in generic mode, compile-time constants otherwise
+    const bool f_geglu = kGeneric ? (p.geglu != 0) : ((MODE & EPI_GEGLU) != 0);
+    const bool f_out32 = kGeneric ? (p.out_fp32 != 0) : ((MODE & EPI_OUT_F32) != 0);
+    const bool f_res = kGeneric ? (p.residual != nullptr) : ((MODE & EPI_RES_F32) != 0);
+    const bool f_res32 = kGeneric ? (p.res_fp32 != 0) : true;
+    const bool f_rowbias = kGeneric ? (p.rowbias != nullptr) : ((MODE & EPI_ROWBIAS) != 0);
+    const bool f_vec = kGeneric ? (p.vec_ok != 0) : true;       // specialised modes require aligned, N % 4 == 0
+    const int f_act = kGeneric ? p.act : 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int mt = tile / p.n_tiles_n;
       const int nt = tile - mt * p.n_tiles_n;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      mbar_wait(tfull_bar(as), aphase);
-      tc_fence_after();
       const int row0 = mt * GEMM_BLOCK_M + quarter * 32;
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * GEMM_MAX_BLOCK_N;
+      const bool full_rows = row0 + 32 <= p.M;                 // warp-uniform: no row masking needed
+      bool waited = false;
       for (int c = half; c < p.block_n / 32; c += 2) {
         const int n0 = nt * p.block_n + c * 32;
         if (n0 >= p.N) break;                  // warp-uniform
-        // ---- prefetch everything this chunk reads from global memory (row-coalesced layout) ----
-        const int u = lane & 7;
-        const int col = n0 + 4 * u;
-        const int nval = p.N - col;             // > 0: valid columns among this lane's 4
-        const bool vec = p.vec_ok && nval >= 4;
-        float4 resv[8];
-        float b4[4] = {0.f, 0.f, 0.f, 0.f};
-        float rb4[4] = {0.f, 0.f, 0.f, 0.f};
-        bool rb_uniform = false;
-        if (!p.geglu) {
-          if (p.residual && vec) {
-#pragma unroll
-            for (int itr = 0; itr < 8; ++itr) {
-              const int m = row0 + itr * 4 + (lane >> 3);
-              resv[itr] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (m < p.M) {
-                const size_t roff = (size_t)m * p.res_ld + col;
-                if (p.res_fp32) {
-                  resv[itr] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + roff));
-                } else {
-                  const uint2 t = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) + roff));
-                  resv[itr] = make_float4(bf16_lo(t.x), bf16_hi(t.x), bf16_lo(t.y), bf16_hi(t.y));
-                }
-              }
-            }
-          }
-          if (p.bias && nval > 0) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (e < nval) b4[e] = __ldg(p.bias + col + e);
-          }
-          if (p.rowbias && nval > 0) {
-            const int mlast = min(row0 + 31, p.M - 1);
-            rb_uniform = row0 < p.M && (row0 / p.rows_per_batch) == (mlast / p.rows_per_batch);   // warp-uniform
-            if (rb_uniform) {
-              const float* rb = p.rowbias + (size_t)(row0 / p.rows_per_batch) * p.rowbias_ld + col;
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (e < nval) rb4[e] = __ldg(rb + e);
-            }
-          }
-        }
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(taddr0 + (uint32_t)(c * 32), r);
-        tmem_ld_wait();
-        if (p.geglu) {
+        if (f_geglu) {
+          if (!waited) { mbar_wait(tfull_bar(as), aphase); tc_fence_after(); waited = true; }
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr0 + (uint32_t)(c * 32), r);
+          tmem_ld_wait();
           // row layout: columns [0,16) = values, [16,32) = gates of output columns n0/2 .. n0/2+15
           float o[16];
 #pragma unroll
@@ -257,15 +230,15 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
             float4 x;
             const uint32_t src = stg + (uint32_t)rr * 64u + (uint32_t)((ug ^ ((rr >> 1) & 3)) << 4);
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(src));
-            if (m < p.M) {
+            if (full_rows || m < p.M) {
               const size_t off = (size_t)m * p.out_ld + colo;
-              if (p.out_fp32) {
+              if (f_out32) {
                 float* dst = reinterpret_cast<float*>(p.out) + off;
-                if (p.vec_ok) *reinterpret_cast<float4*>(dst) = x;
+                if (f_vec) *reinterpret_cast<float4*>(dst) = x;
                 else { dst[0] = x.x; dst[1] = x.y; dst[2] = x.z; dst[3] = x.w; }
               } else {
                 __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
-                if (p.vec_ok) *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
+                if (f_vec) *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
                 else { dst[0] = __float2bfloat16(x.x); dst[1] = __float2bfloat16(x.y); dst[2] = __float2bfloat16(x.z); dst[3] = __float2bfloat16(x.w); }
               }
             }
@@ -273,8 +246,56 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
           __syncwarp();
           continue;
         }
-        // (reached only for the non-GEGLU path; the residual / bias prefetch for this chunk was issued
-        //  above, before the TMEM load, so its HBM latency overlaps the TMEM read and the transpose)
+        // ---- prefetch everything this chunk reads from global memory (row-coalesced layout: lane ->
+        //      4 columns, 8 row groups) BEFORE waiting for the accumulator, so HBM latency is hidden ----
+        const int u = lane & 7;
+        const int col = n0 + 4 * u;
+        const int nval = p.N - col;             // > 0: valid columns among this lane's 4
+        const bool vec = f_vec && nval >= 4;
+        float4 resv[8];
+        float b4[4] = {0.f, 0.f, 0.f, 0.f};
+        float rb4[4] = {0.f, 0.f, 0.f, 0.f};
+        bool rb_uniform = false;
+        if (f_res && vec) {
+#pragma unroll
+          for (int itr = 0; itr < 8; ++itr) {
+            const int m = row0 + itr * 4 + (lane >> 3);
+            resv[itr] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (full_rows || m < p.M) {
+              const size_t roff = (size_t)m * p.res_ld + col;
+              if (f_res32) {
+                resv[itr] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + roff));
+              } else {
+                const uint2 t = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) + roff));
+                resv[itr] = make_float4(bf16_lo(t.x), bf16_hi(t.x), bf16_lo(t.y), bf16_hi(t.y));
+              }
+            }
+          }
+        }
+        if (p.bias && nval > 0) {
+          if (vec) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+            b4[0] = t.x; b4[1] = t.y; b4[2] = t.z; b4[3] = t.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (e < nval) b4[e] = __ldg(p.bias + col + e);
+          }
+        }
+        if (f_rowbias && nval > 0) {
+          const int mlast = min(row0 + 31, p.M - 1);
+          rb_uniform = row0 < p.M && (row0 / p.rows_per_batch) == (mlast / p.rows_per_batch);   // warp-uniform
+          if (rb_uniform) {
+            const float* rb = p.rowbias + (size_t)(row0 / p.rows_per_batch) * p.rowbias_ld + col;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (e < nval) b4[e] += __ldg(rb + e);       // folded into the per-column bias
+          }
+        }
+        if (!waited) { mbar_wait(tfull_bar(as), aphase); tc_fence_after(); waited = true; }
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr0 + (uint32_t)(c * 32), r);
+        tmem_ld_wait();
         // staging tile [32 rows][128 B], 128-byte swizzle
 #pragma unroll
         for (int u2 = 0; u2 < 8; ++u2) {
@@ -290,29 +311,24 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
           float x[4];
           const uint32_t src = stg + (uint32_t)rr * 128u + (uint32_t)((u ^ (rr & 7)) << 4);
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[0]), "=f"(x[1]), "=f"(x[2]), "=f"(x[3]) : "r"(src));
-          if (m >= p.M || nval <= 0) continue;
+          if ((!full_rows && m >= p.M) || nval <= 0) continue;
 #pragma unroll
           for (int e = 0; e < 4; ++e) x[e] += b4[e];
-          if (p.rowbias) {
-            if (rb_uniform) {
+          if (f_rowbias && !rb_uniform) {
+            const float* rb = p.rowbias + (size_t)(m / p.rows_per_batch) * p.rowbias_ld + col;
 #pragma unroll
-              for (int e = 0; e < 4; ++e) x[e] += rb4[e];
-            } else {
-              const float* rb = p.rowbias + (size_t)(m / p.rows_per_batch) * p.rowbias_ld + col;
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (e < nval) x[e] += __ldg(rb + e);
-            }
+            for (int e = 0; e < 4; ++e)
+              if (e < nval) x[e] += __ldg(rb + e);
           }
-          if (p.act) {
+          if (kGeneric && f_act) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              if (p.act == DFB_ACT_SILU) x[e] = silu_f(x[e]);
-              else if (p.act == DFB_ACT_LEAKY_RELU) x[e] = x[e] > 0.f ? x[e] : 0.01f * x[e];
+              if (f_act == DFB_ACT_SILU) x[e] = silu_f(x[e]);
+              else if (f_act == DFB_ACT_LEAKY_RELU) x[e] = x[e] > 0.f ? x[e] : 0.01f * x[e];
               else x[e] = tanhf(x[e]);
             }
           }
-          if (p.residual) {
+          if (f_res) {
             if (vec) {
               x[0] += resv[itr].x; x[1] += resv[itr].y; x[2] += resv[itr].z; x[3] += resv[itr].w;
             } else {
@@ -320,12 +336,12 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
 #pragma unroll
               for (int e = 0; e < 4; ++e)
                 if (e < nval)
-                  x[e] += p.res_fp32 ? reinterpret_cast<const float*>(p.residual)[roff + e]
-                                     : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.residual)[roff + e]);
+                  x[e] += f_res32 ? reinterpret_cast<const float*>(p.residual)[roff + e]
+                                  : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.residual)[roff + e]);
             }
           }
           const size_t off = (size_t)m * p.out_ld + col;
-          if (p.out_fp32) {
+          if (f_out32) {
             float* dst = reinterpret_cast<float*>(p.out) + off;
             if (vec) *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
             else {
@@ -345,6 +361,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
         }
         __syncwarp();
       }
+      if (!waited) { mbar_wait(tfull_bar(as), aphase); tc_fence_after(); }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(as));
@@ -477,16 +494,53 @@ extern "C" int dfb_gemm(const dfb_gemm_params* q, void* stream_) {
   }
   kp.vec_ok = vec_ok ? 1 : 0;
 
-  static bool attr_done[64] = {false};
-  int dev = 0;
-  DFB_CHECK_CUDA(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && !attr_done[dev]) {
-    DFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-    attr_done[dev] = true;
+  // epilogue specialisation
+  int mode = EPI_GENERIC;
+  const bool simple = kp.vec_ok && (q->N % 4) == 0 && kp.act == 0 && (q->residual == nullptr || kp.res_fp32) &&
+                      (q->bias == nullptr || (reinterpret_cast<uintptr_t>(q->bias) & 15) == 0) &&
+                      (q->rowbias == nullptr || kp.rows_per_batch >= 32);
+  if (simple) {
+    if (kp.geglu) {
+      if (!kp.out_fp32) mode = EPI_GEGLU;
+    } else {
+      mode = (kp.out_fp32 ? EPI_OUT_F32 : 0) | (q->residual ? EPI_RES_F32 : 0) | (q->rowbias ? EPI_ROWBIAS : 0);
+      // instantiated combinations only; anything else runs the generic kernel
+      if (!(mode == 0 || mode == EPI_RES_F32 || mode == EPI_OUT_F32 || mode == (EPI_OUT_F32 | EPI_RES_F32) ||
+            mode == (EPI_OUT_F32 | EPI_ROWBIAS)))
+        mode = EPI_GENERIC;
+    }
   }
   const int num_tiles = kp.n_tiles_m * kp.n_tiles_n;
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  gemm_tcgen05_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(maps, kp);
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  DFB_CHECK_CUDA(cudaGetDevice(&dev));
+#define DFB_GEMM_CASE(M_)                                                                                        \
+  case M_:                                                                                                       \
+    if (first) DFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<M_>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES)); \
+    if (launch) gemm_tcgen05_kernel<M_><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(maps, kp);              \
+    break;
+  const bool need_attr = dev >= 0 && dev < 64 && !attr_done[dev];
+  for (int pass = need_attr ? 0 : 1; pass < 2; ++pass) {
+    const bool first = pass == 0, launch = pass == 1;
+    const int modes[7] = {0, EPI_RES_F32, EPI_OUT_F32, EPI_OUT_F32 | EPI_RES_F32, EPI_OUT_F32 | EPI_ROWBIAS, EPI_GEGLU, EPI_GENERIC};
+    for (int i = 0; i < (first ? 7 : 1); ++i) {
+      switch (first ? modes[i] : mode) {
+        DFB_GEMM_CASE(0)
+        DFB_GEMM_CASE(EPI_RES_F32)
+        DFB_GEMM_CASE(EPI_OUT_F32)
+        DFB_GEMM_CASE(EPI_OUT_F32 | EPI_RES_F32)
+        DFB_GEMM_CASE(EPI_OUT_F32 | EPI_ROWBIAS)
+        DFB_GEMM_CASE(EPI_GEGLU)
+        DFB_GEMM_CASE(EPI_GENERIC)
+        default:
+          set_last_error_msg("dfb_gemm: internal: epilogue mode not instantiated");
+          return DFB_ERR_INVALID;
+      }
+    }
+  }
+#undef DFB_GEMM_CASE
+  if (need_attr) attr_done[dev] = true;
   DFB_CHECK_CUDA(cudaGetLastError());
   return DFB_OK;
 }

@@ -16,7 +16,7 @@ R = int(os.environ.get("ROWS", "64"))          # UNet rows (batch)
 g = torch.Generator().manual_seed(0)
 rn = lambda *s: torch.randn(*s, generator=g)
 
-which = set(os.environ.get("WHICH", "geglu,outproj,conv,attn,xattn,gn,ln,cfg").split(","))
+which = set(os.environ.get("WHICH", "geglu,outproj,qkv,conv,attn,xattn,gn,ln,cfg").split(","))
 for rep in range(2):                           # launch 0 = warm-up, launch 1 = the one to look at
     if "geglu" in which:                       # GEGLU proj at 64x64: M = R*4096, N = 2560, K = 320
         M, C = R * 4096, 320
@@ -30,6 +30,12 @@ for rep in range(2):                           # launch 0 = warm-up, launch 1 = 
         w = ops.pack_linear(rn(320, 384) * 384 ** -0.5).to(dev)
         res = rn(M, 320).to(dev)
         ops.gemm([a], w, 320, out=res, bias=rn(320).to(dev), residual=res)
+    if "qkv" in which:                         # fused q/k/v projection: bf16 out, no bias/residual, N = 1152, K = 320
+        M = R * 4096
+        a = rn(M, 320).bfloat16().to(dev)
+        w = ops.pack_linear(rn(1152, 320) * 320 ** -0.5).to(dev)
+        out = torch.empty(M, 1152, dtype=torch.bfloat16, device=dev)
+        ops.gemm([a], w, 1152, out=out)
     if "conv" in which:                        # ResNet conv 640->640 at 32x32
         x = rn(R, 32, 32, 640).bfloat16().to(dev)
         w = ops.pack_conv3x3(rn(640, 640, 3, 3) * (9 * 640) ** -0.5).to(dev)
