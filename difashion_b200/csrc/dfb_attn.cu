@@ -101,16 +101,19 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ A
   const uint32_t tmem_O = tmem_base + (uint32_t)p.block_kv;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ---------------- TMA producer ----------------
+    // ---------------- TMA producer (warp-uniform loop, one elected lane issues) ----------------
+    if (elect_one()) {
       mbar_expect_tx(q_full, q_bytes);
       for (int c = 0; c < dchunks; ++c)
         tma_load_3d(&maps.q, sQ + (uint32_t)c * ATT_BLOCK_Q * 32u, q_full, p.q_col0 + head * p.dp + c * 16,
                     qt * ATT_BLOCK_Q, b);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int st = j % ATT_STAGES;
-        const uint32_t ph = (uint32_t)(j / ATT_STAGES) & 1u;
-        mbar_wait(kv_empty(st), ph ^ 1u);
+    }
+    __syncwarp();
+    for (int j = 0; j < n_tiles; ++j) {
+      const int st = j % ATT_STAGES;
+      const uint32_t ph = (uint32_t)(j / ATT_STAGES) & 1u;
+      mbar_wait(kv_empty(st), ph ^ 1u);
+      if (elect_one()) {
         const uint32_t sK = sKV + (uint32_t)st * 2 * kv_tile_bytes;
         const uint32_t sV = sK + kv_tile_bytes;
         mbar_expect_tx(kv_full(st), 2 * kv_tile_bytes);
@@ -121,43 +124,53 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ A
           tma_load_3d(&maps.v, sV + (uint32_t)c * kv_chunk_bytes, kv_full(st), p.v_col0 + head * p.dp + c * 16,
                       j * p.block_kv, b);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------- MMA issuer ----------------
-      const uint32_t idesc_qk = make_idesc_f16(ATT_BLOCK_Q, (uint32_t)p.block_kv, true, 0, 0);
-      const uint32_t idesc_pv = make_idesc_f16(ATT_BLOCK_Q, (uint32_t)p.dp, true, 0, 1);
-      auto issue_qk = [&](int st) {
-        const uint32_t sK = sKV + (uint32_t)st * 2 * kv_tile_bytes;
-        for (int c = 0; c < dchunks; ++c) {
-          const uint64_t da = make_smem_desc(sQ + (uint32_t)c * ATT_BLOCK_Q * 32u, 16, 256, SWZ_32B);
-          const uint64_t db = make_smem_desc(sK + (uint32_t)c * kv_chunk_bytes, 16, 256, SWZ_32B);
-          umma_f16_ss(tmem_S, da, db, idesc_qk, c != 0);
-        }
+    // ---------------- MMA issuer ----------------
+    // Whole warp runs the warp-uniform loop (descriptors stay in uniform registers); one elected lane
+    // issues tcgen05.mma / tcgen05.commit.
+    const uint32_t idesc_qk = make_idesc_f16(ATT_BLOCK_Q, (uint32_t)p.block_kv, true, 0, 0);
+    const uint32_t idesc_pv = make_idesc_f16(ATT_BLOCK_Q, (uint32_t)p.dp, true, 0, 1);
+    const uint64_t desc_q0 = make_smem_desc(sQ, 16, 256, SWZ_32B);
+    const uint64_t desc_p0 = make_smem_desc(sP, 16, 256, SWZ_32B);
+    const uint64_t desc_k0 = make_smem_desc(sKV, 16, 256, SWZ_32B);
+    const uint64_t desc_v0 = make_smem_desc(sKV + kv_tile_bytes, p.v_lbo, p.v_sbo, SWZ_32B);
+    const uint32_t stage_step = (2 * kv_tile_bytes) >> 4;
+    const uint32_t kchunk_step = kv_chunk_bytes >> 4;
+    const int pv_steps = p.block_kv >> 4;
+    auto issue_qk = [&](int st) {
+      if (elect_one()) {
+        const uint64_t dk = desc_k0 + (uint64_t)((uint32_t)st * stage_step);
+        for (int c = 0; c < dchunks; ++c)
+          umma_f16_ss(tmem_S, desc_q0 + (uint64_t)(c * (ATT_BLOCK_Q * 32 / 16)), dk + (uint64_t)((uint32_t)c * kchunk_step),
+                      idesc_qk, c != 0);
         umma_commit(s_full);
-      };
-      mbar_wait(q_full, 0);
-      mbar_wait(kv_full(0), 0);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    mbar_wait(kv_full(0), 0);
+    tc_fence_after();
+    issue_qk(0);
+    for (int j = 0; j < n_tiles; ++j) {
+      const int st = j % ATT_STAGES;
+      mbar_wait(p_full, (uint32_t)j & 1u);
       tc_fence_after();
-      issue_qk(0);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int st = j % ATT_STAGES;
-        mbar_wait(p_full, (uint32_t)j & 1u);
-        tc_fence_after();
-        const uint32_t sV = sKV + (uint32_t)st * 2 * kv_tile_bytes + kv_tile_bytes;
-        for (int k = 0; k < (p.block_kv >> 4); ++k) {
-          const uint64_t da = make_smem_desc(sP + (uint32_t)k * ATT_BLOCK_Q * 32u, 16, 256, SWZ_32B);
-          const uint64_t db = make_smem_desc(sV + (uint32_t)k * 512u, p.v_lbo, p.v_sbo, SWZ_32B);
-          umma_f16_ss(tmem_O, da, db, idesc_pv, (j | k) != 0);
-        }
+      if (elect_one()) {
+        const uint64_t dv = desc_v0 + (uint64_t)((uint32_t)st * stage_step);
+        for (int k = 0; k < pv_steps; ++k)
+          umma_f16_ss(tmem_O, desc_p0 + (uint64_t)(k * (ATT_BLOCK_Q * 32 / 16)), dv + (uint64_t)(k * (512 / 16)), idesc_pv,
+                      (j | k) != 0);
         umma_commit(o_done);
         umma_commit(kv_empty(st));
-        if (j + 1 < n_tiles) {
-          const int st2 = (j + 1) % ATT_STAGES;
-          mbar_wait(kv_full(st2), (uint32_t)((j + 1) / ATT_STAGES) & 1u);
-          tc_fence_after();
-          issue_qk(st2);
-        }
+      }
+      __syncwarp();
+      if (j + 1 < n_tiles) {
+        const int st2 = (j + 1) % ATT_STAGES;
+        mbar_wait(kv_full(st2), (uint32_t)((j + 1) / ATT_STAGES) & 1u);
+        tc_fence_after();
+        issue_qk(st2);
       }
     }
   } else {

@@ -98,31 +98,31 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const uint32_t tx_bytes = GEMM_A_BYTES + (uint32_t)p.block_n * GEMM_BLOCK_K * 2;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mt = tile / p.n_tiles_n;
-        const int nt = tile - mt * p.n_tiles_n;
-        int b0 = 0, h0 = 0;
-        if (p.conv) {
-          if (p.TB == 1) {
-            b0 = mt / p.tiles_per_img;
-            h0 = (mt - b0 * p.tiles_per_img) * p.TH;
-          } else {
-            b0 = mt * p.TB;
-          }
+    // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t tx_bytes = GEMM_A_BYTES + (uint32_t)p.block_n * GEMM_BLOCK_K * 2;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int mt = tile / p.n_tiles_n;
+      const int nt = tile - mt * p.n_tiles_n;
+      int b0 = 0, h0 = 0;
+      if (p.conv) {
+        if (p.TB == 1) {
+          b0 = mt / p.tiles_per_img;
+          h0 = (mt - b0 * p.tiles_per_img) * p.TH;
+        } else {
+          b0 = mt * p.TB;
         }
-        int kb = 0;
-        for (int s = 0; s < p.nseg; ++s) {
-          const void* tm = &maps.a[s];
-          for (int tap = 0; tap < p.seg_ntaps[s]; ++tap) {
-            const int ti = s * 9 + tap;
-            const int dh = p.tap_dh[ti], dw = p.tap_dw[ti], coff = p.tap_coff[ti];
-            for (int cb = 0; cb < p.seg_ncblk[s]; ++cb, ++kb) {
-              mbar_wait(empty_bar(stage), phase ^ 1u);
+      }
+      int kb = 0;
+      for (int s = 0; s < p.nseg; ++s) {
+        const void* tm = &maps.a[s];
+        for (int tap = 0; tap < p.seg_ntaps[s]; ++tap) {
+          const int ti = s * 9 + tap;
+          const int dh = p.tap_dh[ti], dw = p.tap_dw[ti], coff = p.tap_coff[ti];
+          for (int cb = 0; cb < p.seg_ncblk[s]; ++cb, ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            if (elect_one()) {
               const uint32_t sa = smem_base + stage * GEMM_STAGE_BYTES;
               const uint32_t sb = sa + GEMM_A_BYTES;
               mbar_expect_tx(full_bar(stage), tx_bytes);
@@ -131,32 +131,34 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
               else
                 tma_load_2d(tm, sa, full_bar(stage), coff + cb * GEMM_BLOCK_K, mt * GEMM_BLOCK_M);
               tma_load_2d(&maps.b, sb, full_bar(stage), kb * GEMM_BLOCK_K, nt * p.block_n);
-              if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1u; }
             }
+            __syncwarp();
+            if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1u; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const uint32_t idesc = make_idesc_f16(GEMM_BLOCK_M, (uint32_t)p.block_n, true);
-      int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int as = it & 1;
-        const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait(tempty_bar(as), aphase ^ 1u);
+    // ===================== MMA issuer =====================
+    // The whole warp runs the (warp-uniform) loop so that descriptors live in uniform registers; one
+    // elected lane issues tcgen05.mma / tcgen05.commit.
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t idesc = make_idesc_f16(GEMM_BLOCK_M, (uint32_t)p.block_n, true);
+    const uint64_t desc_a0 = make_smem_desc(smem_base, 16, 1024, SWZ_128B);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(tempty_bar(as), aphase ^ 1u);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)as * GEMM_MAX_BLOCK_N;
+      for (int kb = 0; kb < nk; ++kb) {
+        mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)as * GEMM_MAX_BLOCK_N;
-        for (int kb = 0; kb < nk; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t sa = smem_base + stage * GEMM_STAGE_BYTES;
-          const uint32_t sb = sa + GEMM_A_BYTES;
-          const uint64_t da = make_smem_desc(sa, 16, 1024, SWZ_128B);
-          const uint64_t db = make_smem_desc(sb, 16, 1024, SWZ_128B);
+        const uint64_t da = desc_a0 + (uint64_t)((uint32_t)(stage * GEMM_STAGE_BYTES) >> 4);
+        const uint64_t db = da + (uint64_t)(GEMM_A_BYTES >> 4);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in the
@@ -164,9 +166,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
             umma_f16_ss(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
           }
           umma_commit(empty_bar(stage));       // frees the smem slot when these MMAs retire
-          if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1u; }
+          if (kb == nk - 1) umma_commit(tfull_bar(as));   // accumulator ready for the epilogue
         }
-        umma_commit(tfull_bar(as));            // accumulator ready for the epilogue
+        __syncwarp();
+        if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else {
