@@ -61,6 +61,8 @@ class AttnParams(C.Structure):
         ("scale", C.c_float),
         ("block_kv", C.c_int32),
         ("dbg_v_lbo", C.c_int32), ("dbg_v_sbo", C.c_int32),
+        ("dbg_flags", C.c_int32),
+        ("dbg_timeline", C.c_void_p),
     ]
 
 

@@ -39,6 +39,7 @@ struct AttnKernelParams {
   long long out_batch_stride;     // elements
   uint32_t tmem_cols;
   uint32_t v_lbo, v_sbo;          // MN-major V descriptor strides (bytes)
+  long long* timeline;            // tuning hook: clock64 stamps of the first softmax thread of CTA (0,0,0)
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -222,12 +223,11 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ A
                 l4[i & 3] += pv[i];
               }
               const uint32_t dst = p_row + (uint32_t)(c * 2 + h) * ATT_BLOCK_Q * 32u;
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (0u ^ flip)), "r"(pack_bf16x2(pv[0], pv[1])),
-                           "r"(pack_bf16x2(pv[2], pv[3])), "r"(pack_bf16x2(pv[4], pv[5])), "r"(pack_bf16x2(pv[6], pv[7]))
-                           : "memory");
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (16u ^ flip)), "r"(pack_bf16x2(pv[8], pv[9])),
-                           "r"(pack_bf16x2(pv[10], pv[11])), "r"(pack_bf16x2(pv[12], pv[13])), "r"(pack_bf16x2(pv[14], pv[15]))
-                           : "memory");
+              uint32_t w[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) w[i] = pack_bf16x2(pv[2 * i], pv[2 * i + 1]);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (0u ^ flip)), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (16u ^ flip)), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
             }
           }
           mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * p.scale_log2;
@@ -374,6 +374,285 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ A
   }
 }
 
+
+// =================================================================================================
+// Double-buffered variant (block_kv == KV, KV = 64 or 128): the main self-attention kernel.
+// Two score buffers S[0|1] in TMEM and two probability buffers P[0|1] in shared memory decouple the
+// softmax warps from the tensor core: while the softmax warps work on tile j the MMA warp runs
+// O += P_{j-1} V_{j-1} and S[(j+1)&1] = Q K_{j+1}^T, so neither the MMA execution (~850 cycles per
+// 128x128 tile: the A operands come from shared memory) nor the mbarrier hand-offs sit on the
+// softmax critical path (measured on B200 with in-kernel clock stamps, see profiles/).
+//   MMA warp     : QK_0, QK_1; for j: wait p_full[j&1] -> PV_j (commit o_done[j&1], kv_empty) -> QK_{j+2}
+//   softmax warps: for j: wait s_full[j&1] (+ o_done[j&1] of tile j-2: P buffer free) -> exponentials
+//                  against the running reference max -> P[j&1] -> arrive p_full[j&1]
+// K/V tiles flow through a 3-stage TMA ring.
+// =================================================================================================
+template <int KV>
+__global__ void __launch_bounds__(ATT_THREADS, KV == 64 ? 2 : 1)
+attn_fwd_db_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnKernelParams p) {
+  constexpr int NST = 3;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int dchunks = p.dp >> 4;
+  const uint32_t q_bytes = (uint32_t)dchunks * ATT_BLOCK_Q * 32u;
+  constexpr uint32_t kv_chunk_bytes = KV * 32u;
+  const uint32_t kv_tile_bytes = (uint32_t)dchunks * kv_chunk_bytes;
+  constexpr uint32_t p_bytes = (KV / 16) * ATT_BLOCK_Q * 32u;
+  const uint32_t sQ = smem_base;
+  const uint32_t sP = sQ + q_bytes;                                        // P[0], P[1]
+  const uint32_t sKV = sP + 2 * p_bytes;                                   // stage s: K then V
+  const uint32_t bar_base = sKV + NST * 2 * kv_tile_bytes;
+  const uint32_t q_full = bar_base;
+  auto s_full = [&](int i) { return bar_base + 8u + 8u * i; };
+  auto p_full = [&](int i) { return bar_base + 24u + 8u * i; };
+  auto o_done = [&](int i) { return bar_base + 40u + 8u * i; };
+  auto kv_full = [&](int s) { return bar_base + 56u + 8u * s; };
+  auto kv_empty = [&](int s) { return bar_base + 56u + 8u * (NST + s); };
+  const uint32_t tmem_ptr_smem = bar_base + 56u + 8u * (2 * NST);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  const int n_tiles = p.n_kv_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.q);
+    tma_prefetch_desc(&maps.k);
+    tma_prefetch_desc(&maps.v);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(s_full(i), 1);
+      mbar_init(p_full(i), 128);
+      mbar_init(o_done(i), 1);
+    }
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(kv_full(s), 1);
+      mbar_init(kv_empty(s), 1);
+    }
+    fence_mbar_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+  const uint32_t tmem_O = tmem_base + 2u * KV;
+  const bool tl_cta = p.timeline != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    if (elect_one()) {
+      mbar_expect_tx(q_full, q_bytes);
+      for (int c = 0; c < dchunks; ++c)
+        tma_load_3d(&maps.q, sQ + (uint32_t)c * ATT_BLOCK_Q * 32u, q_full, p.q_col0 + head * p.dp + c * 16,
+                    qt * ATT_BLOCK_Q, b);
+    }
+    __syncwarp();
+    int st = 0;
+    uint32_t ph = 0;
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(kv_empty(st), ph ^ 1u);
+      if (elect_one()) {
+        const uint32_t sK = sKV + (uint32_t)st * 2 * kv_tile_bytes;
+        const uint32_t sV = sK + kv_tile_bytes;
+        mbar_expect_tx(kv_full(st), 2 * kv_tile_bytes);
+        for (int c = 0; c < dchunks; ++c)
+          tma_load_3d(&maps.k, sK + (uint32_t)c * kv_chunk_bytes, kv_full(st), p.k_col0 + head * p.dp + c * 16, j * KV, b);
+        for (int c = 0; c < dchunks; ++c)
+          tma_load_3d(&maps.v, sV + (uint32_t)c * kv_chunk_bytes, kv_full(st), p.v_col0 + head * p.dp + c * 16, j * KV, b);
+      }
+      __syncwarp();
+      if (++st == NST) { st = 0; ph ^= 1u; }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer (warp-uniform, one elected lane issues) ----------------
+    const uint32_t idesc_qk = make_idesc_f16(ATT_BLOCK_Q, (uint32_t)KV, true, 0, 0);
+    const uint32_t idesc_pv = make_idesc_f16(ATT_BLOCK_Q, (uint32_t)p.dp, true, 0, 1);
+    const uint64_t desc_q0 = make_smem_desc(sQ, 16, 256, SWZ_32B);
+    const uint64_t desc_p0 = make_smem_desc(sP, 16, 256, SWZ_32B);
+    const uint64_t desc_k0 = make_smem_desc(sKV, 16, 256, SWZ_32B);
+    const uint64_t desc_v0 = make_smem_desc(sKV + kv_tile_bytes, KV * 32u, 256, SWZ_32B);
+    const uint32_t stage_step = (2 * kv_tile_bytes) >> 4;
+    auto issue_qk = [&](int jj) {                 // S[jj & 1] = Q K_jj^T
+      const int st = jj % NST;
+      mbar_wait(kv_full(st), (uint32_t)(jj / NST) & 1u);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t dk = desc_k0 + (uint64_t)((uint32_t)st * stage_step);
+        const uint32_t tS = tmem_base + (uint32_t)(jj & 1) * KV;
+        for (int c = 0; c < dchunks; ++c)
+          umma_f16_ss(tS, desc_q0 + (uint64_t)(c * (ATT_BLOCK_Q * 32 / 16)), dk + (uint64_t)(c * (int)(kv_chunk_bytes >> 4)),
+                      idesc_qk, c != 0);
+        umma_commit(s_full(jj & 1));
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    issue_qk(0);
+    if (n_tiles > 1) issue_qk(1);
+    for (int j = 0; j < n_tiles; ++j) {
+      const int bi = j & 1;
+      const int st = j % NST;
+      mbar_wait(p_full(bi), (uint32_t)(j >> 1) & 1u);      // P[bi] written, S[bi] consumed
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t dv = desc_v0 + (uint64_t)((uint32_t)st * stage_step);
+        const uint64_t dp = desc_p0 + (uint64_t)((uint32_t)bi * (p_bytes >> 4));
+#pragma unroll
+        for (int k = 0; k < KV / 16; ++k)
+          umma_f16_ss(tmem_O, dp + (uint64_t)(k * (ATT_BLOCK_Q * 32 / 16)), dv + (uint64_t)(k * (512 / 16)), idesc_pv, (j | k) != 0);
+        umma_commit(o_done(bi));
+        umma_commit(kv_empty(st));
+      }
+      __syncwarp();
+      if (j + 2 < n_tiles) issue_qk(j + 2);
+    }
+  } else {
+    // ---------------- softmax / correction / epilogue warps ----------------
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const int q_row = qt * ATT_BLOCK_Q + row;
+    float m_ref = -INFINITY, l = 0.f;
+    const uint32_t flip = (uint32_t)((row >> 2) & 1) << 4;     // 32B-swizzle: 16B halves swap on rows 4..7 of 8
+    const bool tls = tl_cta && warp == 2 && lane == 0;
+    for (int j = 0; j < n_tiles; ++j) {
+      const int bi = j & 1;
+      const uint32_t tS = tmem_base + (uint32_t)bi * KV + lane_addr;
+      const uint32_t p_row = sP + (uint32_t)bi * p_bytes + (uint32_t)row * 32u;
+      if (tls && j < 60) p.timeline[j * 8 + 0] = clock64();
+      mbar_wait(s_full(bi), (uint32_t)(j >> 1) & 1u);
+      if (j >= 2) mbar_wait(o_done(bi), (uint32_t)((j >> 1) - 1) & 1u);     // PV_{j-2} retired: P[bi] is free
+      tc_fence_after();
+      if (tls && j < 60) p.timeline[j * 8 + 1] = clock64();
+      const int kv_valid = min(KV, p.Skv - j * KV);
+      uint32_t sreg[KV];
+      bool careful = (kv_valid != KV) || (j == 0);
+      float mx = -INFINITY;
+      if (!careful) {
+        // optimistic pass: exponentials against the running reference max, TMEM load of the next
+        // 32-column chunk in flight meanwhile; 8 independent max / sum chains for ILP
+        float m8[8], l8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { m8[i] = -INFINITY; l8[i] = 0.f; }
+        tmem_ld_32x32b_x32(tS, *reinterpret_cast<uint32_t(*)[32]>(&sreg[0]));
+#pragma unroll
+        for (int c = 0; c < KV / 32; ++c) {
+          tmem_ld_wait();
+          if (c + 1 < KV / 32)
+            tmem_ld_32x32b_x32(tS + (uint32_t)((c + 1) * 32), *reinterpret_cast<uint32_t(*)[32]>(&sreg[(c + 1) * 32]));
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float pv[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float sv = __uint_as_float(sreg[c * 32 + h * 16 + i]);
+              m8[i & 7] = fmaxf(m8[i & 7], sv);
+              pv[i] = ex2f(fmaf(sv, p.scale_log2, -m_ref));
+              l8[i & 7] += pv[i];
+            }
+            const uint32_t dst = p_row + (uint32_t)(c * 2 + h) * ATT_BLOCK_Q * 32u;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (0u ^ flip)), "r"(pack_bf16x2(pv[0], pv[1])),
+                         "r"(pack_bf16x2(pv[2], pv[3])), "r"(pack_bf16x2(pv[4], pv[5])), "r"(pack_bf16x2(pv[6], pv[7])) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (16u ^ flip)), "r"(pack_bf16x2(pv[8], pv[9])),
+                         "r"(pack_bf16x2(pv[10], pv[11])), "r"(pack_bf16x2(pv[12], pv[13])), "r"(pack_bf16x2(pv[14], pv[15])) : "memory");
+          }
+        }
+        mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7]))) * p.scale_log2;
+        careful = __any_sync(0xffffffffu, mx > m_ref + 8.0f);
+        if (!careful) l += ((l8[0] + l8[1]) + (l8[2] + l8[3])) + ((l8[4] + l8[5]) + (l8[6] + l8[7]));
+      } else {
+#pragma unroll
+        for (int c = 0; c < KV / 32; ++c)
+          tmem_ld_32x32b_x32(tS + (uint32_t)(c * 32), *reinterpret_cast<uint32_t(*)[32]>(&sreg[c * 32]));
+        tmem_ld_wait();
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int i = 0; i < KV; ++i)
+          if (i < kv_valid) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(sreg[i]));
+        mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * p.scale_log2;
+      }
+      if (careful) {
+        // new reference max: rescale O (needs every earlier PV retired) and l, redo the tile from registers
+        const bool need = mx > m_ref + 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          const float m_new = need ? mx : m_ref;
+          const float alpha = ex2f(m_ref - m_new);     // m_ref = -inf on the first tile -> 0
+          if (j > 0) {
+            mbar_wait(o_done((j - 1) & 1), (uint32_t)((j - 1) >> 1) & 1u);
+            tc_fence_after();
+            for (int c = 0; c < dchunks; ++c) {
+              uint32_t r[16];
+              tmem_ld_32x32b_x16(tmem_O + lane_addr + (uint32_t)(c * 16), r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+              tmem_st_32x32b_x16(tmem_O + lane_addr + (uint32_t)(c * 16), r);
+            }
+            tmem_st_wait();
+          }
+          l *= alpha;
+          m_ref = m_new;
+        }
+        float l4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < KV / 16; ++c) {
+          float pv[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float e = ex2f(fmaf(__uint_as_float(sreg[c * 16 + i]), p.scale_log2, -m_ref));
+            pv[i] = (c * 16 + i < kv_valid) ? e : 0.f;
+            l4[i & 3] += pv[i];
+          }
+          const uint32_t dst = p_row + (uint32_t)c * ATT_BLOCK_Q * 32u;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (0u ^ flip)), "r"(pack_bf16x2(pv[0], pv[1])),
+                       "r"(pack_bf16x2(pv[2], pv[3])), "r"(pack_bf16x2(pv[4], pv[5])), "r"(pack_bf16x2(pv[6], pv[7])) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (16u ^ flip)), "r"(pack_bf16x2(pv[8], pv[9])),
+                       "r"(pack_bf16x2(pv[10], pv[11])), "r"(pack_bf16x2(pv[12], pv[13])), "r"(pack_bf16x2(pv[14], pv[15])) : "memory");
+        }
+        l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+      }
+      if (tls && j < 60) p.timeline[j * 8 + 2] = clock64();
+      fence_proxy_async_smem();     // generic-proxy P writes -> visible to the tensor core's async proxy
+      tc_fence_before();
+      mbar_arrive(p_full(bi));
+      if (tls && j < 60) p.timeline[j * 8 + 3] = clock64();
+    }
+    // ---- epilogue: O / l -> bf16 ----
+    mbar_wait(o_done((n_tiles - 1) & 1), (uint32_t)((n_tiles - 1) >> 1) & 1u);
+    tc_fence_after();
+    const float inv_l = 1.0f / l;
+    __nv_bfloat16* orow = p.out + (size_t)b * p.out_batch_stride + (size_t)q_row * p.out_ld + p.out_col0 + head * p.dp;
+    for (int c = 0; c < dchunks; ++c) {
+      uint32_t r[16];
+      tmem_ld_32x32b_x16(tmem_O + lane_addr + (uint32_t)(c * 16), r);
+      tmem_ld_wait();
+      if (q_row < p.Sq) {
+        uint4 a, bq;
+        a.x = pack_bf16x2(__uint_as_float(r[0]) * inv_l, __uint_as_float(r[1]) * inv_l);
+        a.y = pack_bf16x2(__uint_as_float(r[2]) * inv_l, __uint_as_float(r[3]) * inv_l);
+        a.z = pack_bf16x2(__uint_as_float(r[4]) * inv_l, __uint_as_float(r[5]) * inv_l);
+        a.w = pack_bf16x2(__uint_as_float(r[6]) * inv_l, __uint_as_float(r[7]) * inv_l);
+        bq.x = pack_bf16x2(__uint_as_float(r[8]) * inv_l, __uint_as_float(r[9]) * inv_l);
+        bq.y = pack_bf16x2(__uint_as_float(r[10]) * inv_l, __uint_as_float(r[11]) * inv_l);
+        bq.z = pack_bf16x2(__uint_as_float(r[12]) * inv_l, __uint_as_float(r[13]) * inv_l);
+        bq.w = pack_bf16x2(__uint_as_float(r[14]) * inv_l, __uint_as_float(r[15]) * inv_l);
+        *reinterpret_cast<uint4*>(orow + c * 16) = a;
+        *reinterpret_cast<uint4*>(orow + c * 16 + 8) = bq;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
 }  // namespace dfb
 
 using namespace dfb;
@@ -397,6 +676,11 @@ extern "C" int dfb_attention(const dfb_attn_params* a, void* stream_) {
     if (skv16 <= 128 && a->dp <= 80 && skv16 > pref) bkv = skv16;   // short KV (cross-attention): one tile
   }
   DFB_REQUIRE(bkv % 16 == 0 && bkv >= 16 && bkv <= 128, "dfb_attention: block_kv must be a multiple of 16 in [16,128]");
+  // kernel family: the double-buffered kernel for multi-tile KV (self-attention), the single-buffer kernel for
+  // one-tile / odd-sized KV (cross-attention, tiny shapes).  dbg_flags bit3 forces the single-buffer family.
+  bool use_db = !(a->dbg_flags & 8) && (bkv == 64 || bkv == 128) && a->Skv > bkv;
+  if (use_db && a->block_kv <= 0) bkv = 64;                       // default tile of the double-buffered kernel
+  if (use_db && bkv == 128 && 2 * 128 + a->dp > 512) use_db = false;
   kp.Sq = a->Sq; kp.Skv = a->Skv; kp.dp = a->dp; kp.block_kv = bkv;
   kp.n_kv_tiles = (a->Skv + bkv - 1) / bkv;
   kp.q_col0 = a->q_col0; kp.k_col0 = a->k_col0; kp.v_col0 = a->v_col0;
@@ -404,12 +688,13 @@ extern "C" int dfb_attention(const dfb_attn_params* a, void* stream_) {
   kp.out = (__nv_bfloat16*)a->out;
   kp.out_ld = a->out_ld; kp.out_col0 = a->out_col0;
   kp.out_batch_stride = (long long)a->Sq * a->out_ld;
-  uint32_t need_cols = (uint32_t)(bkv + a->dp), cols = 32;
+  uint32_t need_cols = (uint32_t)((use_db ? 2 : 1) * bkv + a->dp), cols = 32;
   while (cols < need_cols) cols <<= 1;
   DFB_REQUIRE(cols <= 512, "dfb_attention: block_kv + dp exceeds TMEM");
   kp.tmem_cols = cols;
   kp.v_lbo = a->dbg_v_lbo > 0 ? (uint32_t)a->dbg_v_lbo : (uint32_t)bkv * 32u;
   kp.v_sbo = a->dbg_v_sbo > 0 ? (uint32_t)a->dbg_v_sbo : 256u;
+  kp.timeline = (long long*)a->dbg_timeline;
 
   AttnMaps maps;
   memset(&maps, 0, sizeof(maps));
@@ -436,20 +721,31 @@ extern "C" int dfb_attention(const dfb_attn_params* a, void* stream_) {
   }
 
   const int dch = a->dp / 16;
-  const size_t smem = 1024 + (size_t)dch * ATT_BLOCK_Q * 32 + (size_t)(bkv / 16) * ATT_BLOCK_Q * 32 +
-                      (size_t)ATT_STAGES * 2 * dch * bkv * 32 + 128;
+  size_t smem;
+  if (use_db)
+    smem = 1024 + (size_t)dch * ATT_BLOCK_Q * 32 + 2 * (size_t)(bkv / 16) * ATT_BLOCK_Q * 32 + (size_t)3 * 2 * dch * bkv * 32 + 256;
+  else
+    smem = 1024 + (size_t)dch * ATT_BLOCK_Q * 32 + (size_t)(bkv / 16) * ATT_BLOCK_Q * 32 + (size_t)ATT_STAGES * 2 * dch * bkv * 32 + 128;
+  if ((a->dbg_flags & 2) && smem < 120 * 1024) smem = 120 * 1024;      // tuning hook: force one CTA per SM
   DFB_REQUIRE(smem <= 227 * 1024, "dfb_attention: tile configuration exceeds shared memory");
-  static size_t max_set[64] = {0};
+  static bool attr_set[64] = {false};
   int dev = 0;
   DFB_CHECK_CUDA(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && smem > max_set[dev]) {
-    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-    max_set[dev] = 227 * 1024;
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    const int mx = 227 * 1024;
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_db_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_db_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    attr_set[dev] = true;
   }
   dim3 grid((a->Sq + ATT_BLOCK_Q - 1) / ATT_BLOCK_Q, a->heads, a->B);
-  if (bkv == 128)
+  if (use_db && bkv == 64)
+    attn_fwd_db_kernel<64><<<grid, ATT_THREADS, smem, stream>>>(maps, kp);
+  else if (use_db)
+    attn_fwd_db_kernel<128><<<grid, ATT_THREADS, smem, stream>>>(maps, kp);
+  else if (bkv == 128)
     attn_fwd_kernel<128><<<grid, ATT_THREADS, smem, stream>>>(maps, kp);
   else if (bkv == 64)
     attn_fwd_kernel<64><<<grid, ATT_THREADS, smem, stream>>>(maps, kp);

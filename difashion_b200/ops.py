@@ -177,7 +177,7 @@ def pad16(d: int) -> int:
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, heads: int, dp: int,
               scale: float, q_col0: int = 0, k_col0: int = 0, v_col0: int = 0, out_col0: int = 0,
-              block_kv: int = 0, dbg_v_lbo: int = 0, dbg_v_sbo: int = 0) -> torch.Tensor:
+              block_kv: int = 0, dbg_v_lbo: int = 0, dbg_v_sbo: int = 0, dbg_flags: int = 0, dbg_timeline: Optional[torch.Tensor] = None) -> torch.Tensor:
     """softmax(Q K^T * scale) V per (batch, head); q/k/v/out are bf16 ``[B, S, ld]`` views whose head
     ``h`` lives in columns ``[col0 + h*dp, col0 + (h+1)*dp)`` (``dp`` = head dim padded to 16)."""
     from ._lib import AttnParams
@@ -192,6 +192,8 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
     p.scale = scale
     p.block_kv = block_kv
     p.dbg_v_lbo, p.dbg_v_sbo = dbg_v_lbo, dbg_v_sbo
+    p.dbg_flags = dbg_flags
+    p.dbg_timeline = _ptr(dbg_timeline)
     e0 = _prof_begin()
     check(_lib.load().dfb_attention(C.byref(p), _stream()), "dfb_attention")
     if e0 is not None:
