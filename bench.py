@@ -290,7 +290,8 @@ def main():
     }
     if args.profile_step and rank == 0:
         for kind, (ms, fl, cnt) in sorted(kinds.items()):
-            print(f"# {kind:10s} launches={cnt:4d} ms={ms:9.3f} executed TFLOP/s={fl / (ms / 1e3) / 1e12 if ms else 0:8.1f}", file=sys.stderr)
+            unit = "TFLOP/s" if kind in ("gemm", "conv", "attention") else "TB/s (tensor bytes touched)"
+            print(f"# {kind:18s} launches={cnt:4d} ms={ms:9.3f} {fl / (ms / 1e3) / 1e12 if ms else 0:8.2f} {unit}", file=sys.stderr)
         print(f"# eager step {eager_ms:.3f} ms; graph step {ms_per_step:.3f} ms", file=sys.stderr)
         agg = {}
         for kind, flops, shape, a, b in prof:

@@ -40,6 +40,7 @@ struct AttnKernelParams {
   uint32_t tmem_cols;
   uint32_t v_lbo, v_sbo;          // MN-major V descriptor strides (bytes)
   long long* timeline;            // tuning hook: clock64 stamps of the first softmax thread of CTA (0,0,0)
+  int kv_stages;                  // K/V ring depth of the double-buffered kernel (2 or 3)
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -390,7 +391,8 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ A
 template <int KV>
 __global__ void __launch_bounds__(ATT_THREADS, KV == 64 ? 2 : 1)
 attn_fwd_db_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnKernelParams p) {
-  constexpr int NST = 3;
+  constexpr int NST_MAX = 3;
+  const int NST = p.kv_stages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int dchunks = p.dp >> 4;
@@ -407,8 +409,8 @@ attn_fwd_db_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant_
   auto p_full = [&](int i) { return bar_base + 24u + 8u * i; };
   auto o_done = [&](int i) { return bar_base + 40u + 8u * i; };
   auto kv_full = [&](int s) { return bar_base + 56u + 8u * s; };
-  auto kv_empty = [&](int s) { return bar_base + 56u + 8u * (NST + s); };
-  const uint32_t tmem_ptr_smem = bar_base + 56u + 8u * (2 * NST);
+  auto kv_empty = [&](int s) { return bar_base + 56u + 8u * (NST_MAX + s); };
+  const uint32_t tmem_ptr_smem = bar_base + 56u + 8u * (2 * NST_MAX);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -722,10 +724,15 @@ extern "C" int dfb_attention(const dfb_attn_params* a, void* stream_) {
 
   const int dch = a->dp / 16;
   size_t smem;
-  if (use_db)
-    smem = 1024 + (size_t)dch * ATT_BLOCK_Q * 32 + 2 * (size_t)(bkv / 16) * ATT_BLOCK_Q * 32 + (size_t)3 * 2 * dch * bkv * 32 + 256;
-  else
+  if (use_db) {
+    // 3 K/V stages when two CTAs still fit per SM with them, else 2
+    const size_t fixed = 1024 + (size_t)dch * ATT_BLOCK_Q * 32 + 2 * (size_t)(bkv / 16) * ATT_BLOCK_Q * 32 + 256;
+    const size_t stage = (size_t)2 * dch * bkv * 32;
+    kp.kv_stages = (fixed + 3 * stage + 1024 <= (size_t)113 * 1024 || fixed + 2 * stage + 1024 > (size_t)113 * 1024) ? 3 : 2;
+    smem = fixed + (size_t)kp.kv_stages * stage;
+  } else {
     smem = 1024 + (size_t)dch * ATT_BLOCK_Q * 32 + (size_t)(bkv / 16) * ATT_BLOCK_Q * 32 + (size_t)ATT_STAGES * 2 * dch * bkv * 32 + 128;
+  }
   if ((a->dbg_flags & 2) && smem < 120 * 1024) smem = 120 * 1024;      // tuning hook: force one CTA per SM
   DFB_REQUIRE(smem <= 227 * 1024, "dfb_attention: tile configuration exceeds shared memory");
   static bool attr_set[64] = {false};

@@ -205,10 +205,30 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
 # ----------------------------------------------------------------------------------------------
 # norms
 # ----------------------------------------------------------------------------------------------
+def _profiled(kind):
+    """bench.py's per-launch CUDA-event profile also covers the streaming / norm kernels (bytes instead of flops)."""
+    def deco(fn):
+        def wrapper(*a, **k):
+            e0 = _prof_begin()
+            out = fn(*a, **k)
+            if e0 is not None:
+                nbytes = 0.0
+                for t in list(a) + list(k.values()):
+                    if torch.is_tensor(t):
+                        nbytes += t.numel() * t.element_size()
+                _prof_end(e0, kind, nbytes, tuple(out.shape) if torch.is_tensor(out) else ())
+            return out
+        wrapper.__name__ = fn.__name__
+        wrapper.__doc__ = fn.__doc__
+        return wrapper
+    return deco
+
+
 def groupnorm_ws_floats(b: int, groups: int) -> int:
     return int(_lib.load().dfb_groupnorm_ws_floats(b, groups))
 
 
+@_profiled("groupnorm")
 def groupnorm(src0: torch.Tensor, src1: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor, *,
               groups: int, eps: float, silu: bool, stats_ws: torch.Tensor, out: torch.Tensor,
               raw_out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -227,6 +247,7 @@ def groupnorm(src0: torch.Tensor, src1: Optional[torch.Tensor], gamma: torch.Ten
     return out
 
 
+@_profiled("layernorm")
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: torch.Tensor, eps: float = 1e-5):
     """LayerNorm over the last dim of fp32 ``[rows, C]`` -> bf16 ``out``."""
     rows = x.numel() // x.shape[-1]
@@ -240,6 +261,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: tor
 # ----------------------------------------------------------------------------------------------
 # streaming kernels
 # ----------------------------------------------------------------------------------------------
+@_profiled("cfg_step")
 def cfg_step(eps: torch.Tensor, weights: Sequence[float], x_src: torch.Tensor, cx: float, ck: Sequence[float],
              hist: Sequence[Optional[torch.Tensor]] = (None, None, None), noise: Optional[torch.Tensor] = None,
              cn: float = 0.0, x_out: Optional[torch.Tensor] = None, eps_out: Optional[torch.Tensor] = None,
@@ -262,6 +284,7 @@ def cfg_step(eps: torch.Tensor, weights: Sequence[float], x_src: torch.Tensor, c
     return x_out
 
 
+@_profiled("mutual_gather_sum")
 def mutual_gather_sum(all_latents: Optional[torch.Tensor], prev_latents: torch.Tensor, idx: torch.Tensor,
                       out: torch.Tensor):
     n_items, n_src = idx.shape
@@ -273,6 +296,7 @@ def mutual_gather_sum(all_latents: Optional[torch.Tensor], prev_latents: torch.T
     return out
 
 
+@_profiled("mutual_blend")
 def mutual_blend(x: torch.Tensor, m: Optional[torch.Tensor], hist: Optional[torch.Tensor], null_latent: torch.Tensor,
                  eta: float, use_m: Sequence[int], use_h: Sequence[int], out: torch.Tensor):
     nb = len(use_m)
@@ -286,6 +310,7 @@ def mutual_blend(x: torch.Tensor, m: Optional[torch.Tensor], hist: Optional[torc
     return out
 
 
+@_profiled("nchw_to_nhwc_bf16")
 def nchw_to_nhwc_bf16(x: torch.Tensor, out: torch.Tensor):
     b, c, h, w = x.shape
     assert x.is_contiguous()
@@ -295,6 +320,7 @@ def nchw_to_nhwc_bf16(x: torch.Tensor, out: torch.Tensor):
     return out
 
 
+@_profiled("nhwc_to_nchw")
 def nhwc_to_nchw(x: torch.Tensor, out: torch.Tensor):
     b, c, h, w = out.shape
     assert x.dtype == torch.float32 and x.is_contiguous() and out.is_contiguous()
@@ -304,6 +330,7 @@ def nhwc_to_nchw(x: torch.Tensor, out: torch.Tensor):
     return out
 
 
+@_profiled("pad_cast_rows")
 def pad_cast_rows(x: torch.Tensor, out: torch.Tensor):
     b, s, d = x.shape
     assert x.is_contiguous() and out.is_contiguous() and out.dtype == torch.bfloat16
@@ -313,6 +340,7 @@ def pad_cast_rows(x: torch.Tensor, out: torch.Tensor):
     return out
 
 
+@_profiled("upsample2x")
 def upsample2x(x: torch.Tensor, out: torch.Tensor):
     b, h, w, c = x.shape
     assert x.dtype == torch.float32 and x.is_contiguous() and out.dtype == torch.bfloat16 and out.is_contiguous()
@@ -321,6 +349,7 @@ def upsample2x(x: torch.Tensor, out: torch.Tensor):
     return out
 
 
+@_profiled("space_to_depth")
 def space_to_depth(x: torch.Tensor, out: torch.Tensor):
     b, h, w, c = x.shape
     assert x.dtype == torch.float32 and x.is_contiguous() and out.dtype == torch.bfloat16 and out.is_contiguous()
@@ -342,6 +371,7 @@ def s2d_taps(c: int) -> Tuple[Tuple[int, int, int], ...]:
     return tuple(taps)
 
 
+@_profiled("timestep_embedding")
 def timestep_embedding(t: torch.Tensor, out: torch.Tensor, flip_sin_to_cos: bool = True, freq_shift: float = 0.0):
     assert t.dtype == torch.float32 and t.is_contiguous() and out.dtype == torch.bfloat16 and out.is_contiguous()
     check(_lib.load().dfb_timestep_embedding(t.data_ptr(), out.data_ptr(), t.shape[0], out.shape[1],
