@@ -48,6 +48,7 @@ class GemmParams(C.Structure):
         ("geglu", C.c_int32),
         ("act", C.c_int32),
         ("block_n", C.c_int32),
+        ("gn_partial", C.c_void_p),
     ]
 
 
@@ -83,6 +84,9 @@ _PROTOTYPES = {
     "dfb_groupnorm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                 C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "dfb_groupnorm_fused": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                      C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                      C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "dfb_layernorm": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int,
                                 C.c_int, C.c_int, C.c_void_p]),
     "dfb_cfg_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_void_p, C.c_float,

@@ -50,14 +50,17 @@ struct GemmKernelParams {
   int res_ld, res_fp32;
   void* out;
   int out_ld, out_fp32, geglu, vec_ok, act;
+  float* gn_partial;   // optional GroupNorm partial statistics of the fp32 output
 };
 
 // Epilogue specialisations (compile-time, so the hot epilogue loop carries no runtime flag tests and the
 // kernel image stays small enough for the instruction cache); EPI_GENERIC keeps every option at run time.
 enum : int { EPI_OUT_F32 = 1, EPI_RES_F32 = 2, EPI_ROWBIAS = 4, EPI_GEGLU = 8, EPI_GENERIC = 16 };
 
-template <int MODE>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+// EW = number of epilogue warps (8, or 16 for the instruction-heavy GEGLU epilogue): EW/4 warps share a
+// TMEM lane quarter and take 32-column chunks round-robin.
+template <int MODE, int EW = GEMM_EPI_WARPS>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ GemmKernelParams p) {
   constexpr bool kGeneric = (MODE & EPI_GENERIC) != 0;
   extern __shared__ uint8_t smem_raw[];
@@ -85,7 +88,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), GEMM_EPI_WARPS);   // one arrive per epilogue warp
+      mbar_init(tempty_bar(s), EW);   // one arrive per epilogue warp
     }
     fence_mbar_init();
     fence_proxy_async_smem();
@@ -180,8 +183,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
     // activation / residual are applied and global memory is touched with full 128-byte rows.
     const int ew = warp - 2;
     const int quarter = warp & 3;              // TMEM lane quarter this warp may access
-    const int half = ew >> 2;
-    const uint32_t stg = smem_base + GEMM_STAGES * GEMM_STAGE_BYTES + (uint32_t)ew * GEMM_EPI_STAGE_BYTES;
+    const int half = ew >> 2;                  // which share of the chunks (0 .. EW/4-1)
+    const uint32_t stg = smem_base + GEMM_STAGES * GEMM_STAGE_BYTES + (uint32_t)ew * (GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES / EW);
     // run-time flags in generic mode, compile-time constants otherwise
     const bool f_geglu = kGeneric ? (p.geglu != 0) : ((MODE & EPI_GEGLU) != 0);
     const bool f_out32 = kGeneric ? (p.out_fp32 != 0) : ((MODE & EPI_OUT_F32) != 0);
@@ -200,7 +203,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * GEMM_MAX_BLOCK_N;
       const bool full_rows = row0 + 32 <= p.M;                 // warp-uniform: no row masking needed
       bool waited = false;
-      for (int c = half; c < p.block_n / 32; c += 2) {
+      for (int c = half; c < p.block_n / 32; c += EW / 4) {
         const int n0 = nt * p.block_n + c * 32;
         if (n0 >= p.N) break;                  // warp-uniform
         if (f_geglu) {
@@ -295,6 +298,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
               if (e < nval) b4[e] += __ldg(rb + e);       // folded into the per-column bias
           }
         }
+        const bool f_gn = (kGeneric || (MODE & EPI_OUT_F32)) && p.gn_partial != nullptr;
+        float gs0 = 0.f, gq0 = 0.f, gs1 = 0.f, gq1 = 0.f;
         if (!waited) { mbar_wait(tfull_bar(as), aphase); tc_fence_after(); waited = true; }
         uint32_t r[32];
         tmem_ld_32x32b_x32(taddr0 + (uint32_t)(c * 32), r);
@@ -343,6 +348,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
                                   : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.residual)[roff + e]);
             }
           }
+          if (f_gn) {
+            gs0 += x[0] + x[1]; gq0 += x[0] * x[0] + x[1] * x[1];
+            gs1 += x[2] + x[3]; gq1 += x[2] * x[2] + x[3] * x[3];
+          }
           const size_t off = (size_t)m * p.out_ld + col;
           if (f_out32) {
             float* dst = reinterpret_cast<float*>(p.out) + off;
@@ -361,6 +370,18 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
                 if (e < nval) dst[e] = __float2bfloat16(x[e]);
             }
           }
+        }
+        if (f_gn) {
+          // fold the 4 row groups (lanes with equal column unit), then lanes 0..7 write (sum, sumsq) of their two
+          // channel pairs over this warp's 32 rows: partial[row_block][pair][2], 128 contiguous bytes per chunk
+#pragma unroll
+          for (int o = 8; o <= 16; o <<= 1) {
+            gs0 += __shfl_xor_sync(0xffffffffu, gs0, o); gq0 += __shfl_xor_sync(0xffffffffu, gq0, o);
+            gs1 += __shfl_xor_sync(0xffffffffu, gs1, o); gq1 += __shfl_xor_sync(0xffffffffu, gq1, o);
+          }
+          if (lane < 8 && nval >= 4 && row0 < p.M)
+            *reinterpret_cast<float4*>(p.gn_partial + ((size_t)(row0 >> 5) * (size_t)(p.N >> 1) + (size_t)(col >> 1)) * 2) =
+                make_float4(gs0, gq0, gs1, gq1);
         }
         __syncwarp();
       }
@@ -488,6 +509,11 @@ extern "C" int dfb_gemm(const dfb_gemm_params* q, void* stream_) {
   kp.out_fp32 = q->out_dtype == DFB_DTYPE_F32;
   kp.geglu = q->geglu ? 1 : 0;
   kp.act = q->act;
+  kp.gn_partial = q->gn_partial;
+  if (q->gn_partial)
+    DFB_REQUIRE(q->out_dtype == DFB_DTYPE_F32 && !q->geglu && q->M % 32 == 0 && q->N % 4 == 0 &&
+                    (reinterpret_cast<uintptr_t>(q->gn_partial) & 15) == 0,
+                "dfb_gemm: gn_partial needs fp32 output, M % 32 == 0, N % 4 == 0, 16B-aligned buffer");
   if (kp.geglu) DFB_REQUIRE(q->N % 32 == 0 && q->residual == nullptr, "dfb_gemm: GEGLU needs N % 32 == 0 and no residual");
   const int out_elem = kp.out_fp32 ? 4 : 2;
   bool vec_ok = ((reinterpret_cast<uintptr_t>(q->out) & 15) == 0) && (((size_t)q->out_ld * out_elem) % 16 == 0);
@@ -519,10 +545,11 @@ extern "C" int dfb_gemm(const dfb_gemm_params* q, void* stream_) {
   int dev = 0;
   DFB_CHECK_CUDA(cudaGetDevice(&dev));
 #define DFB_GEMM_CASE(M_)                                                                                        \
-  case M_:                                                                                                       \
-    if (first) DFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<M_>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES)); \
-    if (launch) gemm_tcgen05_kernel<M_><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(maps, kp);              \
-    break;
+  case M_: {                                                                                                     \
+    constexpr int EW_ = (M_ == EPI_GEGLU) ? 16 : GEMM_EPI_WARPS;                                                 \
+    if (first) DFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<M_, EW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES)); \
+    if (launch) gemm_tcgen05_kernel<M_, EW_><<<grid, 64 + 32 * EW_, GEMM_SMEM_BYTES, stream>>>(maps, kp);        \
+  } break;
   const bool need_attr = dev >= 0 && dev < 64 && !attr_done[dev];
   for (int pass = need_attr ? 0 : 1; pass < 2; ++pass) {
     const bool first = pass == 0, launch = pass == 1;

@@ -105,6 +105,43 @@ __global__ void groupnorm_finalize_kernel(const float* __restrict__ partial, int
   }
 }
 
+// Statistics from the producers' epilogue partials (dfb_gemm_params.gn_partial: [M/32][C/2][2] per source):
+// one warp per (b, g) folds the (row block, channel pair) partials of its group in a fixed order.
+__global__ void groupnorm_finalize_partials_kernel(const float* __restrict__ p0, int c0, const float* __restrict__ p1, int c1,
+                                                   int hw, int groups, int B, float eps, float* __restrict__ stats) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int b = w / groups, g = w - b * groups;
+  if (b >= B) return;
+  const int C = c0 + c1;
+  const int cg = C / groups;
+  const int ppg = cg >> 1;                 // channel pairs per group (cg is even)
+  const int pair0 = g * ppg;
+  const int rbs = hw >> 5;                 // 32-row blocks per image
+  const int h0 = c0 >> 1, h1 = c1 >> 1;
+  float s = 0.f, q = 0.f;
+  for (int idx = lane; idx < rbs * ppg; idx += 32) {
+    const int rb = idx / ppg;
+    const int pr = pair0 + (idx - rb * ppg);
+    const float* src = pr < h0 ? p0 + ((size_t)(b * rbs + rb) * h0 + pr) * 2
+                               : p1 + ((size_t)(b * rbs + rb) * h1 + (pr - h0)) * 2;
+    const float2 v = __ldg(reinterpret_cast<const float2*>(src));
+    s += v.x; q += v.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (lane == 0) {
+    const float inv_n = 1.f / ((float)cg * (float)hw);
+    const float mean = s * inv_n;
+    const float var = fmaxf(q * inv_n - mean * mean, 0.f);
+    stats[((size_t)b * groups + g) * 2 + 0] = mean;
+    stats[((size_t)b * groups + g) * 2 + 1] = rsqrtf(var + eps);
+  }
+}
+
 // y = (x - mean) * rstd * gamma + beta (optionally SiLU) -> bf16 [B, HW, C] (ld_out), optional raw
 // bf16 copy of x (A operand of the 1x1 shortcut folded into conv2).  Same thread mapping as the
 // statistics kernel: a thread owns fixed channel vectors, so gamma/beta/mean/rstd are folded into a
@@ -211,6 +248,22 @@ layernorm_kernel(const float* __restrict__ x, int ld_x, const float* __restrict_
 
 using namespace dfb;
 
+static int launch_gn_apply(const float* src0, int c0, int ld0, const float* src1, int c1, int ld1, int B, int hw, int groups,
+                           const float* stats, const float* gamma, const float* beta, int silu, void* out_bf16, int ld_out,
+                           void* raw_out_bf16, int ld_raw, cudaStream_t stream) {
+  // ~16 CTAs per SM over (B x pixel chunks)
+  int ach = (num_sms() * 16 + B - 1) / B;
+  if (ach > hw) ach = hw;
+  if (ach < 1) ach = 1;
+  const int appb = (hw + ach - 1) / ach;
+  ach = (hw + appb - 1) / appb;
+  groupnorm_apply_kernel<<<dim3(ach, B), GN_THREADS, 0, stream>>>(src0, c0, ld0, src1, c1, ld1, hw, groups, appb, stats, gamma,
+                                                                  beta, silu, (__nv_bfloat16*)out_bf16, ld_out,
+                                                                  (__nv_bfloat16*)raw_out_bf16, ld_raw);
+  DFB_CHECK_CUDA(cudaGetLastError());
+  return DFB_OK;
+}
+
 extern "C" {
 
 size_t dfb_groupnorm_ws_floats(int B, int groups) {
@@ -247,19 +300,31 @@ int dfb_groupnorm(const float* src0, int c0, int ld0, const float* src1, int c1,
     groupnorm_finalize_kernel<<<blocks, threads, 0, stream>>>(partial, chunks, groups, B, inv_n, eps, stats);
     DFB_CHECK_CUDA(cudaGetLastError());
   }
+  return launch_gn_apply(src0, c0, ld0, src1, c1, ld1, B, hw, groups, stats, gamma, beta, silu, out_bf16, ld_out, raw_out_bf16,
+                         ld_raw, stream);
+}
+
+int dfb_groupnorm_fused(const float* src0, int c0, int ld0, const float* partial0, const float* src1, int c1, int ld1,
+                        const float* partial1, int B, int hw, int groups, float eps, const float* gamma,
+                        const float* beta, int silu, float* stats_ws, void* out_bf16, int ld_out, void* raw_out_bf16,
+                        int ld_raw, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DFB_REQUIRE(src0 && partial0 && gamma && beta && stats_ws && out_bf16, "dfb_groupnorm_fused: null buffer");
+  DFB_REQUIRE(c1 == 0 || (src1 != nullptr && partial1 != nullptr), "dfb_groupnorm_fused: second source missing");
+  const int Cch = c0 + c1;
+  DFB_REQUIRE(B > 0 && hw > 0 && hw % 32 == 0 && groups > 0 && groups <= 64 && Cch % groups == 0, "dfb_groupnorm_fused: bad sizes");
+  DFB_REQUIRE((Cch / groups) % 2 == 0 && c0 % 4 == 0 && c1 % 4 == 0, "dfb_groupnorm_fused: channels/group must be even, sources multiple of 4");
+  DFB_REQUIRE(Cch / 4 <= GN_THREADS * GN_MAX_VEC_PER_THREAD, "dfb_groupnorm_fused: too many channels");
+  DFB_REQUIRE(ld0 % 4 == 0 && ld1 % 4 == 0 && ld_out % 4 == 0 && ld_raw % 4 == 0, "dfb_groupnorm_fused: pitches must be multiples of 4");
   {
-    // apply: ~8 resident CTAs per SM over (B x pixel chunks)
-    int ach = (num_sms() * 16 + B - 1) / B;
-    if (ach > hw) ach = hw;
-    if (ach < 1) ach = 1;
-    const int appb = (hw + ach - 1) / ach;
-    ach = (hw + appb - 1) / appb;
-    groupnorm_apply_kernel<<<dim3(ach, B), GN_THREADS, 0, stream>>>(src0, c0, ld0, src1, c1, ld1, hw, groups, appb, stats, gamma,
-                                                                    beta, silu, (__nv_bfloat16*)out_bf16, ld_out,
-                                                                    (__nv_bfloat16*)raw_out_bf16, ld_raw);
+    const int warps = B * groups;
+    const int threads = 128;
+    const int blocks = (warps * 32 + threads - 1) / threads;
+    groupnorm_finalize_partials_kernel<<<blocks, threads, 0, stream>>>(partial0, c0, partial1, c1, hw, groups, B, eps, stats_ws);
     DFB_CHECK_CUDA(cudaGetLastError());
   }
-  return DFB_OK;
+  return launch_gn_apply(src0, c0, ld0, src1, c1, ld1, B, hw, groups, stats_ws, gamma, beta, silu, out_bf16, ld_out, raw_out_bf16,
+                         ld_raw, stream);
 }
 
 int dfb_layernorm(const float* x, int ld_x, const float* gamma, const float* beta, float eps, void* out_bf16, int ld_out,

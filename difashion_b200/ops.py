@@ -112,7 +112,7 @@ def gemm(a: Sequence[torch.Tensor], w: torch.Tensor, n: int, *, out: torch.Tenso
          a_c: Optional[Sequence[int]] = None, conv_geom: Optional[Tuple[int, int, int]] = None,
          bias: Optional[torch.Tensor] = None, rowbias: Optional[torch.Tensor] = None,
          rows_per_batch: int = 1, residual: Optional[torch.Tensor] = None, geglu: bool = False,
-         block_n: int = 0, act: int = 0) -> torch.Tensor:
+         block_n: int = 0, act: int = 0, gn_partial: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``out = epilogue(A @ w.T)`` on tcgen05 tensor cores (see ``dfb_gemm`` in include/dfb200.h).
 
     a:    1 or 2 bf16 operands; each ``[M, C]`` (plain) or ``[B, H, W, C]`` (conv), last dim
@@ -156,6 +156,9 @@ def gemm(a: Sequence[torch.Tensor], w: torch.Tensor, n: int, *, out: torch.Tenso
     p.geglu = 1 if geglu else 0
     p.act = act
     p.block_n = block_n
+    if gn_partial is not None:
+        assert gn_partial.dtype == torch.float32 and gn_partial.numel() >= (m_rows // 32) * (n // 2) * 2
+        p.gn_partial = gn_partial.data_ptr()
     e0 = _prof_begin()
     check(_lib.load().dfb_gemm(C.byref(p), _stream()), "dfb_gemm")
     if e0 is not None:
@@ -229,10 +232,29 @@ def groupnorm_ws_floats(b: int, groups: int) -> int:
 
 
 @_profiled("groupnorm")
+def gn_partial_shape(m_rows: int, n: int):
+    """Shape of the GroupNorm partial-statistics buffer a GEMM epilogue emits for an fp32 ``[m_rows, n]`` output."""
+    return (m_rows // 32, n // 2, 2)
+
+
 def groupnorm(src0: torch.Tensor, src1: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor, *,
               groups: int, eps: float, silu: bool, stats_ws: torch.Tensor, out: torch.Tensor,
-              raw_out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """GroupNorm(+SiLU) over the channel-concat of fp32 NHWC sources ``[B, H, W, C]`` -> bf16 ``out``."""
+              raw_out: Optional[torch.Tensor] = None, partials: Optional[Sequence[Optional[torch.Tensor]]] = None) -> torch.Tensor:
+    """GroupNorm(+SiLU) over the channel-concat of fp32 NHWC sources ``[B, H, W, C]`` -> bf16 ``out``.
+    ``partials`` = per-source statistics emitted by the producers' GEMM epilogues (skips the statistics pass)."""
+    if partials is not None and partials[0] is not None and (src1 is None or partials[1] is not None):
+        b = src0.shape[0]
+        hw = src0.shape[1] * src0.shape[2] if src0.dim() == 4 else src0.shape[1]
+        c0 = src0.shape[-1]
+        c1 = 0 if src1 is None else src1.shape[-1]
+        assert hw % 32 == 0 and src0.dtype == torch.float32 and out.dtype == torch.bfloat16
+        check(_lib.load().dfb_groupnorm_fused(
+            src0.data_ptr(), c0, src0.stride(-2), partials[0].data_ptr(), _ptr(src1), c1,
+            0 if src1 is None else src1.stride(-2), None if src1 is None else partials[1].data_ptr(), b, hw, groups, eps,
+            gamma.data_ptr(), beta.data_ptr(), 1 if silu else 0, stats_ws.data_ptr(), out.data_ptr(), out.stride(-2),
+            _ptr(raw_out), 0 if raw_out is None else raw_out.stride(-2), _stream()), "dfb_groupnorm_fused")
+        _count(2)
+        return out
     b = src0.shape[0]
     hw = src0.shape[1] * src0.shape[2] if src0.dim() == 4 else src0.shape[1]
     c0 = src0.shape[-1]

@@ -357,6 +357,20 @@ class B200UNet2DConditionModel(nn.Module):
         return P
 
     # ---------------------------------------------------------------- kernels sequencing
+    def _gnp_new(self, ws: "Workspace", tag: str, out: torch.Tensor):
+        """Partial-statistics buffer for an fp32 output that a GroupNorm will consume (emitted by the GEMM epilogue)."""
+        hw = out.shape[1] * out.shape[2]
+        m_rows, n = out.shape[0] * hw, out.shape[3]
+        self._gnp.pop(out.data_ptr(), None)
+        if hw % 32 != 0 or n % 4 != 0:
+            return None
+        part = ws.get(tag + "_gnp", ops.gn_partial_shape(m_rows, n), torch.float32)
+        self._gnp[out.data_ptr()] = part
+        return part
+
+    def _gnp_of(self, t: Optional[torch.Tensor]):
+        return None if t is None else self._gnp.get(t.data_ptr())
+
     def _resnet(self, pk, srcs: List[torch.Tensor], temb_all, ws: Workspace, out_tag: str):
         x0 = srcs[0]
         x1 = srcs[1] if len(srcs) > 1 else None
@@ -366,19 +380,23 @@ class B200UNet2DConditionModel(nn.Module):
         stats = ws.get("gn_stats", (ops.groupnorm_ws_floats(B, groups),), torch.float32)
         xn = ws.get("xn", (B, H, W, cin), torch.bfloat16)
         xraw = ws.get("xraw", (B, H, W, cin), torch.bfloat16) if pk["shortcut"] else None
-        ops.groupnorm(x0, x1, g, b, groups=groups, eps=eps, silu=True, stats_ws=stats, out=xn, raw_out=xraw)
+        ops.groupnorm(x0, x1, g, b, groups=groups, eps=eps, silu=True, stats_ws=stats, out=xn, raw_out=xraw,
+                      partials=(self._gnp_of(x0), self._gnp_of(x1)))
         h1 = ws.get("h1", (B, H, W, cout), torch.float32)
+        h1p = self._gnp_new(ws, "h1", h1)
         ops.gemm([xn], pk["w1"], cout, out=h1, taps=[ops.TAPS_3X3], conv_geom=(B, H, W), bias=pk["b1"],
-                 rowbias=temb_all[:, pk["temb_off"]:pk["temb_off"] + cout], rows_per_batch=H * W)
+                 rowbias=temb_all[:, pk["temb_off"]:pk["temb_off"] + cout], rows_per_batch=H * W, gn_partial=h1p)
         g, b, eps, groups = pk["n2"]
         hn = ws.get("hn", (B, H, W, cout), torch.bfloat16)
-        ops.groupnorm(h1, None, g, b, groups=groups, eps=eps, silu=True, stats_ws=stats, out=hn)
+        ops.groupnorm(h1, None, g, b, groups=groups, eps=eps, silu=True, stats_ws=stats, out=hn, partials=(h1p, None))
         out = ws.get(out_tag, (B, H, W, cout), torch.float32)
+        outp = self._gnp_new(ws, out_tag, out)
         if pk["shortcut"]:
             ops.gemm([hn, xraw], pk["w2"], cout, out=out, taps=[ops.TAPS_3X3, ops.TAP_CENTER], conv_geom=(B, H, W),
-                     bias=pk["b2"])
+                     bias=pk["b2"], gn_partial=outp)
         else:
-            ops.gemm([hn], pk["w2"], cout, out=out, taps=[ops.TAPS_3X3], conv_geom=(B, H, W), bias=pk["b2"], residual=x0)
+            ops.gemm([hn], pk["w2"], cout, out=out, taps=[ops.TAPS_3X3], conv_geom=(B, H, W), bias=pk["b2"], residual=x0,
+                     gn_partial=outp)
         return out
 
     def cross_attention_layers(self, P=None):
@@ -413,7 +431,8 @@ class B200UNet2DConditionModel(nn.Module):
         g, b, eps, groups = pk["gn"]
         stats = ws.get("gn_stats", (ops.groupnorm_ws_floats(B, groups),), torch.float32)
         xn = ws.get("xn", (M, C), torch.bfloat16)
-        ops.groupnorm(x, None, g, b, groups=groups, eps=eps, silu=False, stats_ws=stats, out=xn.view(B, H, W, C))
+        ops.groupnorm(x, None, g, b, groups=groups, eps=eps, silu=False, stats_ws=stats, out=xn.view(B, H, W, C),
+                      partials=(self._gnp_of(x), None))
         h = ws.get("tr_h", (M, C), torch.float32)
         ops.gemm([xn], pk["pin"][0], C, out=h, bias=pk["pin"][1])
         ln = ws.get("ln", (M, C), torch.bfloat16)
@@ -452,7 +471,8 @@ class B200UNet2DConditionModel(nn.Module):
         hb = ws.get("tr_hb", (M, C), torch.bfloat16)
         ops.gemm([ff], pk["ffo"][0], C, out=hb, bias=pk["ffo"][1], residual=h)
         out = ws.get(out_tag, (B, H, W, C), torch.float32)
-        ops.gemm([hb], pk["pout"][0], C, out=out.view(M, C), bias=pk["pout"][1], residual=x.view(M, C))
+        ops.gemm([hb], pk["pout"][0], C, out=out.view(M, C), bias=pk["pout"][1], residual=x.view(M, C),
+                 gn_partial=self._gnp_new(ws, out_tag, out))
         return out
 
     def _temb(self, P, t_dev: torch.Tensor, ws: Workspace):
@@ -476,10 +496,12 @@ class B200UNet2DConditionModel(nn.Module):
         ``project_context(ctx)``.  Returns the fp32 NHWC noise prediction [B,H,W,out_channels] (a workspace buffer)."""
         P = self.pack(x_in.device)
         B, H, W, cin = x_in.shape
+        self._gnp = {}
         temb_all = self._temb(P, t_dev, ws)
         c0 = self.config.block_out_channels[0]
         h = ws.get("skip0", (B, H, W, c0), torch.float32)
-        ops.gemm([x_in], P["conv_in"][0], c0, out=h, taps=[ops.TAPS_3X3], conv_geom=(B, H, W), bias=P["conv_in"][1])
+        ops.gemm([x_in], P["conv_in"][0], c0, out=h, taps=[ops.TAPS_3X3], conv_geom=(B, H, W), bias=P["conv_in"][1],
+                 gn_partial=self._gnp_new(ws, "skip0", h))
         if taps is not None:
             taps["conv_in"] = h.clone()
         skips, ns = [h], 1
@@ -496,7 +518,8 @@ class B200UNet2DConditionModel(nn.Module):
                 s2d = ws.get("s2d", (Bh, Hh // 2, Wh // 2, 4 * c), torch.bfloat16)
                 ops.space_to_depth(h, s2d)
                 h = ws.get(f"skip{ns}", (Bh, Hh // 2, Wh // 2, c), torch.float32)
-                ops.gemm([s2d], w, c, out=h, taps=[ops.s2d_taps(c)], a_c=[c], conv_geom=(Bh, Hh // 2, Wh // 2), bias=b)
+                ops.gemm([s2d], w, c, out=h, taps=[ops.s2d_taps(c)], a_c=[c], conv_geom=(Bh, Hh // 2, Wh // 2), bias=b,
+                         gn_partial=self._gnp_new(ws, f"skip{ns}", h))
                 skips.append(h)
                 ns += 1
             if taps is not None:
@@ -521,13 +544,14 @@ class B200UNet2DConditionModel(nn.Module):
                 up = ws.get("upx", (Bh, 2 * Hh, 2 * Wh, c), torch.bfloat16)
                 ops.upsample2x(h, up)
                 h = ws.get("up_conv", (Bh, 2 * Hh, 2 * Wh, c), torch.float32)
-                ops.gemm([up], w, c, out=h, taps=[ops.TAPS_3X3], conv_geom=(Bh, 2 * Hh, 2 * Wh), bias=b)
+                ops.gemm([up], w, c, out=h, taps=[ops.TAPS_3X3], conv_geom=(Bh, 2 * Hh, 2 * Wh), bias=b,
+                         gn_partial=self._gnp_new(ws, "up_conv", h))
             if taps is not None:
                 taps[f"up{i}"] = h.clone()
         g, b, eps, groups = P["norm_out"]
         stats = ws.get("gn_stats", (ops.groupnorm_ws_floats(B, groups),), torch.float32)
         xn = ws.get("xn", (B, H, W, c0), torch.bfloat16)
-        ops.groupnorm(h, None, g, b, groups=groups, eps=eps, silu=True, stats_ws=stats, out=xn)
+        ops.groupnorm(h, None, g, b, groups=groups, eps=eps, silu=True, stats_ws=stats, out=xn, partials=(self._gnp_of(h), None))
         cout = self.config.out_channels
         eps_out = ws.get("eps_out", (B, H, W, cout), torch.float32)
         ops.gemm([xn], P["conv_out"][0], cout, out=eps_out, taps=[ops.TAPS_3X3], conv_geom=(B, H, W), bias=P["conv_out"][1])

@@ -87,6 +87,9 @@ typedef struct dfb_gemm_params {
   int32_t geglu;         /* 1: columns come in (16 value | 16 gate) groups; N_out = N / 2  */
   int32_t act;           /* DFB_ACT_* applied after bias/rowbias, before the residual      */
   int32_t block_n;       /* N tile (multiple of 32, <= 256); 0 = choose automatically      */
+  float* gn_partial;     /* NULL, or fp32 [M/32, N/2, 2]: per (32-row block, channel pair) sum and sum of
+                            squares of the fp32 output, emitted from the epilogue for a following GroupNorm
+                            (dfb_groupnorm_fused); needs fp32 output, M % 32 == 0, N % 4 == 0            */
 } dfb_gemm_params;
 
 int dfb_gemm(const dfb_gemm_params* p, void* stream);
@@ -135,6 +138,12 @@ size_t dfb_groupnorm_ws_floats(int B, int groups);
 int dfb_groupnorm(const float* src0, int c0, int ld0, const float* src1, int c1, int ld1, int B, int hw,
                   int groups, float eps, const float* gamma, const float* beta, int silu, float* stats_ws,
                   void* out_bf16, int ld_out, void* raw_out_bf16, int ld_raw, void* stream);
+/* GroupNorm whose statistics come from the producers' epilogues (dfb_gemm_params.gn_partial) instead of an
+ * extra pass over the input: finalize (fixed-order fold of the partials) + apply.  hw % 32 == 0. */
+int dfb_groupnorm_fused(const float* src0, int c0, int ld0, const float* partial0, const float* src1, int c1, int ld1,
+                        const float* partial1, int B, int hw, int groups, float eps, const float* gamma,
+                        const float* beta, int silu, float* stats_ws, void* out_bf16, int ld_out, void* raw_out_bf16,
+                        int ld_raw, void* stream);
 int dfb_layernorm(const float* x, int ld_x, const float* gamma, const float* beta, float eps, void* out_bf16,
                   int ld_out, int rows, int C, void* stream);
 

@@ -173,3 +173,37 @@ def test_gemm_activations():
         ops.gemm([a], wp, 512, out=out, bias=b, act=act)
         torch.cuda.synchronize()
         assert rel_l2(out, fn(y)) < 1e-5
+
+
+@pytest.mark.parametrize("B,H,W,c0,c1", [(2, 64, 64, 320, 0), (3, 16, 16, 640, 320), (2, 8, 8, 1280, 1280), (2, 32, 32, 1280, 640)])
+def test_groupnorm_fused_statistics_from_gemm_epilogue(B, H, W, c0, c1):
+    """The producing conv/GEMM epilogue emits per-(32-row block, channel pair) partial sums; GroupNorm then skips its
+    statistics pass.  Checked against F.group_norm on the producers' actual fp32 outputs."""
+    from difashion_b200 import ops
+    srcs, parts = [], []
+    for i, c in enumerate([c0, c1]):
+        if c == 0:
+            continue
+        a = _r((B * H * W, 64), 60 + i).bfloat16().cuda()
+        w = ops.pack_linear(_r((c, 64), 62 + i, 0.3).cuda())
+        bias = _r((c,), 64 + i).cuda()
+        out = torch.empty(B, H, W, c, dtype=torch.float32, device="cuda")
+        part = torch.zeros(ops.gn_partial_shape(B * H * W, c), dtype=torch.float32, device="cuda")
+        ops.gemm([a], w, c, out=out.view(B * H * W, c), bias=bias, gn_partial=part)
+        torch.cuda.synchronize()
+        # the partials are exact block sums of the stored output
+        ref_s = out.view(B * H * W // 32, 32, c // 2, 2).double().sum(dim=(1, 3))
+        ref_q = (out.view(B * H * W // 32, 32, c // 2, 2).double() ** 2).sum(dim=(1, 3))
+        assert rel_l2(part[..., 0], ref_s) < 1e-5 and rel_l2(part[..., 1], ref_q) < 1e-5
+        srcs.append(out)
+        parts.append(part)
+    C = c0 + c1
+    gamma, beta = _r((C,), 66).cuda(), _r((C,), 67).cuda()
+    ws = torch.empty(ops.groupnorm_ws_floats(B, 32), dtype=torch.float32, device="cuda")
+    o = torch.empty(B, H, W, C, dtype=torch.bfloat16, device="cuda")
+    ops.groupnorm(srcs[0], srcs[1] if c1 else None, gamma, beta, groups=32, eps=1e-5, silu=True, stats_ws=ws, out=o,
+                  partials=(parts[0], parts[1] if c1 else None))
+    torch.cuda.synchronize()
+    x = srcs[0] if not c1 else torch.cat(srcs, -1)
+    ref = F.silu(F.group_norm(x.double().permute(0, 3, 1, 2), 32, gamma.double(), beta.double(), 1e-5)).permute(0, 2, 3, 1)
+    assert rel_l2(o, ref) < 4e-3, err_report(o.reshape(-1, C), ref.reshape(-1, C), "gn fused")
