@@ -546,9 +546,9 @@ extern "C" int dfb_gemm(const dfb_gemm_params* q, void* stream_) {
   DFB_CHECK_CUDA(cudaGetDevice(&dev));
 #define DFB_GEMM_CASE(M_)                                                                                        \
   case M_: {                                                                                                     \
-    constexpr int EW_ = (M_ == EPI_GEGLU) ? 16 : GEMM_EPI_WARPS;                                                 \
-    if (first) DFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<M_, EW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES)); \
-    if (launch) gemm_tcgen05_kernel<M_, EW_><<<grid, 64 + 32 * EW_, GEMM_SMEM_BYTES, stream>>>(maps, kp);        \
+    constexpr int EW_ = ((M_) == EPI_GEGLU) ? 16 : GEMM_EPI_WARPS;                                                 \
+    if (first) DFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<(M_), EW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES)); \
+    if (launch) gemm_tcgen05_kernel<(M_), EW_><<<grid, 64 + 32 * EW_, GEMM_SMEM_BYTES, stream>>>(maps, kp);        \
   } break;
   const bool need_attr = dev >= 0 && dev < 64 && !attr_done[dev];
   for (int pass = need_attr ? 0 : 1; pass < 2; ++pass) {
