@@ -388,7 +388,10 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ A
 //                  against the running reference max -> P[j&1] -> arrive p_full[j&1]
 // K/V tiles flow through a 3-stage TMA ring.
 // =================================================================================================
-template <int KV>
+// PT: the probabilities go back into tensor memory (over the score buffer they came from) and O += P V reads
+// its A operand from TMEM (tcgen05.mma TS form): no P round trip through shared memory, no proxy fence, and the
+// PV MMA no longer pays the 4 KB-per-instruction shared-memory A fetch.
+template <int KV, bool PT>
 __global__ void __launch_bounds__(ATT_THREADS, KV == 64 ? 2 : 1)
 attn_fwd_db_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnKernelParams p) {
   constexpr int NST_MAX = 3;
@@ -402,7 +405,7 @@ attn_fwd_db_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant_
   constexpr uint32_t p_bytes = (KV / 16) * ATT_BLOCK_Q * 32u;
   const uint32_t sQ = smem_base;
   const uint32_t sP = sQ + q_bytes;                                        // P[0], P[1]
-  const uint32_t sKV = sP + 2 * p_bytes;                                   // stage s: K then V
+  const uint32_t sKV = sP + (PT ? 0u : 2 * p_bytes);                        // stage s: K then V
   const uint32_t bar_base = sKV + NST * 2 * kv_tile_bytes;
   const uint32_t q_full = bar_base;
   auto s_full = [&](int i) { return bar_base + 8u + 8u * i; };
@@ -503,8 +506,12 @@ attn_fwd_db_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant_
         const uint64_t dv = desc_v0 + (uint64_t)((uint32_t)st * stage_step);
         const uint64_t dp = desc_p0 + (uint64_t)((uint32_t)bi * (p_bytes >> 4));
 #pragma unroll
-        for (int k = 0; k < KV / 16; ++k)
-          umma_f16_ss(tmem_O, dp + (uint64_t)(k * (ATT_BLOCK_Q * 32 / 16)), dv + (uint64_t)(k * (512 / 16)), idesc_pv, (j | k) != 0);
+        for (int k = 0; k < KV / 16; ++k) {
+          if constexpr (PT)
+            umma_f16_ts(tmem_O, tmem_base + (uint32_t)bi * KV + (uint32_t)(8 * k), dv + (uint64_t)(k * (512 / 16)), idesc_pv, (j | k) != 0);
+          else
+            umma_f16_ss(tmem_O, dp + (uint64_t)(k * (ATT_BLOCK_Q * 32 / 16)), dv + (uint64_t)(k * (512 / 16)), idesc_pv, (j | k) != 0);
+        }
         umma_commit(o_done(bi));
         umma_commit(kv_empty(st));
       }
@@ -526,11 +533,12 @@ attn_fwd_db_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant_
       const uint32_t p_row = sP + (uint32_t)bi * p_bytes + (uint32_t)row * 32u;
       if (tls && j < 60) p.timeline[j * 8 + 0] = clock64();
       mbar_wait(s_full(bi), (uint32_t)(j >> 1) & 1u);
-      if (j >= 2) mbar_wait(o_done(bi), (uint32_t)((j >> 1) - 1) & 1u);     // PV_{j-2} retired: P[bi] is free
+      if (!PT && j >= 2) mbar_wait(o_done(bi), (uint32_t)((j >> 1) - 1) & 1u);     // PV_{j-2} retired: P[bi] is free
       tc_fence_after();
       if (tls && j < 60) p.timeline[j * 8 + 1] = clock64();
       const int kv_valid = min(KV, p.Skv - j * KV);
       uint32_t sreg[KV];
+      uint32_t pw[PT ? KV / 2 : 1];            // packed bf16 probabilities (TMEM path)
       bool careful = (kv_valid != KV) || (j == 0);
       float mx = -INFINITY;
       if (!careful) {
@@ -555,11 +563,16 @@ attn_fwd_db_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant_
               pv[i] = ex2f(fmaf(sv, p.scale_log2, -m_ref));
               l8[i & 7] += pv[i];
             }
-            const uint32_t dst = p_row + (uint32_t)(c * 2 + h) * ATT_BLOCK_Q * 32u;
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (0u ^ flip)), "r"(pack_bf16x2(pv[0], pv[1])),
-                         "r"(pack_bf16x2(pv[2], pv[3])), "r"(pack_bf16x2(pv[4], pv[5])), "r"(pack_bf16x2(pv[6], pv[7])) : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (16u ^ flip)), "r"(pack_bf16x2(pv[8], pv[9])),
-                         "r"(pack_bf16x2(pv[10], pv[11])), "r"(pack_bf16x2(pv[12], pv[13])), "r"(pack_bf16x2(pv[14], pv[15])) : "memory");
+            if constexpr (PT) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) pw[(c * 2 + h) * 8 + i] = pack_bf16x2(pv[2 * i], pv[2 * i + 1]);
+            } else {
+              const uint32_t dst = p_row + (uint32_t)(c * 2 + h) * ATT_BLOCK_Q * 32u;
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (0u ^ flip)), "r"(pack_bf16x2(pv[0], pv[1])),
+                           "r"(pack_bf16x2(pv[2], pv[3])), "r"(pack_bf16x2(pv[4], pv[5])), "r"(pack_bf16x2(pv[6], pv[7])) : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (16u ^ flip)), "r"(pack_bf16x2(pv[8], pv[9])),
+                           "r"(pack_bf16x2(pv[10], pv[11])), "r"(pack_bf16x2(pv[12], pv[13])), "r"(pack_bf16x2(pv[14], pv[15])) : "memory");
+            }
           }
         }
         mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7]))) * p.scale_log2;
@@ -608,16 +621,29 @@ attn_fwd_db_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant_
             pv[i] = (c * 16 + i < kv_valid) ? e : 0.f;
             l4[i & 3] += pv[i];
           }
-          const uint32_t dst = p_row + (uint32_t)c * ATT_BLOCK_Q * 32u;
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (0u ^ flip)), "r"(pack_bf16x2(pv[0], pv[1])),
-                       "r"(pack_bf16x2(pv[2], pv[3])), "r"(pack_bf16x2(pv[4], pv[5])), "r"(pack_bf16x2(pv[6], pv[7])) : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (16u ^ flip)), "r"(pack_bf16x2(pv[8], pv[9])),
-                       "r"(pack_bf16x2(pv[10], pv[11])), "r"(pack_bf16x2(pv[12], pv[13])), "r"(pack_bf16x2(pv[14], pv[15])) : "memory");
+          if constexpr (PT) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pw[c * 8 + i] = pack_bf16x2(pv[2 * i], pv[2 * i + 1]);
+          } else {
+            const uint32_t dst = p_row + (uint32_t)c * ATT_BLOCK_Q * 32u;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (0u ^ flip)), "r"(pack_bf16x2(pv[0], pv[1])),
+                         "r"(pack_bf16x2(pv[2], pv[3])), "r"(pack_bf16x2(pv[4], pv[5])), "r"(pack_bf16x2(pv[6], pv[7])) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (16u ^ flip)), "r"(pack_bf16x2(pv[8], pv[9])),
+                         "r"(pack_bf16x2(pv[10], pv[11])), "r"(pack_bf16x2(pv[12], pv[13])), "r"(pack_bf16x2(pv[14], pv[15])) : "memory");
+          }
         }
         l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
       }
       if (tls && j < 60) p.timeline[j * 8 + 2] = clock64();
-      fence_proxy_async_smem();     // generic-proxy P writes -> visible to the tensor core's async proxy
+      if constexpr (PT) {
+        // P (bf16, two per column) over the first KV/2 columns of the score buffer it was computed from
+#pragma unroll
+        for (int c = 0; c < KV / 64; ++c)
+          tmem_st_32x32b_x32(tS + (uint32_t)(c * 32), *reinterpret_cast<uint32_t(*)[32]>(&pw[c * 32]));
+        tmem_st_wait();
+      } else {
+        fence_proxy_async_smem();   // generic-proxy P writes -> visible to the tensor core's async proxy
+      }
       tc_fence_before();
       mbar_arrive(p_full(bi));
       if (tls && j < 60) p.timeline[j * 8 + 3] = clock64();
@@ -723,10 +749,11 @@ extern "C" int dfb_attention(const dfb_attn_params* a, void* stream_) {
   }
 
   const int dch = a->dp / 16;
+  const bool p_tmem = use_db && (a->dbg_flags & 16) != 0;     // tuning hook: P through tensor memory (TS MMA)
   size_t smem;
   if (use_db) {
     // 3 K/V stages when two CTAs still fit per SM with them, else 2
-    const size_t fixed = 1024 + (size_t)dch * ATT_BLOCK_Q * 32 + 2 * (size_t)(bkv / 16) * ATT_BLOCK_Q * 32 + 256;
+    const size_t fixed = 1024 + (size_t)dch * ATT_BLOCK_Q * 32 + (p_tmem ? 0 : 2 * (size_t)(bkv / 16) * ATT_BLOCK_Q * 32) + 256;
     const size_t stage = (size_t)2 * dch * bkv * 32;
     kp.kv_stages = (fixed + 3 * stage + 1024 <= (size_t)113 * 1024 || fixed + 2 * stage + 1024 > (size_t)113 * 1024) ? 3 : 2;
     smem = fixed + (size_t)kp.kv_stages * stage;
@@ -743,15 +770,21 @@ extern "C" int dfb_attention(const dfb_attn_params* a, void* stream_) {
     DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_db_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_db_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_db_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_db_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_db_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_db_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     attr_set[dev] = true;
   }
   dim3 grid((a->Sq + ATT_BLOCK_Q - 1) / ATT_BLOCK_Q, a->heads, a->B);
-  if (use_db && bkv == 64)
-    attn_fwd_db_kernel<64><<<grid, ATT_THREADS, smem, stream>>>(maps, kp);
+  if (use_db && bkv == 64 && p_tmem)
+    attn_fwd_db_kernel<64, true><<<grid, ATT_THREADS, smem, stream>>>(maps, kp);
+  else if (use_db && bkv == 64)
+    attn_fwd_db_kernel<64, false><<<grid, ATT_THREADS, smem, stream>>>(maps, kp);
+  else if (use_db && p_tmem)
+    attn_fwd_db_kernel<128, true><<<grid, ATT_THREADS, smem, stream>>>(maps, kp);
   else if (use_db)
-    attn_fwd_db_kernel<128><<<grid, ATT_THREADS, smem, stream>>>(maps, kp);
+    attn_fwd_db_kernel<128, false><<<grid, ATT_THREADS, smem, stream>>>(maps, kp);
   else if (bkv == 128)
     attn_fwd_kernel<128><<<grid, ATT_THREADS, smem, stream>>>(maps, kp);
   else if (bkv == 64)

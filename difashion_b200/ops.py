@@ -231,12 +231,12 @@ def groupnorm_ws_floats(b: int, groups: int) -> int:
     return int(_lib.load().dfb_groupnorm_ws_floats(b, groups))
 
 
-@_profiled("groupnorm")
 def gn_partial_shape(m_rows: int, n: int):
     """Shape of the GroupNorm partial-statistics buffer a GEMM epilogue emits for an fp32 ``[m_rows, n]`` output."""
     return (m_rows // 32, n // 2, 2)
 
 
+@_profiled("groupnorm")
 def groupnorm(src0: torch.Tensor, src1: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor, *,
               groups: int, eps: float, silu: bool, stats_ws: torch.Tensor, out: torch.Tensor,
               raw_out: Optional[torch.Tensor] = None, partials: Optional[Sequence[Optional[torch.Tensor]]] = None) -> torch.Tensor:
