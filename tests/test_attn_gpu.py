@@ -74,8 +74,8 @@ def test_attention_fused_qkv_layout_and_large_logits():
 
 @pytest.mark.parametrize("B,H,Sq,Skv,d,bkv", [(2, 8, 1024, 1024, 40, 64), (2, 8, 512, 512, 40, 128), (1, 1, 200, 300, 16, 64),
                                                (2, 8, 256, 256, 160, 64), (2, 4, 384, 1000, 80, 64)])
-def test_attention_p_through_tensor_memory(B, H, Sq, Skv, d, bkv):
-    """Tuning variant: probabilities written back to TMEM, O += P V with the A operand from tensor memory."""
+def test_attention_variants_smem_p_and_single_buffer(B, H, Sq, Skv, d, bkv):
+    """Non-default variants behind the tuning hooks: P through shared memory (bit4) and the single-buffer kernel (bit3)."""
     from difashion_b200 import ops
     g = torch.Generator().manual_seed(Sq + Skv + d)
     q = torch.randn(B, Sq, H * d, generator=g).bfloat16().cuda()
@@ -84,8 +84,10 @@ def test_attention_p_through_tensor_memory(B, H, Sq, Skv, d, bkv):
     dp = ops.pad16(d)
     qp, kp, vp = (_pad_heads(t, H, d, dp).contiguous() for t in (q, k, v))
     out = torch.full((B, Sq, H * dp), float("nan"), dtype=torch.bfloat16, device="cuda")
-    ops.attention(qp, kp, vp, out, heads=H, dp=dp, scale=d ** -0.5, block_kv=bkv, dbg_flags=16)
-    torch.cuda.synchronize()
-    got = out.reshape(B, Sq, H, dp)[..., :d].reshape(B, Sq, H * d)
     ref = _ref(q, k, v, H, d, d ** -0.5)
-    assert rel_l2(got, ref) < 1e-2, err_report(got.reshape(-1, H * d), ref.reshape(-1, H * d), "attn TS")
+    for flags in (16, 8):
+        out.fill_(float("nan"))
+        ops.attention(qp, kp, vp, out, heads=H, dp=dp, scale=d ** -0.5, block_kv=bkv, dbg_flags=flags)
+        torch.cuda.synchronize()
+        got = out.reshape(B, Sq, H, dp)[..., :d].reshape(B, Sq, H * d)
+        assert rel_l2(got, ref) < 1e-2, err_report(got.reshape(-1, H * d), ref.reshape(-1, H * d), f"attn flags={flags}")

@@ -15,12 +15,12 @@ def run(flags, bkv=0, reps=5):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
 tiles = B * 8 * 32 * 32 / 148
-for name, flags, bkv in [("double-buffer KV=64 (smem P)", 0, 64), ("double-buffer KV=64, P in TMEM", 16, 64),
-                         ("double-buffer KV=128 (smem P, 1 CTA/SM)", 0, 128), ("double-buffer KV=128, P in TMEM (1 CTA/SM)", 16, 128)]:
+for name, flags, bkv in [("double-buffer KV=64 (smem P)", 16, 64), ("double-buffer KV=64, P in TMEM (default)", 0, 64),
+                         ("double-buffer KV=128 (smem P, 1 CTA/SM)", 16, 128), ("double-buffer KV=128, P in TMEM (1 CTA/SM)", 0, 128)]:
     ms = run(flags, bkv)
     print(f"{name:44s} {ms:8.3f} ms -> {ms * 1e-3 * 1.9e9 / tiles:7.0f} cycles per 128x128 tile per SM (@1.9GHz)")
 tl = torch.zeros(4096, dtype=torch.int64, device="cuda")
-ops.attention(qkv[..., :384], qkv[..., 384:768], qkv[..., 768:], o, heads=8, dp=48, scale=40 ** -0.5, block_kv=64, dbg_flags=16, dbg_timeline=tl)
+ops.attention(qkv[..., :384], qkv[..., 384:768], qkv[..., 768:], o, heads=8, dp=48, scale=40 ** -0.5, block_kv=64, dbg_timeline=tl)
 torch.cuda.synchronize()
 t = tl.cpu().tolist()
 base = t[8 * 8]
