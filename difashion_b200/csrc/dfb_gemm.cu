@@ -1,9 +1,9 @@
 // Persistent warp-specialised tcgen05 GEMM / implicit-GEMM convolution for sm_100a.
 //
-//   warp 0      : TMA producer  (A tile 128x64 bf16 via 2-D or 4-D tiled tensor map, OOB = zero
+//   warp EW     : TMA producer  (A tile 128x64 bf16 via 2-D or 4-D tiled tensor map, OOB = zero
 //                 gives the 3x3 'same' padding for free; B tile block_n x 64)
-//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=block_n, K=16)
-//   warps 2..9  : epilogue (tcgen05.ld -> registers -> swizzled smem transpose -> row-coalesced
+//   warp EW+1   : TMEM allocator + single-lane tcgen05.mma issuer (M=128, N=block_n, K=16)
+//   warps 0..EW-1: epilogue (tcgen05.ld -> registers -> swizzled smem transpose -> row-coalesced
 //                 bias / time-embedding row bias / activation / residual / GEGLU -> bf16 or fp32
 //                 global stores touching full 128-byte rows)
 //
@@ -73,12 +73,16 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * GEMM_STAGES + 2 + s); };
   const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * GEMM_STAGES + 4);
 
+  // Roles: warps 0..EW-1 epilogue (TMEM lane quarter = warp & 3), warp EW TMA producer, warp EW+1 MMA issuer.
+  // The issue arbiter favours the highest warp id of a scheduler, so the two single-lane control warps sit
+  // above the issue-heavy epilogue warps (otherwise their TMA / MMA issue is starved).
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  constexpr int W_TMA = EW, W_MMA = EW + 1;
   const int num_tiles = p.n_tiles_m * p.n_tiles_n;
   const int nk = p.seg_ntaps[0] * p.seg_ncblk[0] + (p.nseg > 1 ? p.seg_ntaps[1] * p.seg_ncblk[1] : 0);
 
-  if (warp == 0 && lane == 0) {
+  if (warp == W_TMA && lane == 0) {
     tma_prefetch_desc(&maps.a[0]);
     if (p.nseg > 1) tma_prefetch_desc(&maps.a[1]);
     tma_prefetch_desc(&maps.b);
@@ -93,14 +97,14 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
     fence_mbar_init();
     fence_proxy_async_smem();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr_smem, GEMM_TMEM_COLS);
+  if (warp == W_MMA) tmem_alloc(tmem_ptr_smem, GEMM_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
-  if (warp == 0) {
+  if (warp == W_TMA) {
     // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
     int stage = 0;
     uint32_t phase = 0;
@@ -141,7 +145,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == W_MMA) {
     // ===================== MMA issuer =====================
     // The whole warp runs the (warp-uniform) loop so that descriptors live in uniform registers; one
     // elected lane issues tcgen05.mma / tcgen05.commit.
@@ -176,12 +180,12 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
       }
     }
   } else {
-    // ===================== epilogue warps (2..9) =====================
+    // ===================== epilogue warps (0..EW-1) =====================
     // Two warps per TMEM lane quarter; each takes every other 32-column chunk.  Accumulators go
     // TMEM -> registers (thread = row) -> a per-warp swizzled smem tile -> registers in a
     // row-coalesced layout (8 lanes x 16 B per row), where bias / time-embedding row bias /
     // activation / residual are applied and global memory is touched with full 128-byte rows.
-    const int ew = warp - 2;
+    const int ew = warp;
     const int quarter = warp & 3;              // TMEM lane quarter this warp may access
     const int half = ew >> 2;                  // which share of the chunks (0 .. EW/4-1)
     const uint32_t stg = smem_base + GEMM_STAGES * GEMM_STAGE_BYTES + (uint32_t)ew * (GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES / EW);
@@ -394,7 +398,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == W_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, GEMM_TMEM_COLS);
   }
