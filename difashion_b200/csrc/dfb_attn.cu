@@ -49,20 +49,8 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
-// exp2 on the FMA/ALU pipes (Cody-Waite range reduction + degree-4 polynomial, |rel err| < 5e-5, far below
-// the bf16 rounding of P).  The MUFU does 16 ex2/clk/SM and saturates inside the softmax phase, so a fixed
-// 3-of-16 share of the exponentials is moved here (the balance point of MUFU time vs issue slots).
-__device__ __forceinline__ float ex2_poly(float x) {
-  x = fmaxf(x, -125.0f);
-  const float t = x + 12582912.0f;                 // 1.5 * 2^23: rounds x to the nearest integer n in the low mantissa bits
-  const float f = x - (t - 12582912.0f);           // f in [-0.5, 0.5]
-  float p = fmaf(0.00961812911f, f, 0.0555041087f);
-  p = fmaf(p, f, 0.240226507f);
-  p = fmaf(p, f, 0.693147181f);
-  p = fmaf(p, f, 1.0f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));   // p * 2^n
-}
-
+// (Measured and rejected: moving 3/16 of the exponentials to an FMA-pipe polynomial.  With two CTAs per SM the
+// softmax warps then become issue-bound and the kernel gets 13 % slower — profiles/r01_attention_experiments.md.)
 // KV_STATIC > 0: block_kv == KV_STATIC, the score row is held in registers (one TMEM pass);
 // KV_STATIC == 0: any block_kv (multiple of 16), two TMEM passes (max, then exponentials).
 template <int KV_STATIC>
@@ -578,8 +566,7 @@ attn_fwd_db_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant_
             for (int i = 0; i < 16; ++i) {
               const float sv = __uint_as_float(sreg[c * 32 + h * 16 + i]);
               m8[i & 7] = fmaxf(m8[i & 7], sv);
-              const float xe = fmaf(sv, p.scale_log2, -m_ref);
-              pv[i] = (i == 2 || i == 7 || i == 13) ? ex2_poly(xe) : ex2f(xe);     // 3/16 on the FMA pipe
+              pv[i] = ex2f(fmaf(sv, p.scale_log2, -m_ref));
               l8[i & 7] += pv[i];
             }
             if constexpr (PT) {
