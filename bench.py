@@ -47,6 +47,20 @@ def _peaks():
     return dict(hbm=6650.0, burst=1590.0, sustained=1400.0, src="fallback")
 
 
+def _ncu_traffic():
+    """DRAM bytes per launch of the tcgen05 GEMM/conv kernel (dram__bytes_read.sum + dram__bytes_write.sum summed over the
+    185 launches of one step / 185) from the newest committed ncu capture of tools/step_traffic.py, or None."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_step_traffic_v*.json")),
+                   key=lambda f: int(f.rsplit("_v", 1)[1].split(".")[0]))
+    if not files:
+        return None, None
+    with open(files[-1]) as f:
+        d = json.load(f)
+    fam = d.get("families", {}).get("gemm_tcgen05_kernel")
+    return (fam["dram_bytes_per_launch"], os.path.basename(files[-1])) if fam else (None, None)
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock + throttle reasons of one GPU via NVML while the timed region runs."""
 
@@ -280,10 +294,12 @@ def main():
     mma_launches = kinds.get("gemm", [0, 0, 0])[2] + kinds.get("conv", [0, 0, 0])[2]
     gemm_alg_flops = rows * (F_ROW - F_ROW_ATTN_CORE)
     achieved = gemm_alg_flops / (mma_ms / 1e3) / 1e12 if mma_ms > 0 else 0.0
+    traffic, traffic_src = _ncu_traffic()
     roofline = {
         "bound": "tensor", "kernel": "gemm_tcgen05_kernel (all conv3x3 / 1x1 / linear launches of one step)",
         "achieved": achieved, "peak": peaks["sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["sustained"],
-        "traffic": None, "peak_source": f"{peaks['src']} (bf16_tflops_sustained; burst {peaks['burst']})",
+        "traffic": traffic, "traffic_unit": "bytes per launch (DRAM read+write, ncu)", "traffic_source": traffic_src,
+        "algorithmic_flop_per_launch": gemm_alg_flops / mma_launches if mma_launches else None, "peak_source": f"{peaks['src']} (bf16_tflops_sustained; burst {peaks['burst']})",
         "launches_per_step": mma_launches, "kernel_ms_per_step": mma_ms, "kernel_share_of_step": mma_ms / eager_ms if eager_ms else None,
         "attention_ms_per_step": kinds.get("attention", [0, 0, 0])[0],
         "step_achieved": step_tflops, "step_frac": step_tflops / peaks["sustained"], "step_frac_of_burst": step_tflops / peaks["burst"],

@@ -248,6 +248,9 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// SiLU with the approximate reciprocal (rcp.approx: 1 ulp) instead of the IEEE division sequence; the result
+// is rounded to bf16 by every caller.
+__device__ __forceinline__ float silu_fast_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf_f(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
@@ -262,6 +265,19 @@ __device__ __forceinline__ float gelu_fast_f(float x) {
   poly = fmaf(poly, t, 0.254829592f);
   const float erf_abs = 1.0f - poly * t * __expf(-z * z);
   return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
+
+// erf-GELU for the GEGLU epilogue (issue-bound: 16 gates per thread per chunk): g * Phi(g) with
+// Phi(g) = sigmoid(2 g q(g^2)), q an even polynomial fitted to the exact erf form (max abs error of the
+// result 2.7e-5 for every g — 1/20 of the bf16 rounding of the product it feeds; tools/fit_gelu.py).
+// 4 FMA-pipe ops + clamp + ex2 + rcp instead of the 17 of the A&S form.  Coefficients carry -2*log2(e).
+__device__ __forceinline__ float gelu_sigmoid_f(float x) {
+  const float x2 = fminf(x * x, 64.0f);
+  float q = fmaf(0.0010188621236011386f, x2, -0.10680417716503143f);
+  q = fmaf(q, x2, -2.3010897636413574f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * q));
+  return __fdividef(x, 1.0f + e);
 }
 
 }  // namespace dfb

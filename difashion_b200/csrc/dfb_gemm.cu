@@ -197,6 +197,24 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
     const bool f_rowbias = kGeneric ? (p.rowbias != nullptr) : ((MODE & EPI_ROWBIAS) != 0);
     const bool f_vec = kGeneric ? (p.vec_ok != 0) : true;       // specialised modes require aligned, N % 4 == 0
     const int f_act = kGeneric ? p.act : 0;
+    // Residual reads are software-pipelined one chunk ahead (across tile boundaries too): small-K GEMMs with an
+    // fp32 residual are HBM-latency-bound in the epilogue, so every warp keeps a second 4 KB of loads in flight
+    // while it transposes / stores the current chunk.
+    constexpr bool kPipeRes = !kGeneric && (MODE & EPI_RES_F32) != 0;
+    constexpr int CSTEP = EW / 4;
+    float4 resn[8];
+    int pf_tile = -1, pf_c = -1;
+    auto load_res = [&](int mt_, int nt_, int c_, float4 (&dst)[8]) {
+      const int r0 = mt_ * GEMM_BLOCK_M + quarter * 32 + (lane >> 3);
+      const int col_ = nt_ * p.block_n + c_ * 32 + 4 * (lane & 7);
+      const bool ok = col_ + 4 <= p.N;
+      const float* rp = reinterpret_cast<const float*>(p.residual) + (size_t)r0 * p.res_ld + col_;
+#pragma unroll
+      for (int itr = 0; itr < 8; ++itr) {
+        dst[itr] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok && r0 + itr * 4 < p.M) dst[itr] = __ldg(reinterpret_cast<const float4*>(rp + (size_t)(itr * 4) * p.res_ld));
+      }
+    };
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int mt = tile / p.n_tiles_n;
@@ -207,7 +225,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * GEMM_MAX_BLOCK_N;
       const bool full_rows = row0 + 32 <= p.M;                 // warp-uniform: no row masking needed
       bool waited = false;
-      for (int c = half; c < p.block_n / 32; c += EW / 4) {
+      // the warps of a lane quarter rotate their first chunk from tile to tile, so an odd chunk count
+      // (block_n = 160: 5 chunks over 2 warps) balances over consecutive tiles
+      for (int c = (half + it) % CSTEP; c < p.block_n / 32; c += CSTEP) {
         const int n0 = nt * p.block_n + c * 32;
         if (n0 >= p.N) break;                  // warp-uniform
         if (f_geglu) {
@@ -217,11 +237,23 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
           tmem_ld_wait();
           // row layout: columns [0,16) = values, [16,32) = gates of output columns n0/2 .. n0/2+15
           float o[16];
+          if (!kGeneric && p.bias) {     // specialised mode: bias is 16-byte aligned, N % 32 == 0 -> uniform float4 loads
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float a = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + n0 + j) : 0.f);
-            const float g = __uint_as_float(r[16 + j]) + (p.bias ? __ldg(p.bias + n0 + 16 + j) : 0.f);
-            o[j] = a * gelu_fast_f(g);
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 bv = __ldg(bp + j4), bg = __ldg(bp + 4 + j4);
+              o[4 * j4 + 0] = (__uint_as_float(r[4 * j4 + 0]) + bv.x) * gelu_sigmoid_f(__uint_as_float(r[16 + 4 * j4 + 0]) + bg.x);
+              o[4 * j4 + 1] = (__uint_as_float(r[4 * j4 + 1]) + bv.y) * gelu_sigmoid_f(__uint_as_float(r[16 + 4 * j4 + 1]) + bg.y);
+              o[4 * j4 + 2] = (__uint_as_float(r[4 * j4 + 2]) + bv.z) * gelu_sigmoid_f(__uint_as_float(r[16 + 4 * j4 + 2]) + bg.z);
+              o[4 * j4 + 3] = (__uint_as_float(r[4 * j4 + 3]) + bv.w) * gelu_sigmoid_f(__uint_as_float(r[16 + 4 * j4 + 3]) + bg.w);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float a = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + n0 + j) : 0.f);
+              const float g = __uint_as_float(r[16 + j]) + (p.bias ? __ldg(p.bias + n0 + 16 + j) : 0.f);
+              o[j] = a * gelu_sigmoid_f(g);
+            }
           }
           // staging tile [32 rows][64 B], 64-byte swizzle
 #pragma unroll
@@ -251,6 +283,124 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
                 if (f_vec) *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
                 else { dst[0] = __float2bfloat16(x.x); dst[1] = __float2bfloat16(x.y); dst[2] = __float2bfloat16(x.z); dst[3] = __float2bfloat16(x.w); }
               }
+            }
+          }
+          __syncwarp();
+          continue;
+        }
+        if constexpr (!kGeneric) {
+          // ---- specialised epilogue (aligned, N % 4 == 0, no activation): straight-line code.  lane -> 4 columns
+          //      (u) x 8 rows (rsub + 4 * itr); a lane has either all 4 of its columns or none. ----
+          const int u = lane & 7, rsub = lane >> 3;
+          const int col = n0 + 4 * u;
+          const bool lane_ok = col < p.N;
+          float4 resv[8];
+          if constexpr (kPipeRes) {
+            if (pf_tile == tile && pf_c == c) {
+#pragma unroll
+              for (int itr = 0; itr < 8; ++itr) resv[itr] = resn[itr];
+            } else {
+              load_res(mt, nt, c, resv);
+            }
+            // this warp's next chunk: same tile, or its first chunk of the CTA's next tile
+            int ntile = tile, nc = c + CSTEP;
+            if (nc >= p.block_n / 32 || nt * p.block_n + nc * 32 >= p.N) {
+              ntile = tile + (int)gridDim.x;
+              nc = (half + it + 1) % CSTEP;
+            }
+            pf_tile = -1;
+            if (ntile < num_tiles) {
+              const int nmt = ntile / p.n_tiles_n, nnt = ntile - nmt * p.n_tiles_n;
+              if (nc < p.block_n / 32 && nnt * p.block_n + nc * 32 < p.N) {
+                load_res(nmt, nnt, nc, resn);
+                pf_tile = ntile;
+                pf_c = nc;
+              }
+            }
+          }
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (lane_ok) {
+            if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+            if constexpr ((MODE & EPI_ROWBIAS) != 0) {
+              // rows_per_batch % 32 == 0 (checked on the host): the warp's 32 rows share one batch row
+              const int rbrow = min(row0, p.M - 1) / p.rows_per_batch;
+              const float4 t = __ldg(reinterpret_cast<const float4*>(p.rowbias + (size_t)rbrow * p.rowbias_ld + col));
+              b4.x += t.x; b4.y += t.y; b4.z += t.z; b4.w += t.w;
+            }
+          }
+          if (!waited) { mbar_wait(tfull_bar(as), aphase); tc_fence_after(); waited = true; }
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr0 + (uint32_t)(c * 32), r);
+          tmem_ld_wait();
+          // staging tile [32 rows][128 B], 128-byte swizzle
+#pragma unroll
+          for (int u2 = 0; u2 < 8; ++u2) {
+            const uint32_t dst = stg + (uint32_t)lane * 128u + (uint32_t)((u2 ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(r[4 * u2]), "r"(r[4 * u2 + 1]),
+                         "r"(r[4 * u2 + 2]), "r"(r[4 * u2 + 3]) : "memory");
+          }
+          __syncwarp();
+          float4 x[8];
+#pragma unroll
+          for (int itr = 0; itr < 8; ++itr) {
+            const int rr = itr * 4 + rsub;
+            const uint32_t src = stg + (uint32_t)rr * 128u + (uint32_t)((u ^ (rr & 7)) << 4);
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[itr].x), "=f"(x[itr].y), "=f"(x[itr].z), "=f"(x[itr].w) : "r"(src));
+          }
+#pragma unroll
+          for (int itr = 0; itr < 8; ++itr) {
+            x[itr].x += b4.x; x[itr].y += b4.y; x[itr].z += b4.z; x[itr].w += b4.w;
+            if constexpr ((MODE & EPI_RES_F32) != 0) {
+              x[itr].x += resv[itr].x; x[itr].y += resv[itr].y; x[itr].z += resv[itr].z; x[itr].w += resv[itr].w;
+            }
+          }
+          const bool f_gn = (MODE & EPI_OUT_F32) != 0 && p.gn_partial != nullptr;
+          if (f_gn) {
+            // (sum, sumsq) of this lane's two channel pairs over the warp's 32 rows (gn_partial needs M % 32 == 0,
+            // so every row is valid): fold the 4 row groups, lanes 0..7 write 128 contiguous bytes per chunk
+            float gs0 = 0.f, gq0 = 0.f, gs1 = 0.f, gq1 = 0.f;
+#pragma unroll
+            for (int itr = 0; itr < 8; ++itr) {
+              gs0 += x[itr].x + x[itr].y; gq0 += x[itr].x * x[itr].x + x[itr].y * x[itr].y;
+              gs1 += x[itr].z + x[itr].w; gq1 += x[itr].z * x[itr].z + x[itr].w * x[itr].w;
+            }
+#pragma unroll
+            for (int o = 8; o <= 16; o <<= 1) {
+              gs0 += __shfl_xor_sync(0xffffffffu, gs0, o); gq0 += __shfl_xor_sync(0xffffffffu, gq0, o);
+              gs1 += __shfl_xor_sync(0xffffffffu, gs1, o); gq1 += __shfl_xor_sync(0xffffffffu, gq1, o);
+            }
+            if (lane < 8 && lane_ok && row0 < p.M)
+              *reinterpret_cast<float4*>(p.gn_partial + ((size_t)(row0 >> 5) * (size_t)(p.N >> 1) + (size_t)(col >> 1)) * 2) =
+                  make_float4(gs0, gq0, gs1, gq1);
+          }
+          const int mrow = row0 + rsub;
+          if constexpr ((MODE & EPI_OUT_F32) != 0) {
+            float* op = reinterpret_cast<float*>(p.out) + (size_t)mrow * p.out_ld + col;
+            const size_t ostep = (size_t)4 * p.out_ld;
+            if (full_rows) {
+              if (lane_ok) {
+#pragma unroll
+                for (int itr = 0; itr < 8; ++itr) *reinterpret_cast<float4*>(op + itr * ostep) = x[itr];
+              }
+            } else {
+#pragma unroll
+              for (int itr = 0; itr < 8; ++itr)
+                if (lane_ok && mrow + itr * 4 < p.M) *reinterpret_cast<float4*>(op + itr * ostep) = x[itr];
+            }
+          } else {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)mrow * p.out_ld + col;
+            const size_t ostep = (size_t)4 * p.out_ld;
+            if (full_rows) {
+              if (lane_ok) {
+#pragma unroll
+                for (int itr = 0; itr < 8; ++itr)
+                  *reinterpret_cast<uint2*>(op + itr * ostep) = make_uint2(pack_bf16x2(x[itr].x, x[itr].y), pack_bf16x2(x[itr].z, x[itr].w));
+              }
+            } else {
+#pragma unroll
+              for (int itr = 0; itr < 8; ++itr)
+                if (lane_ok && mrow + itr * 4 < p.M)
+                  *reinterpret_cast<uint2*>(op + itr * ostep) = make_uint2(pack_bf16x2(x[itr].x, x[itr].y), pack_bf16x2(x[itr].z, x[itr].w));
             }
           }
           __syncwarp();
@@ -531,7 +681,8 @@ extern "C" int dfb_gemm(const dfb_gemm_params* q, void* stream_) {
   int mode = EPI_GENERIC;
   const bool simple = kp.vec_ok && (q->N % 4) == 0 && kp.act == 0 && (q->residual == nullptr || kp.res_fp32) &&
                       (q->bias == nullptr || (reinterpret_cast<uintptr_t>(q->bias) & 15) == 0) &&
-                      (q->rowbias == nullptr || kp.rows_per_batch >= 32);
+                      (q->rowbias == nullptr || (kp.rows_per_batch % 32 == 0 && (q->rowbias_ld % 4) == 0 &&
+                                                 (reinterpret_cast<uintptr_t>(q->rowbias) & 15) == 0));
   if (simple) {
     if (kp.geglu) {
       if (!kp.out_fp32) mode = EPI_GEGLU;

@@ -138,3 +138,54 @@ def test_conv3x3_plus_shortcut_segment_and_rowbias():
            + F.conv2d(xr.double().permute(0, 3, 1, 2), ws.bfloat16().double())
            + temb.double()[:, :, None, None]).permute(0, 2, 3, 1)
     assert rel_l2(out, ref) < 1e-5, err_report(out.reshape(-1, Cout), ref.reshape(-1, Cout), "conv+shortcut")
+
+
+@pytest.mark.parametrize("M,N,K,out_dtype", [
+    (25600, 320, 384, torch.float32),      # 400 tiles of 128x160 on 148 CTAs: chunk rotation + prefetch across tiles
+    (25600, 320, 384, torch.bfloat16),
+    (19000, 328, 320, torch.float32),      # ragged M (partial row block), N % 32 != 0 (half-valid chunk)
+    (33000, 640, 640, torch.float32),
+    (70000, 96, 64, torch.bfloat16),       # one k-block, 3 chunks over 2 warps
+])
+def test_gemm_pipelined_residual_epilogue_many_tiles(M, N, K, out_dtype):
+    """Specialised epilogue (residual prefetched one chunk ahead, also across tile boundaries; in-place
+    ``out is residual`` as the transformer blocks use it)."""
+    ops = _ops()
+    a = _rand((M, K), 21).bfloat16().cuda()
+    w = _rand((N, K), 22, K ** -0.5).cuda()
+    bias = _rand((N,), 23).cuda()
+    res = _rand((M, N), 24).cuda()
+    wp = ops.pack_linear(w)
+    ref = a.double() @ wp[:, :K].double().t() + bias.double() + res.double()
+    if out_dtype == torch.float32:
+        out = res.clone()
+        ops.gemm([a], wp, N, out=out, bias=bias, residual=out)      # in place
+        tol = 1e-5
+    else:
+        out = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+        ops.gemm([a], wp, N, out=out, bias=bias, residual=res)
+        tol = 3e-3
+    torch.cuda.synchronize()
+    assert rel_l2(out, ref) < tol, err_report(out, ref, f"res epilogue {M}x{N}x{K}")
+    # every row block individually (a wrong tile/chunk mapping hides in a global norm)
+    blk = (out.double() - ref).reshape(-1)[: (M // 128) * 128 * N].reshape(M // 128, -1).norm(dim=1) / \
+        ref.reshape(-1)[: (M // 128) * 128 * N].reshape(M // 128, -1).norm(dim=1)
+    assert float(blk.max()) < 10 * tol
+
+
+def test_gemm_geglu_many_tiles_matches_exact_erf_gelu():
+    ops = _ops()
+    M, C = 20000, 320
+    a = _rand((M, C), 30).bfloat16().cuda()
+    w = _rand((8 * C, C), 31, 2.0 * C ** -0.5).cuda()          # gates spread over ~[-6, 6]
+    b = _rand((8 * C,), 32, 0.1).cuda()
+    wp, bp = ops.pack_geglu(w, b)
+    out = torch.empty(M, 4 * C, dtype=torch.bfloat16, device="cuda")
+    ops.gemm([a], wp, 8 * C, out=out, bias=bp, geglu=True)
+    torch.cuda.synchronize()
+    y = a.double() @ w.bfloat16().double().t() + b.double()
+    ref = y[:, :4 * C] * F.gelu(y[:, 4 * C:])
+    assert rel_l2(out, ref) < 3e-3, err_report(out, ref, "geglu many tiles")
+    # the erf-GELU approximation error (<= 2.7e-5 abs) must stay far below the bf16 output rounding
+    err = (out.double() - ref).abs()
+    assert float((err - 2.0 ** -8 * ref.abs()).max()) < 2e-4

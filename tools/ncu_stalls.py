@@ -7,7 +7,12 @@ n_top = int(sys.argv[1]) if len(sys.argv) > 1 else 25
 rows = list(csv.reader(sys.stdin))
 hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hdr_i]
-body = [r for r in rows[hdr_i + 1:] if len(r) == len(hdr)]
+body = []
+for r in rows[hdr_i + 1:]:          # first table only (a report page may hold several kernels)
+    if not r or r[0] in ("Address", "Kernel Name"):
+        break
+    if len(r) == len(hdr):
+        body.append(r)
 ci = {h: i for i, h in enumerate(hdr)}
 samp = ci["# Samples"]
 stall_cols = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
