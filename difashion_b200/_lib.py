@@ -79,31 +79,34 @@ _PROTOTYPES = {
     "dfb_sizeof_gemm_params": (C.c_size_t, []),
     "dfb_sizeof_attn_params": (C.c_size_t, []),
     "dfb_gemm": (C.c_int, [C.POINTER(GemmParams), C.c_void_p]),
+    "dfb_gemm_f32": (C.c_int, [C.POINTER(GemmParams), C.c_void_p]),
+    "dfb_geglu_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "dfb_attention": (C.c_int, [C.POINTER(AttnParams), C.c_void_p]),
+    "dfb_attention_f32": (C.c_int, [C.POINTER(AttnParams), C.c_void_p]),
     "dfb_groupnorm_ws_floats": (C.c_size_t, [C.c_int, C.c_int]),
     "dfb_groupnorm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
-                                C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                 C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "dfb_groupnorm_fused": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                       C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
-                                      C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
-    "dfb_layernorm": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int,
+                                      C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "dfb_layernorm": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_int,
                                 C.c_int, C.c_int, C.c_void_p]),
     "dfb_cfg_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_void_p, C.c_float,
                                C.POINTER(C.c_float), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
                                C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "dfb_mutual_gather_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
-                                        C.c_void_p, C.c_void_p]),
+                                        C.c_void_p, C.c_int, C.c_void_p]),
     "dfb_mutual_blend": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int,
-                                   C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_void_p,
+                                   C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_void_p, C.c_int,
                                    C.c_void_p]),
-    "dfb_nchw_to_nhwc_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "dfb_nchw_to_nhwc": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "dfb_nhwc_to_nchw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
-    "dfb_pad_cast_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+    "dfb_pad_cast_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_void_p]),
-    "dfb_upsample2x": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
-    "dfb_space_to_depth": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
-    "dfb_timestep_embedding": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float,
+    "dfb_upsample2x": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "dfb_space_to_depth": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "dfb_timestep_embedding": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                          C.c_void_p]),
 }
 

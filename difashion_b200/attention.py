@@ -37,7 +37,7 @@ def pack_head_cols(w: torch.Tensor, heads: int, dp: int) -> torch.Tensor:
 class AttnPack:
     """Pre-packed bf16 weights of one Attention layer (padded-head layout)."""
 
-    def __init__(self, attn, device):
+    def __init__(self, attn, device, dtype: torch.dtype = torch.bfloat16):
         heads = attn.heads
         inner = attn.to_q.weight.shape[0]
         d = inner // heads
@@ -48,10 +48,10 @@ class AttnPack:
         wq, wk, wv = f(attn.to_q.weight), f(attn.to_k.weight), f(attn.to_v.weight)
         self.is_cross = wk.shape[1] != wq.shape[1] or getattr(attn, "is_cross_attention", False)
         hp = lambda w: pack_head_rows(w, heads, self.dp)
-        self.w_q = ops.pack_linear(hp(wq))
-        self.w_kv = ops.pack_linear(torch.cat([hp(wk), hp(wv)], 0))
-        self.w_qkv = ops.pack_linear(torch.cat([hp(wq), hp(wk), hp(wv)], 0)) if wk.shape[1] == wq.shape[1] else None
-        self.w_o = ops.pack_linear(pack_head_cols(f(attn.to_out[0].weight), heads, self.dp))
+        self.w_q = ops.pack_linear(hp(wq), dtype)
+        self.w_kv = ops.pack_linear(torch.cat([hp(wk), hp(wv)], 0), dtype)
+        self.w_qkv = ops.pack_linear(torch.cat([hp(wq), hp(wk), hp(wv)], 0), dtype) if wk.shape[1] == wq.shape[1] else None
+        self.w_o = ops.pack_linear(pack_head_cols(f(attn.to_out[0].weight), heads, self.dp), dtype)
         b = attn.to_out[0].bias
         self.b_o = f(b).contiguous() if b is not None else None
         self.c_out = attn.to_out[0].weight.shape[0]

@@ -100,10 +100,11 @@ __global__ void __launch_bounds__(256) cfg_step_kernel(const CfgStepParams p) {
 // sibling row (-idx-1) of prev_latents, sentinel INT_MIN -> skip.  Output bf16 [N, D] (A operand
 // of the MutualEncoder's first Linear).
 // ---------------------------------------------------------------------------------------------
+template <typename TOut>
 __global__ void __launch_bounds__(256) mutual_gather_sum_kernel(const float* __restrict__ all_latents,
                                                                 const float* __restrict__ prev_latents,
                                                                 const int* __restrict__ idx, int n_items,
-                                                                int n_src, int d, __nv_bfloat16* __restrict__ out) {
+                                                                int n_src, int d, TOut* __restrict__ out) {
   const int dq = d >> 2;
   const long long total = (long long)n_items * dq;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(256) mutual_gather_sum_kernel(const float* __r
       const float4 v = ldg4(src + q);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
-    *reinterpret_cast<uint2*>(out + (size_t)n * d + q) = make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
+    store4(out + (size_t)n * d + q, acc.x, acc.y, acc.z, acc.w);
   }
 }
 
@@ -139,9 +140,10 @@ struct BlendParams {
   int use_m[4];
   int use_h[4];
   int n_items, hw;
-  __nv_bfloat16* out;
+  void* out;
 };
 
+template <typename TOut>
 __global__ void __launch_bounds__(256) mutual_blend_kernel(const BlendParams p) {
   const long long total = (long long)p.n_items * p.hw;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -165,8 +167,9 @@ __global__ void __launch_bounds__(256) mutual_blend_kernel(const BlendParams p) 
         v[4 + c] = p.use_h[b] ? h[c] : z[c];
       }
       const size_t o = (((size_t)b * p.n_items + n) * p.hw + px) * 8;
-      *reinterpret_cast<uint4*>(p.out + o) =
-          make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+      TOut* op = reinterpret_cast<TOut*>(p.out) + o;
+      store4(op, v[0], v[1], v[2], v[3]);
+      store4(op + 4, v[4], v[5], v[6], v[7]);
     }
   }
 }
@@ -174,9 +177,9 @@ __global__ void __launch_bounds__(256) mutual_blend_kernel(const BlendParams p) 
 // ---------------------------------------------------------------------------------------------
 // layout conversions at the diffusers-API boundary
 // ---------------------------------------------------------------------------------------------
-template <typename TIn>
-__global__ void __launch_bounds__(256) nchw_to_nhwc_bf16_kernel(const TIn* __restrict__ in, __nv_bfloat16* __restrict__ out,
-                                                                int B, int C, int HW) {
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const TIn* __restrict__ in, TOut* __restrict__ out,
+                                                           int B, int C, int HW) {
   // small C (8): one thread per pixel reads C strided-but-coalesced-across-threads values
   const long long total = (long long)B * HW;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -184,7 +187,7 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_bf16_kernel(const TIn* __res
     const int b = (int)(i / HW);
     const int px = (int)(i - (long long)b * HW);
     for (int c = 0; c < C; ++c)
-      out[((size_t)b * HW + px) * C + c] = __float2bfloat16((float)in[((size_t)b * C + c) * HW + px]);
+      store1(out + ((size_t)b * HW + px) * C + c, (float)in[((size_t)b * C + c) * HW + px]);
   }
 }
 
@@ -202,8 +205,8 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const float* __restri
 
 // fp32/bf16 [rows, cols] -> bf16 [rows_out >= rows ... ] with per-batch row padding:
 // in [B, S, D] -> out [B, S_pad, D] (rows >= S zero).  Used for encoder_hidden_states (S=77 -> 80).
-template <typename TIn>
-__global__ void __launch_bounds__(256) pad_cast_rows_kernel(const TIn* __restrict__ in, __nv_bfloat16* __restrict__ out,
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256) pad_cast_rows_kernel(const TIn* __restrict__ in, TOut* __restrict__ out,
                                                             int B, int S, int S_pad, int D) {
   const long long total = (long long)B * S_pad * D;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -212,14 +215,15 @@ __global__ void __launch_bounds__(256) pad_cast_rows_kernel(const TIn* __restric
     const long long r = i / D;
     const int s = (int)(r % S_pad);
     const int b = (int)(r / S_pad);
-    out[i] = s < S ? __float2bfloat16((float)in[((size_t)b * S + s) * D + dcol]) : __float2bfloat16(0.f);
+    store1(out + i, s < S ? (float)in[((size_t)b * S + s) * D + dcol] : 0.f);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // nearest-2x upsample (Upsample2D, App. A.2 item 7): fp32 NHWC [B,H,W,C] -> bf16 NHWC [B,2H,2W,C]
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) upsample2x_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
+template <typename TOut>
+__global__ void __launch_bounds__(256) upsample2x_kernel(const float* __restrict__ in, TOut* __restrict__ out,
                                                          int B, int H, int W, int C) {
   const int cq = C >> 2;
   const long long total = (long long)B * H * W * cq;
@@ -231,12 +235,11 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const float* __restrict
     const int h = (int)(r % H);
     const int b = (int)(r / H);
     const float4 v = ldg4(in + (((size_t)b * H + h) * W + w) * C + c);
-    const uint2 pk = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
 #pragma unroll
     for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
       for (int dx = 0; dx < 2; ++dx)
-        *reinterpret_cast<uint2*>(out + (((size_t)b * 2 * H + 2 * h + dy) * 2 * W + 2 * w + dx) * C + c) = pk;
+        store4(out + (((size_t)b * 2 * H + 2 * h + dy) * 2 * W + 2 * w + dx) * C + c, v.x, v.y, v.z, v.w);
   }
 }
 
@@ -245,7 +248,8 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const float* __restrict
 // plane p = (h&1)*2 + (w&1) stored at channel offset p*C.  The stride-2 3x3 conv then becomes a
 // stride-1 9-tap gather over these planes (tap table built on the host).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) space_to_depth_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
+template <typename TOut>
+__global__ void __launch_bounds__(256) space_to_depth_kernel(const float* __restrict__ in, TOut* __restrict__ out,
                                                              int B, int H, int W, int C) {
   const int cq = C >> 2;
   const long long total = (long long)B * H * W * cq;
@@ -259,15 +263,15 @@ __global__ void __launch_bounds__(256) space_to_depth_kernel(const float* __rest
     const int b = (int)(r / H);
     const float4 v = ldg4(in + (((size_t)b * H + h) * W + w) * C + c);
     const int plane = (h & 1) * 2 + (w & 1);
-    *reinterpret_cast<uint2*>(out + ((((size_t)b * H2 + (h >> 1)) * W2 + (w >> 1)) * 4 + plane) * C + c) =
-        make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    store4(out + ((((size_t)b * H2 + (h >> 1)) * W2 + (w >> 1)) * 4 + plane) * C + c, v.x, v.y, v.z, v.w);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // sinusoidal timestep projection (Timesteps, App. A.2 item 2): fp32 math, [cos | sin], bf16 out
 // ---------------------------------------------------------------------------------------------
-__global__ void timestep_embedding_kernel(const float* __restrict__ t, __nv_bfloat16* __restrict__ out, int B, int dim,
+template <typename TOut>
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, TOut* __restrict__ out, int B, int dim,
                                           int flip_sin_to_cos, float freq_shift) {
   const int half = dim >> 1;
   const int total = B * half;
@@ -276,9 +280,9 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, __nv_bflo
     const float freq = expf(-logf(10000.f) * (float)k / ((float)half - freq_shift));
     const float arg = t[b] * freq;
     const float s = sinf(arg), c = cosf(arg);
-    __nv_bfloat16* o = out + (size_t)b * dim;
-    if (flip_sin_to_cos) { o[k] = __float2bfloat16(c); o[half + k] = __float2bfloat16(s); }
-    else { o[k] = __float2bfloat16(s); o[half + k] = __float2bfloat16(c); }
+    TOut* o = out + (size_t)b * dim;
+    if (flip_sin_to_cos) { store1(o + k, c); store1(o + half + k, s); }
+    else { store1(o + k, s); store1(o + half + k, c); }
   }
 }
 
@@ -311,38 +315,48 @@ int dfb_cfg_step(const float* eps, int eps_nchw, int nb, const float* w, const f
 }
 
 int dfb_mutual_gather_sum(const float* all_latents, const float* prev_latents, const int32_t* idx, int n_items,
-                          int n_src, int d, void* out_bf16, void* stream) {
-  DFB_REQUIRE(prev_latents && idx && out_bf16, "dfb_mutual_gather_sum: null buffer");
+                          int n_src, int d, void* out, int out_dtype, void* stream) {
+  DFB_REQUIRE(prev_latents && idx && out, "dfb_mutual_gather_sum: null buffer");
   DFB_REQUIRE(n_items > 0 && n_src >= 0 && d > 0 && d % 4 == 0, "dfb_mutual_gather_sum: bad sizes");
   const long long work = (long long)n_items * (d / 4);
-  mutual_gather_sum_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>(
-      all_latents, prev_latents, idx, n_items, n_src, d, (__nv_bfloat16*)out_bf16);
+  const int g = grid_for(work, 256);
+  if (out_dtype == DFB_DTYPE_F32)
+    mutual_gather_sum_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>(all_latents, prev_latents, idx, n_items, n_src, d, (float*)out);
+  else
+    mutual_gather_sum_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream>>>(all_latents, prev_latents, idx, n_items, n_src, d, (__nv_bfloat16*)out);
   DFB_CHECK_CUDA(cudaGetLastError());
   return DFB_OK;
 }
 
 int dfb_mutual_blend(const float* x, const float* m, const float* hist, const float* null_latent, float eta, int nb,
-                     const int32_t* use_m, const int32_t* use_h, int n_items, int hw, void* out_bf16, void* stream) {
-  DFB_REQUIRE(x && null_latent && out_bf16 && use_m && use_h, "dfb_mutual_blend: null buffer");
+                     const int32_t* use_m, const int32_t* use_h, int n_items, int hw, void* out, int out_dtype, void* stream) {
+  DFB_REQUIRE(x && null_latent && out && use_m && use_h, "dfb_mutual_blend: null buffer");
   DFB_REQUIRE(nb >= 1 && nb <= 4 && n_items > 0 && hw > 0, "dfb_mutual_blend: bad sizes");
-  DFB_REQUIRE(((uintptr_t)out_bf16) % 16 == 0, "dfb_mutual_blend: output must be 16B aligned");
+  DFB_REQUIRE(((uintptr_t)out) % 16 == 0, "dfb_mutual_blend: output must be 16B aligned");
   BlendParams p;
   memset(&p, 0, sizeof(p));
   p.x = x; p.m = m; p.hist = hist; p.null_latent = null_latent; p.eta = eta; p.nb = nb;
   for (int b = 0; b < nb; ++b) { p.use_m[b] = use_m[b]; p.use_h[b] = use_h[b]; }
-  p.n_items = n_items; p.hw = hw; p.out = (__nv_bfloat16*)out_bf16;
-  mutual_blend_kernel<<<grid_for((long long)n_items * hw, 256), 256, 0, (cudaStream_t)stream>>>(p);
+  p.n_items = n_items; p.hw = hw; p.out = out;
+  const int g = grid_for((long long)n_items * hw, 256);
+  if (out_dtype == DFB_DTYPE_F32) mutual_blend_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>(p);
+  else mutual_blend_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream>>>(p);
   DFB_CHECK_CUDA(cudaGetLastError());
   return DFB_OK;
 }
 
-int dfb_nchw_to_nhwc_bf16(const void* in, int in_dtype, void* out_bf16, int B, int Cch, int HW, void* stream) {
-  DFB_REQUIRE(in && out_bf16 && B > 0 && Cch > 0 && HW > 0, "dfb_nchw_to_nhwc_bf16: bad args");
+int dfb_nchw_to_nhwc(const void* in, int in_dtype, void* out, int out_dtype, int B, int Cch, int HW, void* stream) {
+  DFB_REQUIRE(in && out && B > 0 && Cch > 0 && HW > 0, "dfb_nchw_to_nhwc: bad args");
   const int g = grid_for((long long)B * HW, 256);
-  if (in_dtype == DFB_DTYPE_F32)
-    nchw_to_nhwc_bf16_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)in, (__nv_bfloat16*)out_bf16, B, Cch, HW);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (in_dtype == DFB_DTYPE_F32 && out_dtype == DFB_DTYPE_F32)
+    nchw_to_nhwc_kernel<float, float><<<g, 256, 0, st>>>((const float*)in, (float*)out, B, Cch, HW);
+  else if (in_dtype == DFB_DTYPE_F32)
+    nchw_to_nhwc_kernel<float, __nv_bfloat16><<<g, 256, 0, st>>>((const float*)in, (__nv_bfloat16*)out, B, Cch, HW);
+  else if (out_dtype == DFB_DTYPE_F32)
+    nchw_to_nhwc_kernel<__nv_bfloat16, float><<<g, 256, 0, st>>>((const __nv_bfloat16*)in, (float*)out, B, Cch, HW);
   else
-    nchw_to_nhwc_bf16_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out_bf16, B, Cch, HW);
+    nchw_to_nhwc_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, B, Cch, HW);
   DFB_CHECK_CUDA(cudaGetLastError());
   return DFB_OK;
 }
@@ -358,37 +372,48 @@ int dfb_nhwc_to_nchw(const float* in, void* out, int out_dtype, int B, int Cch, 
   return DFB_OK;
 }
 
-int dfb_pad_cast_rows(const void* in, int in_dtype, void* out_bf16, int B, int S, int S_pad, int D, void* stream) {
-  DFB_REQUIRE(in && out_bf16 && B > 0 && S > 0 && S_pad >= S && D > 0, "dfb_pad_cast_rows: bad args");
+int dfb_pad_cast_rows(const void* in, int in_dtype, void* out, int out_dtype, int B, int S, int S_pad, int D, void* stream) {
+  DFB_REQUIRE(in && out && B > 0 && S > 0 && S_pad >= S && D > 0, "dfb_pad_cast_rows: bad args");
   const int g = grid_for((long long)B * S_pad * D, 256);
-  if (in_dtype == DFB_DTYPE_F32)
-    pad_cast_rows_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)in, (__nv_bfloat16*)out_bf16, B, S, S_pad, D);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (in_dtype == DFB_DTYPE_F32 && out_dtype == DFB_DTYPE_F32)
+    pad_cast_rows_kernel<float, float><<<g, 256, 0, st>>>((const float*)in, (float*)out, B, S, S_pad, D);
+  else if (in_dtype == DFB_DTYPE_F32)
+    pad_cast_rows_kernel<float, __nv_bfloat16><<<g, 256, 0, st>>>((const float*)in, (__nv_bfloat16*)out, B, S, S_pad, D);
+  else if (out_dtype == DFB_DTYPE_F32)
+    pad_cast_rows_kernel<__nv_bfloat16, float><<<g, 256, 0, st>>>((const __nv_bfloat16*)in, (float*)out, B, S, S_pad, D);
   else
-    pad_cast_rows_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out_bf16, B, S, S_pad, D);
+    pad_cast_rows_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, B, S, S_pad, D);
   DFB_CHECK_CUDA(cudaGetLastError());
   return DFB_OK;
 }
 
-int dfb_upsample2x(const float* in, void* out_bf16, int B, int H, int W, int Cch, void* stream) {
-  DFB_REQUIRE(in && out_bf16 && B > 0 && H > 0 && W > 0 && Cch > 0 && Cch % 4 == 0, "dfb_upsample2x: bad args");
-  upsample2x_kernel<<<grid_for((long long)B * H * W * (Cch / 4), 256), 256, 0, (cudaStream_t)stream>>>(
-      in, (__nv_bfloat16*)out_bf16, B, H, W, Cch);
+int dfb_upsample2x(const float* in, void* out, int out_dtype, int B, int H, int W, int Cch, void* stream) {
+  DFB_REQUIRE(in && out && B > 0 && H > 0 && W > 0 && Cch > 0 && Cch % 4 == 0, "dfb_upsample2x: bad args");
+  const int g = grid_for((long long)B * H * W * (Cch / 4), 256);
+  if (out_dtype == DFB_DTYPE_F32) upsample2x_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>(in, (float*)out, B, H, W, Cch);
+  else upsample2x_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream>>>(in, (__nv_bfloat16*)out, B, H, W, Cch);
   DFB_CHECK_CUDA(cudaGetLastError());
   return DFB_OK;
 }
 
-int dfb_space_to_depth(const float* in, void* out_bf16, int B, int H, int W, int Cch, void* stream) {
-  DFB_REQUIRE(in && out_bf16 && B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && Cch % 4 == 0, "dfb_space_to_depth: bad args");
-  space_to_depth_kernel<<<grid_for((long long)B * H * W * (Cch / 4), 256), 256, 0, (cudaStream_t)stream>>>(
-      in, (__nv_bfloat16*)out_bf16, B, H, W, Cch);
+int dfb_space_to_depth(const float* in, void* out, int out_dtype, int B, int H, int W, int Cch, void* stream) {
+  DFB_REQUIRE(in && out && B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && Cch % 4 == 0, "dfb_space_to_depth: bad args");
+  const int g = grid_for((long long)B * H * W * (Cch / 4), 256);
+  if (out_dtype == DFB_DTYPE_F32) space_to_depth_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>(in, (float*)out, B, H, W, Cch);
+  else space_to_depth_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream>>>(in, (__nv_bfloat16*)out, B, H, W, Cch);
   DFB_CHECK_CUDA(cudaGetLastError());
   return DFB_OK;
 }
 
-int dfb_timestep_embedding(const float* t, void* out_bf16, int B, int dim, int flip_sin_to_cos, float freq_shift, void* stream) {
-  DFB_REQUIRE(t && out_bf16 && B > 0 && dim > 0 && dim % 2 == 0, "dfb_timestep_embedding: bad args");
+int dfb_timestep_embedding(const float* t, void* out, int out_dtype, int B, int dim, int flip_sin_to_cos, float freq_shift,
+                           void* stream) {
+  DFB_REQUIRE(t && out && B > 0 && dim > 0 && dim % 2 == 0, "dfb_timestep_embedding: bad args");
   const int total = B * dim / 2;
-  timestep_embedding_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(t, (__nv_bfloat16*)out_bf16, B, dim, flip_sin_to_cos, freq_shift);
+  if (out_dtype == DFB_DTYPE_F32)
+    timestep_embedding_kernel<float><<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(t, (float*)out, B, dim, flip_sin_to_cos, freq_shift);
+  else
+    timestep_embedding_kernel<__nv_bfloat16><<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(t, (__nv_bfloat16*)out, B, dim, flip_sin_to_cos, freq_shift);
   DFB_CHECK_CUDA(cudaGetLastError());
   return DFB_OK;
 }

@@ -147,11 +147,12 @@ __global__ void groupnorm_finalize_partials_kernel(const float* __restrict__ p0,
 // bf16 copy of x (A operand of the 1x1 shortcut folded into conv2).  Same thread mapping as the
 // statistics kernel: a thread owns fixed channel vectors, so gamma/beta/mean/rstd are folded into a
 // per-thread (scale, shift) once and the pixel loop is load -> FMA -> SiLU -> store (no index math).
+template <typename TOut>
 __global__ void __launch_bounds__(GN_THREADS)
 groupnorm_apply_kernel(const float* __restrict__ src0, int c0, int ld0, const float* __restrict__ src1, int c1, int ld1,
                        int hw, int groups, int pix_per_block, const float* __restrict__ stats,
                        const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
-                       __nv_bfloat16* __restrict__ out, int ld_out, __nv_bfloat16* __restrict__ raw_out, int ld_raw) {
+                       TOut* __restrict__ out, int ld_out, TOut* __restrict__ raw_out, int ld_raw) {
   const int b = blockIdx.y;
   const int C = c0 + c1;
   const int cg = C / groups;
@@ -177,13 +178,16 @@ groupnorm_apply_kernel(const float* __restrict__ src0, int c0, int ld0, const fl
     const float mb = st[gb * 2], rb = st[gb * 2 + 1];
     const float s0 = ra * g.x, s1 = ra * g.y, s2 = rb * g.z, s3 = rb * g.w;
     const float h0 = bt.x - ma * s0, h1 = bt.y - ma * s1, h2 = bt.z - mb * s2, h3 = bt.w - mb * s3;
-    __nv_bfloat16* o = out + (size_t)b * hw * ld_out + c;
-    __nv_bfloat16* ro = raw_out ? raw_out + (size_t)b * hw * ld_raw + c : nullptr;
+    TOut* o = out + (size_t)b * hw * ld_out + c;
+    TOut* ro = raw_out ? raw_out + (size_t)b * hw * ld_raw + c : nullptr;
     auto emit = [&](int px, const float4& x) {
       float y0 = fmaf(x.x, s0, h0), y1 = fmaf(x.y, s1, h1), y2 = fmaf(x.z, s2, h2), y3 = fmaf(x.w, s3, h3);
-      if (silu) { y0 = silu_fast_f(y0); y1 = silu_fast_f(y1); y2 = silu_fast_f(y2); y3 = silu_fast_f(y3); }
-      *reinterpret_cast<uint2*>(o + (size_t)px * ld_out) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
-      if (ro) *reinterpret_cast<uint2*>(ro + (size_t)px * ld_raw) = make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
+      if (silu) {
+        if constexpr (sizeof(TOut) == 4) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }   // fp32 path: IEEE division
+        else { y0 = silu_fast_f(y0); y1 = silu_fast_f(y1); y2 = silu_fast_f(y2); y3 = silu_fast_f(y3); }
+      }
+      store4(o + (size_t)px * ld_out, y0, y1, y2, y3);
+      if (ro) store4(ro + (size_t)px * ld_raw, x.x, x.y, x.z, x.w);
     };
     // GN_BATCH independent 16-byte loads in flight per thread before any of them is consumed (the compiler does
     // not hoist loads over the stores of an unrolled loop: ncu showed one exposed DRAM round trip per pixel)
@@ -203,10 +207,10 @@ groupnorm_apply_kernel(const float* __restrict__ src0, int c0, int ld0, const fl
 // LayerNorm over the last dim: one warp per row, row held in registers (C <= 2048), two-pass
 // (mean, then centred variance) in fp32; bf16 output.
 // ---------------------------------------------------------------------------------------------
-template <int LN_MAX_VEC>   // float4 per lane -> C <= 128 * LN_MAX_VEC
+template <int LN_MAX_VEC, typename TOut>   // float4 per lane -> C <= 128 * LN_MAX_VEC
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, int ld_x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                 float eps, __nv_bfloat16* __restrict__ out, int ld_out, int rows, int C) {
+                 float eps, TOut* __restrict__ out, int ld_out, int rows, int C) {
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nvec = C >> 2;
@@ -237,7 +241,7 @@ layernorm_kernel(const float* __restrict__ x, int ld_x, const float* __restrict_
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
     const float rstd = rsqrtf(q / (float)C + eps);
-    __nv_bfloat16* orow = out + (size_t)row * ld_out;
+    TOut* orow = out + (size_t)row * ld_out;
 #pragma unroll
     for (int k = 0; k < LN_MAX_VEC; ++k) {
       const int j = lane + k * 32;
@@ -248,7 +252,7 @@ layernorm_kernel(const float* __restrict__ x, int ld_x, const float* __restrict_
         const float y1 = (v[k].y - mean) * rstd * g.y + bt.y;
         const float y2 = (v[k].z - mean) * rstd * g.z + bt.z;
         const float y3 = (v[k].w - mean) * rstd * g.w + bt.w;
-        *reinterpret_cast<uint2*>(orow + (j << 2)) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+        store4(orow + (j << 2), y0, y1, y2, y3);
       }
     }
   }
@@ -259,17 +263,21 @@ layernorm_kernel(const float* __restrict__ x, int ld_x, const float* __restrict_
 using namespace dfb;
 
 static int launch_gn_apply(const float* src0, int c0, int ld0, const float* src1, int c1, int ld1, int B, int hw, int groups,
-                           const float* stats, const float* gamma, const float* beta, int silu, void* out_bf16, int ld_out,
-                           void* raw_out_bf16, int ld_raw, cudaStream_t stream) {
+                           const float* stats, const float* gamma, const float* beta, int silu, void* out, int out_dtype,
+                           int ld_out, void* raw_out, int ld_raw, cudaStream_t stream) {
   // ~16 CTAs per SM over (B x pixel chunks)
   int ach = (num_sms() * 16 + B - 1) / B;
   if (ach > hw) ach = hw;
   if (ach < 1) ach = 1;
   const int appb = (hw + ach - 1) / ach;
   ach = (hw + appb - 1) / appb;
-  groupnorm_apply_kernel<<<dim3(ach, B), GN_THREADS, 0, stream>>>(src0, c0, ld0, src1, c1, ld1, hw, groups, appb, stats, gamma,
-                                                                  beta, silu, (__nv_bfloat16*)out_bf16, ld_out,
-                                                                  (__nv_bfloat16*)raw_out_bf16, ld_raw);
+  if (out_dtype == DFB_DTYPE_F32)
+    groupnorm_apply_kernel<float><<<dim3(ach, B), GN_THREADS, 0, stream>>>(src0, c0, ld0, src1, c1, ld1, hw, groups, appb, stats,
+                                                                           gamma, beta, silu, (float*)out, ld_out, (float*)raw_out, ld_raw);
+  else
+    groupnorm_apply_kernel<__nv_bfloat16><<<dim3(ach, B), GN_THREADS, 0, stream>>>(src0, c0, ld0, src1, c1, ld1, hw, groups, appb, stats,
+                                                                                   gamma, beta, silu, (__nv_bfloat16*)out, ld_out,
+                                                                                   (__nv_bfloat16*)raw_out, ld_raw);
   DFB_CHECK_CUDA(cudaGetLastError());
   return DFB_OK;
 }
@@ -281,10 +289,10 @@ size_t dfb_groupnorm_ws_floats(int B, int groups) {
 }
 
 int dfb_groupnorm(const float* src0, int c0, int ld0, const float* src1, int c1, int ld1, int B, int hw, int groups,
-                  float eps, const float* gamma, const float* beta, int silu, float* stats_ws, void* out_bf16, int ld_out,
-                  void* raw_out_bf16, int ld_raw, void* stream_) {
+                  float eps, const float* gamma, const float* beta, int silu, float* stats_ws, void* out, int out_dtype,
+                  int ld_out, void* raw_out, int ld_raw, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  DFB_REQUIRE(src0 && gamma && beta && stats_ws && out_bf16, "dfb_groupnorm: null buffer");
+  DFB_REQUIRE(src0 && gamma && beta && stats_ws && out, "dfb_groupnorm: null buffer");
   DFB_REQUIRE(c1 == 0 || src1 != nullptr, "dfb_groupnorm: second source missing");
   const int Cch = c0 + c1;
   DFB_REQUIRE(B > 0 && hw > 0 && groups > 0 && groups <= 64 && Cch % groups == 0, "dfb_groupnorm: bad sizes");
@@ -310,16 +318,16 @@ int dfb_groupnorm(const float* src0, int c0, int ld0, const float* src1, int c1,
     groupnorm_finalize_kernel<<<blocks, threads, 0, stream>>>(partial, chunks, groups, B, inv_n, eps, stats);
     DFB_CHECK_CUDA(cudaGetLastError());
   }
-  return launch_gn_apply(src0, c0, ld0, src1, c1, ld1, B, hw, groups, stats, gamma, beta, silu, out_bf16, ld_out, raw_out_bf16,
+  return launch_gn_apply(src0, c0, ld0, src1, c1, ld1, B, hw, groups, stats, gamma, beta, silu, out, out_dtype, ld_out, raw_out,
                          ld_raw, stream);
 }
 
 int dfb_groupnorm_fused(const float* src0, int c0, int ld0, const float* partial0, const float* src1, int c1, int ld1,
                         const float* partial1, int B, int hw, int groups, float eps, const float* gamma,
-                        const float* beta, int silu, float* stats_ws, void* out_bf16, int ld_out, void* raw_out_bf16,
+                        const float* beta, int silu, float* stats_ws, void* out, int out_dtype, int ld_out, void* raw_out,
                         int ld_raw, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  DFB_REQUIRE(src0 && partial0 && gamma && beta && stats_ws && out_bf16, "dfb_groupnorm_fused: null buffer");
+  DFB_REQUIRE(src0 && partial0 && gamma && beta && stats_ws && out, "dfb_groupnorm_fused: null buffer");
   DFB_REQUIRE(c1 == 0 || (src1 != nullptr && partial1 != nullptr), "dfb_groupnorm_fused: second source missing");
   const int Cch = c0 + c1;
   DFB_REQUIRE(B > 0 && hw > 0 && hw % 32 == 0 && groups > 0 && groups <= 64 && Cch % groups == 0, "dfb_groupnorm_fused: bad sizes");
@@ -333,24 +341,30 @@ int dfb_groupnorm_fused(const float* src0, int c0, int ld0, const float* partial
     groupnorm_finalize_partials_kernel<<<blocks, threads, 0, stream>>>(partial0, c0, partial1, c1, hw, groups, B, eps, stats_ws);
     DFB_CHECK_CUDA(cudaGetLastError());
   }
-  return launch_gn_apply(src0, c0, ld0, src1, c1, ld1, B, hw, groups, stats_ws, gamma, beta, silu, out_bf16, ld_out, raw_out_bf16,
+  return launch_gn_apply(src0, c0, ld0, src1, c1, ld1, B, hw, groups, stats_ws, gamma, beta, silu, out, out_dtype, ld_out, raw_out,
                          ld_raw, stream);
 }
 
-int dfb_layernorm(const float* x, int ld_x, const float* gamma, const float* beta, float eps, void* out_bf16, int ld_out,
-                  int rows, int Cch, void* stream) {
-  DFB_REQUIRE(x && gamma && beta && out_bf16, "dfb_layernorm: null buffer");
+int dfb_layernorm(const float* x, int ld_x, const float* gamma, const float* beta, float eps, void* out, int out_dtype,
+                  int ld_out, int rows, int Cch, void* stream) {
+  DFB_REQUIRE(x && gamma && beta && out, "dfb_layernorm: null buffer");
   DFB_REQUIRE(rows > 0 && Cch > 0 && Cch % 4 == 0 && Cch <= 2048, "dfb_layernorm: C must be a multiple of 4, <= 2048");
   DFB_REQUIRE(ld_x % 4 == 0 && ld_out % 4 == 0, "dfb_layernorm: pitches must be multiples of 4");
   long long blocks = ((long long)rows + 7) / 8;
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
   cudaStream_t st = (cudaStream_t)stream;
-  __nv_bfloat16* o = (__nv_bfloat16*)out_bf16;
-  if (Cch <= 384) layernorm_kernel<3><<<(int)blocks, 256, 0, st>>>(x, ld_x, gamma, beta, eps, o, ld_out, rows, Cch);
-  else if (Cch <= 640) layernorm_kernel<5><<<(int)blocks, 256, 0, st>>>(x, ld_x, gamma, beta, eps, o, ld_out, rows, Cch);
-  else if (Cch <= 1280) layernorm_kernel<10><<<(int)blocks, 256, 0, st>>>(x, ld_x, gamma, beta, eps, o, ld_out, rows, Cch);
-  else layernorm_kernel<16><<<(int)blocks, 256, 0, st>>>(x, ld_x, gamma, beta, eps, o, ld_out, rows, Cch);
+#define DFB_LN_LAUNCH(T)                                                                                                   \
+  do {                                                                                                                      \
+    T* o = (T*)out;                                                                                                         \
+    if (Cch <= 384) layernorm_kernel<3, T><<<(int)blocks, 256, 0, st>>>(x, ld_x, gamma, beta, eps, o, ld_out, rows, Cch);     \
+    else if (Cch <= 640) layernorm_kernel<5, T><<<(int)blocks, 256, 0, st>>>(x, ld_x, gamma, beta, eps, o, ld_out, rows, Cch); \
+    else if (Cch <= 1280) layernorm_kernel<10, T><<<(int)blocks, 256, 0, st>>>(x, ld_x, gamma, beta, eps, o, ld_out, rows, Cch); \
+    else layernorm_kernel<16, T><<<(int)blocks, 256, 0, st>>>(x, ld_x, gamma, beta, eps, o, ld_out, rows, Cch);               \
+  } while (0)
+  if (out_dtype == DFB_DTYPE_F32) DFB_LN_LAUNCH(float);
+  else DFB_LN_LAUNCH(__nv_bfloat16);
+#undef DFB_LN_LAUNCH
   DFB_CHECK_CUDA(cudaGetLastError());
   return DFB_OK;
 }

@@ -38,21 +38,21 @@ class MutualEncoder(nn.Module):
     def d(self) -> int:
         return self.latent_channels * self.latent_size * self.latent_size
 
-    def pack(self, device):
-        key = (str(device), tuple((p.data_ptr(), p._version) for p in self.mlp.parameters()))
+    def pack(self, device, dtype: torch.dtype = torch.bfloat16):
+        key = (str(device), str(dtype), tuple((p.data_ptr(), p._version) for p in self.mlp.parameters()))
         if self._pk is None or self._pk["key"] != key:
             l1, l2 = self.mlp[0], self.mlp[3]
             f = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()
-            self._pk = dict(key=key, w1=ops.pack_linear(l1.weight.to(device)), b1=f(l1.bias),
-                            w2=ops.pack_linear(l2.weight.to(device)), b2=f(l2.bias))
+            self._pk = dict(key=key, w1=ops.pack_linear(l1.weight.to(device), dtype), b1=f(l1.bias),
+                            w2=ops.pack_linear(l2.weight.to(device), dtype), b2=f(l2.bias))
         return self._pk
 
     def encode_bf16(self, x_bf16: torch.Tensor, out: torch.Tensor, hid: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """x: bf16 [N, d] (the neighbour sum) -> out fp32 [N, d] in (-1, 1)."""
-        pk = self.pack(x_bf16.device)
+        """x: bf16 (or fp32: verification path) [N, d] (the neighbour sum) -> out fp32 [N, d] in (-1, 1)."""
+        pk = self.pack(x_bf16.device, x_bf16.dtype)
         n = x_bf16.shape[0]
         if hid is None:
-            hid = torch.empty(n, self.hid_dim, dtype=torch.bfloat16, device=x_bf16.device)
+            hid = torch.empty(n, self.hid_dim, dtype=x_bf16.dtype, device=x_bf16.device)
         ops.gemm([x_bf16], pk["w1"], self.hid_dim, out=hid, bias=pk["b1"], act=ops.ACT_LEAKY_RELU)
         ops.gemm([hid], pk["w2"], self.d, out=out, bias=pk["b2"], act=ops.ACT_TANH)
         return out

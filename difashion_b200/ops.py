@@ -70,26 +70,27 @@ def ceil64(x: int) -> int:
 # ----------------------------------------------------------------------------------------------
 # weight packing (done once, on the host side of the boundary)
 # ----------------------------------------------------------------------------------------------
-def pack_linear(weight: torch.Tensor) -> torch.Tensor:
-    """nn.Linear / 1x1-conv weight ``[N, K(,1,1)]`` -> bf16 ``[N, ceil64(K)]`` (K-major)."""
+def pack_linear(weight: torch.Tensor, dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """nn.Linear / 1x1-conv weight ``[N, K(,1,1)]`` -> ``[N, ceil64(K)]`` (K-major); bf16 for the tensor-core
+    path, fp32 for the fp32 verification path."""
     w = weight.detach().reshape(weight.shape[0], -1).float()
     n, k = w.shape
-    out = torch.zeros(n, ceil64(k), dtype=torch.bfloat16, device=w.device)
-    out[:, :k] = w.to(torch.bfloat16)
+    out = torch.zeros(n, ceil64(k), dtype=dtype, device=w.device)
+    out[:, :k] = w.to(dtype)
     return out.contiguous()
 
 
-def pack_conv3x3(weight: torch.Tensor) -> torch.Tensor:
-    """OIHW 3x3 weight -> bf16 ``[O, 9 * ceil64(I)]`` with k = (kh*3+kw) * ceil64(I) + i."""
+def pack_conv3x3(weight: torch.Tensor, dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """OIHW 3x3 weight -> ``[O, 9 * ceil64(I)]`` with k = (kh*3+kw) * ceil64(I) + i."""
     o, i, kh, kw = weight.shape
     assert kh == 3 and kw == 3
     ip = ceil64(i)
-    out = torch.zeros(o, 9, ip, dtype=torch.bfloat16, device=weight.device)
-    out[:, :, :i] = weight.detach().float().permute(0, 2, 3, 1).reshape(o, 9, i).to(torch.bfloat16)
+    out = torch.zeros(o, 9, ip, dtype=dtype, device=weight.device)
+    out[:, :, :i] = weight.detach().float().permute(0, 2, 3, 1).reshape(o, 9, i).to(dtype)
     return out.reshape(o, 9 * ip).contiguous()
 
 
-def pack_geglu(weight: torch.Tensor, bias: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+def pack_geglu(weight: torch.Tensor, bias: torch.Tensor, dtype: torch.dtype = torch.bfloat16) -> Tuple[torch.Tensor, torch.Tensor]:
     """GEGLU ``proj`` ``[2*I, K]`` (rows [0,I) values, [I,2I) gates) -> rows interleaved in groups of
     16 (16 value rows, then their 16 gate rows) so one 32-column epilogue chunk holds both."""
     two_i, k = weight.shape
@@ -101,7 +102,7 @@ def pack_geglu(weight: torch.Tensor, bias: torch.Tensor) -> Tuple[torch.Tensor, 
     bv, bg = b[:inner].reshape(inner // 16, 16), b[inner:].reshape(inner // 16, 16)
     wi = torch.stack([wv, wg], dim=1).reshape(two_i, k)
     bi = torch.stack([bv, bg], dim=1).reshape(two_i)
-    return pack_linear(wi), bi.contiguous()
+    return pack_linear(wi, dtype), bi.contiguous()
 
 
 # ----------------------------------------------------------------------------------------------
@@ -120,6 +121,15 @@ def gemm(a: Sequence[torch.Tensor], w: torch.Tensor, n: int, *, out: torch.Tenso
     taps: per segment a list of ``(dh, dw, channel_offset)``; default one centre tap.
     a_c:  per segment channel extent read per tap (default: the tensor's last dim).
     """
+    f32 = a[0].dtype == torch.float32          # fp32 verification path (CUDA cores): fp32 operands throughout
+    if f32 and geglu:
+        # projection with bias into a scratch buffer, then pair the packed (value | gate) columns
+        tmp = torch.empty(out.numel() // out.shape[-1], n, dtype=torch.float32, device=out.device)
+        gemm(a, w, n, out=tmp, taps=taps, a_c=a_c, conv_geom=conv_geom, bias=bias)
+        check(_lib.load().dfb_geglu_f32(tmp.data_ptr(), tmp.stride(0), out.data_ptr(), out.stride(-2), tmp.shape[0], n, _stream()),
+              "dfb_geglu_f32")
+        _count(1)
+        return out
     p = GemmParams()
     nseg = len(a)
     assert 1 <= nseg <= 2
@@ -127,8 +137,9 @@ def gemm(a: Sequence[torch.Tensor], w: torch.Tensor, n: int, *, out: torch.Tenso
     m_rows = 1
     for d in out.shape[:-1]:
         m_rows *= d
+    op_dtype = torch.float32 if f32 else torch.bfloat16
     for s, t in enumerate(a):
-        assert t.dtype == torch.bfloat16 and t.is_cuda and t.stride(-1) == 1
+        assert t.dtype == op_dtype and t.is_cuda and t.stride(-1) == 1
         p.a[s] = t.data_ptr()
         p.a_ld[s] = t.stride(-2)
         p.a_c[s] = a_c[s] if a_c is not None else t.shape[-1]
@@ -140,7 +151,7 @@ def gemm(a: Sequence[torch.Tensor], w: torch.Tensor, n: int, *, out: torch.Tenso
         p.conv = 1
         p.B, p.H, p.W = conv_geom
     p.M, p.N = m_rows, n
-    assert w.dtype == torch.bfloat16 and w.is_contiguous()
+    assert w.dtype == op_dtype and w.is_contiguous()
     p.w, p.w_ld = w.data_ptr(), w.shape[1]
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.is_contiguous()
@@ -160,7 +171,10 @@ def gemm(a: Sequence[torch.Tensor], w: torch.Tensor, n: int, *, out: torch.Tenso
         assert gn_partial.dtype == torch.float32 and gn_partial.numel() >= (m_rows // 32) * (n // 2) * 2
         p.gn_partial = gn_partial.data_ptr()
     e0 = _prof_begin()
-    check(_lib.load().dfb_gemm(C.byref(p), _stream()), "dfb_gemm")
+    if f32:
+        check(_lib.load().dfb_gemm_f32(C.byref(p), _stream()), "dfb_gemm_f32")
+    else:
+        check(_lib.load().dfb_gemm(C.byref(p), _stream()), "dfb_gemm")
     if e0 is not None:
         k_exec = sum(int(p.ntaps[s]) * ceil64(int(p.a_c[s])) for s in range(nseg))
         _prof_end(e0, "conv" if conv_geom is not None else "gemm", 2.0 * m_rows * n * k_exec, (m_rows, n, k_exec))
@@ -186,7 +200,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
     from ._lib import AttnParams
     p = AttnParams()
     for t in (q, k, v, out):
-        assert t.dtype == torch.bfloat16 and t.is_cuda and t.dim() == 3 and t.stride(-1) == 1
+        assert t.dtype == q.dtype and t.dtype in (torch.bfloat16, torch.float32) and t.is_cuda and t.dim() == 3 and t.stride(-1) == 1
         assert t.stride(0) == t.shape[1] * t.stride(1), "batch stride must be S * row pitch"
     p.q, p.k, p.v, p.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
     p.q_ld, p.k_ld, p.v_ld, p.out_ld = q.stride(1), k.stride(1), v.stride(1), out.stride(1)
@@ -198,7 +212,10 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
     p.dbg_flags = dbg_flags
     p.dbg_timeline = _ptr(dbg_timeline)
     e0 = _prof_begin()
-    check(_lib.load().dfb_attention(C.byref(p), _stream()), "dfb_attention")
+    if q.dtype == torch.float32:
+        check(_lib.load().dfb_attention_f32(C.byref(p), _stream()), "dfb_attention_f32")
+    else:
+        check(_lib.load().dfb_attention(C.byref(p), _stream()), "dfb_attention")
     if e0 is not None:
         _prof_end(e0, "attention", 4.0 * q.shape[0] * heads * q.shape[1] * k.shape[1] * dp, (q.shape[0], heads, q.shape[1], k.shape[1], dp))
     _count(1)
@@ -247,11 +264,11 @@ def groupnorm(src0: torch.Tensor, src1: Optional[torch.Tensor], gamma: torch.Ten
         hw = src0.shape[1] * src0.shape[2] if src0.dim() == 4 else src0.shape[1]
         c0 = src0.shape[-1]
         c1 = 0 if src1 is None else src1.shape[-1]
-        assert hw % 32 == 0 and src0.dtype == torch.float32 and out.dtype == torch.bfloat16
+        assert hw % 32 == 0 and src0.dtype == torch.float32 and (raw_out is None or raw_out.dtype == out.dtype)
         check(_lib.load().dfb_groupnorm_fused(
             src0.data_ptr(), c0, src0.stride(-2), partials[0].data_ptr(), _ptr(src1), c1,
             0 if src1 is None else src1.stride(-2), None if src1 is None else partials[1].data_ptr(), b, hw, groups, eps,
-            gamma.data_ptr(), beta.data_ptr(), 1 if silu else 0, stats_ws.data_ptr(), out.data_ptr(), out.stride(-2),
+            gamma.data_ptr(), beta.data_ptr(), 1 if silu else 0, stats_ws.data_ptr(), out.data_ptr(), _dt(out), out.stride(-2),
             _ptr(raw_out), 0 if raw_out is None else raw_out.stride(-2), _stream()), "dfb_groupnorm_fused")
         _count(2)
         return out
@@ -259,11 +276,11 @@ def groupnorm(src0: torch.Tensor, src1: Optional[torch.Tensor], gamma: torch.Ten
     hw = src0.shape[1] * src0.shape[2] if src0.dim() == 4 else src0.shape[1]
     c0 = src0.shape[-1]
     c1 = 0 if src1 is None else src1.shape[-1]
-    assert src0.dtype == torch.float32 and out.dtype == torch.bfloat16
+    assert src0.dtype == torch.float32 and (raw_out is None or raw_out.dtype == out.dtype)
     assert stats_ws.dtype == torch.float32 and stats_ws.numel() >= groupnorm_ws_floats(b, groups)
     check(_lib.load().dfb_groupnorm(
         src0.data_ptr(), c0, src0.stride(-2), _ptr(src1), c1, 0 if src1 is None else src1.stride(-2), b, hw,
-        groups, eps, gamma.data_ptr(), beta.data_ptr(), 1 if silu else 0, stats_ws.data_ptr(), out.data_ptr(),
+        groups, eps, gamma.data_ptr(), beta.data_ptr(), 1 if silu else 0, stats_ws.data_ptr(), out.data_ptr(), _dt(out),
         out.stride(-2), _ptr(raw_out), 0 if raw_out is None else raw_out.stride(-2), _stream()), "dfb_groupnorm")
     _count(3)
     return out
@@ -271,11 +288,11 @@ def groupnorm(src0: torch.Tensor, src1: Optional[torch.Tensor], gamma: torch.Ten
 
 @_profiled("layernorm")
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: torch.Tensor, eps: float = 1e-5):
-    """LayerNorm over the last dim of fp32 ``[rows, C]`` -> bf16 ``out``."""
+    """LayerNorm over the last dim of fp32 ``[rows, C]`` -> ``out`` (bf16, or fp32 on the verification path)."""
     rows = x.numel() // x.shape[-1]
-    assert x.dtype == torch.float32 and out.dtype == torch.bfloat16
+    assert x.dtype == torch.float32
     check(_lib.load().dfb_layernorm(x.data_ptr(), x.stride(-2), gamma.data_ptr(), beta.data_ptr(), eps,
-                                    out.data_ptr(), out.stride(-2), rows, x.shape[-1], _stream()), "dfb_layernorm")
+                                    out.data_ptr(), _dt(out), out.stride(-2), rows, x.shape[-1], _stream()), "dfb_layernorm")
     _count(1)
     return out
 
@@ -311,9 +328,9 @@ def mutual_gather_sum(all_latents: Optional[torch.Tensor], prev_latents: torch.T
                       out: torch.Tensor):
     n_items, n_src = idx.shape
     d = prev_latents[0].numel()
-    assert idx.dtype == torch.int32 and idx.is_contiguous() and out.dtype == torch.bfloat16
+    assert idx.dtype == torch.int32 and idx.is_contiguous()
     check(_lib.load().dfb_mutual_gather_sum(_ptr(all_latents), prev_latents.data_ptr(), idx.data_ptr(), n_items,
-                                            n_src, d, out.data_ptr(), _stream()), "dfb_mutual_gather_sum")
+                                            n_src, d, out.data_ptr(), _dt(out), _stream()), "dfb_mutual_gather_sum")
     _count(1)
     return out
 
@@ -325,9 +342,9 @@ def mutual_blend(x: torch.Tensor, m: Optional[torch.Tensor], hist: Optional[torc
     n_items, hw = x.shape[0], x.shape[2] * x.shape[3]
     um = (C.c_int32 * nb)(*[int(v) for v in use_m])
     uh = (C.c_int32 * nb)(*[int(v) for v in use_h])
-    assert out.dtype == torch.bfloat16 and out.numel() == nb * n_items * hw * 8
+    assert out.numel() == nb * n_items * hw * 8
     check(_lib.load().dfb_mutual_blend(x.data_ptr(), _ptr(m), _ptr(hist), null_latent.data_ptr(), float(eta), nb, um,
-                                       uh, n_items, hw, out.data_ptr(), _stream()), "dfb_mutual_blend")
+                                       uh, n_items, hw, out.data_ptr(), _dt(out), _stream()), "dfb_mutual_blend")
     _count(1)
     return out
 
@@ -336,8 +353,8 @@ def mutual_blend(x: torch.Tensor, m: Optional[torch.Tensor], hist: Optional[torc
 def nchw_to_nhwc_bf16(x: torch.Tensor, out: torch.Tensor):
     b, c, h, w = x.shape
     assert x.is_contiguous()
-    check(_lib.load().dfb_nchw_to_nhwc_bf16(x.data_ptr(), _dt(x), out.data_ptr(), b, c, h * w, _stream()),
-          "dfb_nchw_to_nhwc_bf16")
+    check(_lib.load().dfb_nchw_to_nhwc(x.data_ptr(), _dt(x), out.data_ptr(), _dt(out), b, c, h * w, _stream()),
+          "dfb_nchw_to_nhwc")
     _count(1)
     return out
 
@@ -352,11 +369,14 @@ def nhwc_to_nchw(x: torch.Tensor, out: torch.Tensor):
     return out
 
 
+nchw_to_nhwc = nchw_to_nhwc_bf16      # the output dtype follows ``out`` (bf16 operand path / fp32 verification path)
+
+
 @_profiled("pad_cast_rows")
 def pad_cast_rows(x: torch.Tensor, out: torch.Tensor):
     b, s, d = x.shape
-    assert x.is_contiguous() and out.is_contiguous() and out.dtype == torch.bfloat16
-    check(_lib.load().dfb_pad_cast_rows(x.data_ptr(), _dt(x), out.data_ptr(), b, s, out.shape[1], d, _stream()),
+    assert x.is_contiguous() and out.is_contiguous()
+    check(_lib.load().dfb_pad_cast_rows(x.data_ptr(), _dt(x), out.data_ptr(), _dt(out), b, s, out.shape[1], d, _stream()),
           "dfb_pad_cast_rows")
     _count(1)
     return out
@@ -365,8 +385,8 @@ def pad_cast_rows(x: torch.Tensor, out: torch.Tensor):
 @_profiled("upsample2x")
 def upsample2x(x: torch.Tensor, out: torch.Tensor):
     b, h, w, c = x.shape
-    assert x.dtype == torch.float32 and x.is_contiguous() and out.dtype == torch.bfloat16 and out.is_contiguous()
-    check(_lib.load().dfb_upsample2x(x.data_ptr(), out.data_ptr(), b, h, w, c, _stream()), "dfb_upsample2x")
+    assert x.dtype == torch.float32 and x.is_contiguous() and out.is_contiguous()
+    check(_lib.load().dfb_upsample2x(x.data_ptr(), out.data_ptr(), _dt(out), b, h, w, c, _stream()), "dfb_upsample2x")
     _count(1)
     return out
 
@@ -374,8 +394,8 @@ def upsample2x(x: torch.Tensor, out: torch.Tensor):
 @_profiled("space_to_depth")
 def space_to_depth(x: torch.Tensor, out: torch.Tensor):
     b, h, w, c = x.shape
-    assert x.dtype == torch.float32 and x.is_contiguous() and out.dtype == torch.bfloat16 and out.is_contiguous()
-    check(_lib.load().dfb_space_to_depth(x.data_ptr(), out.data_ptr(), b, h, w, c, _stream()), "dfb_space_to_depth")
+    assert x.dtype == torch.float32 and x.is_contiguous() and out.is_contiguous()
+    check(_lib.load().dfb_space_to_depth(x.data_ptr(), out.data_ptr(), _dt(out), b, h, w, c, _stream()), "dfb_space_to_depth")
     _count(1)
     return out
 
@@ -395,8 +415,8 @@ def s2d_taps(c: int) -> Tuple[Tuple[int, int, int], ...]:
 
 @_profiled("timestep_embedding")
 def timestep_embedding(t: torch.Tensor, out: torch.Tensor, flip_sin_to_cos: bool = True, freq_shift: float = 0.0):
-    assert t.dtype == torch.float32 and t.is_contiguous() and out.dtype == torch.bfloat16 and out.is_contiguous()
-    check(_lib.load().dfb_timestep_embedding(t.data_ptr(), out.data_ptr(), t.shape[0], out.shape[1],
+    assert t.dtype == torch.float32 and t.is_contiguous() and out.is_contiguous()
+    check(_lib.load().dfb_timestep_embedding(t.data_ptr(), out.data_ptr(), _dt(out), t.shape[0], out.shape[1],
                                              1 if flip_sin_to_cos else 0, float(freq_shift), _stream()),
           "dfb_timestep_embedding")
     _count(1)

@@ -110,7 +110,7 @@ class B200DiFashionPipeline:
         x = st.latents[ch.n0:ch.n1]
         m = st.m[ch.n0:ch.n1] if st.m is not None else None
         hist = st.hist[ch.n0:ch.n1] if st.hist is not None else None
-        x_in = st.ws.get("pipe_x_in", (st.nb * n, st.size, st.size, 8), torch.bfloat16)
+        x_in = st.ws.get("pipe_x_in", (st.nb * n, st.size, st.size, 8), self.unet._op_dtype)
         ops.mutual_blend(x, m, hist, st.null, self.eta_mutual, st.use_m, st.use_h, x_in)
         return self.unet.forward_nhwc(x_in, st.t_dev[: st.nb * n], ch.ctx_bf16, ch.kv_store, st.ws)
 
@@ -122,7 +122,7 @@ class B200DiFashionPipeline:
 
     def _state(self, dev, n, n_given, olen, size, nb, S, D, plan) -> "_State":
         key = (str(dev), n, n_given, olen, size, nb, S, D, tuple(map(tuple, plan[:3])), self.use_history,
-               self.use_mutual_guidance, self.max_rows)
+               self.use_mutual_guidance, self.max_rows, str(self.unet._op_dtype))
         st = self._states.get(key)
         if st is not None:
             return st
@@ -140,18 +140,18 @@ class B200DiFashionPipeline:
             if self.mutual_encoder is None:
                 raise ValueError("use_mutual_guidance=True needs a MutualEncoder")
             st.idx = torch.empty(n, max(olen - 1, 1), dtype=torch.int32, device=dev)
-            st.msum = torch.empty(n, 4 * hw, dtype=torch.bfloat16, device=dev)
-            st.mhid = torch.empty(n, self.mutual_encoder.hid_dim, dtype=torch.bfloat16, device=dev)
+            st.msum = torch.empty(n, 4 * hw, dtype=self.unet._op_dtype, device=dev)
+            st.mhid = torch.empty(n, self.mutual_encoder.hid_dim, dtype=self.unet._op_dtype, device=dev)
             st.m = f(n, 4, size, size)
         per = max(1, self.max_rows // nb)
         st.t_dev = torch.zeros(nb * min(n, per), dtype=torch.float32, device=dev)
-        st.ws = self.unet.workspace(("pipe", nb, min(n, per), size), dev)
+        st.ws = self.unet.workspace(("pipe", nb, min(n, per), size, str(self.unet._op_dtype)), dev)
         st.chunks = []
         for n0 in range(0, n, per):
             n1 = min(n, n0 + per)
             rows = nb * (n1 - n0)
             st.chunks.append(_Chunk(n0, n1, torch.empty(rows, S, D, dtype=torch.float32, device=dev),
-                                    torch.empty(rows, S, D, dtype=torch.bfloat16, device=dev)))
+                                    torch.empty(rows, S, D, dtype=self.unet._op_dtype, device=dev)))
         st.warm = False
         self._states[key] = st
         return st

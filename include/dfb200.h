@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define DFB200_ABI_VERSION 1
+#define DFB200_ABI_VERSION 2
 
 #define DFB_OK 0
 #define DFB_ERR_INVALID (-1)
@@ -94,6 +94,14 @@ typedef struct dfb_gemm_params {
 
 int dfb_gemm(const dfb_gemm_params* p, void* stream);
 
+/* fp32 verification path (BASELINE.json north_star: per-step noise-prediction rel-L2 <= 1e-4 in fp32): the same
+ * operator with fp32 A segments, fp32 packed weights (same [N, Kp] layout), fp32 residual / output, on the CUDA
+ * cores (FFMA).  Same struct; geglu must be 0 (pair the packed columns with dfb_geglu_f32 afterwards:
+ * out[m, g*16+j] = in[m, g*32+j] * gelu_erf(in[m, g*32+16+j])), gn_partial must be NULL, block_n is ignored.
+ * Not a throughput path. */
+int dfb_gemm_f32(const dfb_gemm_params* p, void* stream);
+int dfb_geglu_f32(const float* in, int in_ld, float* out, int out_ld, int M, int N, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Flash attention forward (tcgen05 QK^T and PV, online softmax, TMA-fed).
  *
@@ -120,16 +128,20 @@ typedef struct dfb_attn_params {
 } dfb_attn_params;
 
 int dfb_attention(const dfb_attn_params* p, void* stream);
+/* fp32 verification path: q/k/v/out fp32, same layout conventions (dp <= 160), expf softmax on the CUDA cores. */
+int dfb_attention_f32(const dfb_attn_params* p, void* stream);
 
 /* ABI self-check for language bindings (ctypes / cgo / JNI mirrors of the structs above). */
 size_t dfb_sizeof_gemm_params(void);
 size_t dfb_sizeof_attn_params(void);
 
 /* ------------------------------------------------------------------------------------------
- * Norm kernels producing bf16 GEMM operands from the fp32 residual stream (NHWC).
+ * Norm kernels producing the GEMM operands from the fp32 residual stream (NHWC).  Every operand-producing
+ * kernel below takes `out_dtype`: DFB_DTYPE_BF16 for the tensor-core path, DFB_DTYPE_F32 for the fp32
+ * verification path (dfb_gemm_f32 / dfb_attention_f32).
  * dfb_groupnorm replaces nn.GroupNorm(32, C)(+SiLU) of ResnetBlock2D.norm1/norm2,
  * Transformer2DModel.norm and conv_norm_out; reads the up-block skip concat from its two sources
- * (torch.cat([h, skip], 1) is never materialised); optional raw bf16 copy of the input (the A
+ * (torch.cat([h, skip], 1) is never materialised); optional raw copy of the input in the output dtype (the A
  * operand of conv_shortcut).  stats_ws: fp32 scratch of dfb_groupnorm_ws_floats(B, groups) elements.
  * Deterministic (fixed-order reductions, no atomics).
  * dfb_layernorm replaces BasicTransformerBlock.norm1/2/3.
@@ -137,14 +149,14 @@ size_t dfb_sizeof_attn_params(void);
 size_t dfb_groupnorm_ws_floats(int B, int groups);
 int dfb_groupnorm(const float* src0, int c0, int ld0, const float* src1, int c1, int ld1, int B, int hw,
                   int groups, float eps, const float* gamma, const float* beta, int silu, float* stats_ws,
-                  void* out_bf16, int ld_out, void* raw_out_bf16, int ld_raw, void* stream);
+                  void* out, int out_dtype, int ld_out, void* raw_out, int ld_raw, void* stream);
 /* GroupNorm whose statistics come from the producers' epilogues (dfb_gemm_params.gn_partial) instead of an
  * extra pass over the input: finalize (fixed-order fold of the partials) + apply.  hw % 32 == 0. */
 int dfb_groupnorm_fused(const float* src0, int c0, int ld0, const float* partial0, const float* src1, int c1, int ld1,
                         const float* partial1, int B, int hw, int groups, float eps, const float* gamma,
-                        const float* beta, int silu, float* stats_ws, void* out_bf16, int ld_out, void* raw_out_bf16,
+                        const float* beta, int silu, float* stats_ws, void* out, int out_dtype, int ld_out, void* raw_out,
                         int ld_raw, void* stream);
-int dfb_layernorm(const float* x, int ld_x, const float* gamma, const float* beta, float eps, void* out_bf16,
+int dfb_layernorm(const float* x, int ld_x, const float* gamma, const float* beta, float eps, void* out, int out_dtype,
                   int ld_out, int rows, int C, void* stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -160,24 +172,24 @@ int dfb_cfg_step(const float* eps, int eps_nchw, int nb, const float* w, const f
                  const float* hist1, const float* hist2, const float* hist3, const float* noise, float cn,
                  float* x_out, float* eps_out, int n_items, int hw, void* stream);
 /* Mutual-condition neighbour sum (difashion.py:475-488): out[n] = sum_s src(idx[n, s]); idx >= 0 ->
- * all_latents row, idx < 0 -> prev_latents row (-idx-1), INT32_MIN -> skip.  out bf16 [N, d]. */
+ * all_latents row, idx < 0 -> prev_latents row (-idx-1), INT32_MIN -> skip.  out [N, d]. */
 int dfb_mutual_gather_sum(const float* all_latents, const float* prev_latents, const int32_t* idx, int n_items,
-                          int n_src, int d, void* out_bf16, void* stream);
+                          int n_src, int d, void* out, int out_dtype, void* stream);
 /* Mutual blend + history concat + CFG branch expansion (difashion.py:458-459, :494-515, :388-390):
- * writes the UNet input NHWC bf16 [nb*N, hw, 8].  use_m / use_h: host int32[nb].              */
+ * writes the UNet input NHWC [nb*N, hw, 8].  use_m / use_h: host int32[nb].              */
 int dfb_mutual_blend(const float* x, const float* m, const float* hist, const float* null_latent, float eta,
-                     int nb, const int32_t* use_m, const int32_t* use_h, int n_items, int hw, void* out_bf16,
+                     int nb, const int32_t* use_m, const int32_t* use_h, int n_items, int hw, void* out, int out_dtype,
                      void* stream);
 /* Layout conversions at the diffusers API boundary (NCHW tensors in, NHWC inside). */
-int dfb_nchw_to_nhwc_bf16(const void* in, int in_dtype, void* out_bf16, int B, int C, int HW, void* stream);
+int dfb_nchw_to_nhwc(const void* in, int in_dtype, void* out, int out_dtype, int B, int C, int HW, void* stream);
 int dfb_nhwc_to_nchw(const float* in, void* out, int out_dtype, int B, int C, int HW, void* stream);
-int dfb_pad_cast_rows(const void* in, int in_dtype, void* out_bf16, int B, int S, int S_pad, int D, void* stream);
-/* Upsample2D nearest-2x (fp32 NHWC -> bf16 NHWC) and the space-to-depth feeding Downsample2D's
- * stride-2 conv (fp32 NHWC [B,H,W,C] -> bf16 [B,H/2,W/2,4C]). */
-int dfb_upsample2x(const float* in, void* out_bf16, int B, int H, int W, int C, void* stream);
-int dfb_space_to_depth(const float* in, void* out_bf16, int B, int H, int W, int C, void* stream);
-/* diffusers Timesteps (get_timestep_embedding): t fp32 [B] -> bf16 [B, dim] = [cos | sin]. */
-int dfb_timestep_embedding(const float* t, void* out_bf16, int B, int dim, int flip_sin_to_cos, float freq_shift,
+int dfb_pad_cast_rows(const void* in, int in_dtype, void* out, int out_dtype, int B, int S, int S_pad, int D, void* stream);
+/* Upsample2D nearest-2x (fp32 NHWC -> NHWC operand) and the space-to-depth feeding Downsample2D's
+ * stride-2 conv (fp32 NHWC [B,H,W,C] -> [B,H/2,W/2,4C]). */
+int dfb_upsample2x(const float* in, void* out, int out_dtype, int B, int H, int W, int C, void* stream);
+int dfb_space_to_depth(const float* in, void* out, int out_dtype, int B, int H, int W, int C, void* stream);
+/* diffusers Timesteps (get_timestep_embedding): t fp32 [B] -> [B, dim] = [cos | sin]. */
+int dfb_timestep_embedding(const float* t, void* out, int out_dtype, int B, int dim, int flip_sin_to_cos, float freq_shift,
                            void* stream);
 
 #ifdef __cplusplus

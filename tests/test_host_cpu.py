@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_library_loads_and_exports_every_declared_symbol():
     from difashion_b200 import _lib
     lib = _lib.load()
-    assert lib.dfb_abi_version() == 1
+    assert lib.dfb_abi_version() == 2
     header = open(os.path.join(ROOT, "include", "dfb200.h")).read()
     declared = set(re.findall(r"\b(dfb_[a-z0-9_]+)\s*\(", header))
     assert declared, "no declarations parsed"
@@ -38,7 +38,12 @@ def test_argument_validation_without_gpu():
     p.nseg = 3
     assert lib.dfb_gemm(ctypes.byref(p), None) == -1
     assert lib.dfb_attention(None, None) == -1
-    assert lib.dfb_layernorm(None, 0, None, None, 1e-5, None, 0, 0, 0, None) == -1
+    assert lib.dfb_layernorm(None, 0, None, None, 1e-5, None, 0, 0, 0, 0, None) == -1
+    # fp32 verification path: same structs, same validation
+    assert lib.dfb_gemm_f32(None, None) == -1
+    assert lib.dfb_gemm_f32(ctypes.byref(p), None) == -1
+    assert lib.dfb_attention_f32(None, None) == -1
+    assert lib.dfb_geglu_f32(None, 0, None, 0, 0, 0, None) == -1
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
