@@ -2,7 +2,7 @@
 
 Public surface (mirrors what ``DiFashion/models/difashion.py`` consumes from diffusers):
 ``B200UNet2DConditionModel``, ``B200AttnProcessor``, ``B200DDIMScheduler``, ``B200PNDMScheduler``,
-``MutualEncoder``, ``B200DiFashionPipeline``.  All arithmetic runs in ``libdfb200.so`` (hand-written CUDA,
+``MutualEncoder``, ``B200DiFashionPipeline``, ``B200AutoencoderKL`` (decode half: the step after the loop).  All arithmetic runs in ``libdfb200.so`` (hand-written CUDA,
 C ABI in ``include/dfb200.h``); importing this package never imports the test oracle.
 """
 from .attention import Attention, B200AttnProcessor  # noqa: F401
@@ -10,7 +10,8 @@ from .mutual import MutualEncoder  # noqa: F401
 from .pipeline import B200DiFashionPipeline, guidance_plan, mutual_index_table, shard_outfits  # noqa: F401
 from .schedulers import B200DDIMScheduler, B200PNDMScheduler  # noqa: F401
 from .unet import B200UNet2DConditionModel, UNet2DConditionOutput  # noqa: F401
+from .vae import B200AutoencoderKL, DecoderOutput  # noqa: F401
 
 __all__ = ["B200UNet2DConditionModel", "UNet2DConditionOutput", "B200AttnProcessor", "Attention", "B200DDIMScheduler",
            "B200PNDMScheduler", "MutualEncoder", "B200DiFashionPipeline", "guidance_plan", "mutual_index_table",
-           "shard_outfits"]
+           "shard_outfits", "B200AutoencoderKL", "DecoderOutput"]

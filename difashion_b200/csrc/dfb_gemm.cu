@@ -38,7 +38,7 @@ struct GemmMaps {
 
 struct GemmKernelParams {
   int M, N, block_n, n_tiles_m, n_tiles_n;
-  int conv, TH, TB, tiles_per_img;
+  int conv, TH, TB, tiles_per_img, w_tiles;   // w_tiles > 1: images wider than 128 pixels, one tile = 128 pixels of a row
   int nseg;
   int seg_ntaps[2];
   int seg_ncblk[2];
@@ -112,11 +112,17 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mt = tile / p.n_tiles_n;
       const int nt = tile - mt * p.n_tiles_n;
-      int b0 = 0, h0 = 0;
+      int b0 = 0, h0 = 0, w0 = 0;
       if (p.conv) {
         if (p.TB == 1) {
           b0 = mt / p.tiles_per_img;
-          h0 = (mt - b0 * p.tiles_per_img) * p.TH;
+          const int r = mt - b0 * p.tiles_per_img;
+          if (p.w_tiles > 1) {
+            h0 = r / p.w_tiles;
+            w0 = (r - h0 * p.w_tiles) * GEMM_BLOCK_M;
+          } else {
+            h0 = r * p.TH;
+          }
         } else {
           b0 = mt * p.TB;
         }
@@ -134,7 +140,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
               const uint32_t sb = sa + GEMM_A_BYTES;
               mbar_expect_tx(full_bar(stage), tx_bytes);
               if (p.conv)
-                tma_load_4d(tm, sa, full_bar(stage), coff + cb * GEMM_BLOCK_K, dw, h0 + dh, b0);
+                tma_load_4d(tm, sa, full_bar(stage), coff + cb * GEMM_BLOCK_K, w0 + dw, h0 + dh, b0);
               else
                 tma_load_2d(tm, sa, full_bar(stage), coff + cb * GEMM_BLOCK_K, mt * GEMM_BLOCK_M);
               tma_load_2d(&maps.b, sb, full_bar(stage), kb * GEMM_BLOCK_K, nt * p.block_n);
@@ -594,16 +600,28 @@ extern "C" int dfb_gemm(const dfb_gemm_params* q, void* stream_) {
   if (kp.conv) {
     const int B = q->B, H = q->H, W = q->W;
     DFB_REQUIRE(B > 0 && H > 0 && W > 0 && (long long)B * H * W == q->M, "dfb_gemm: conv geometry does not match M");
-    DFB_REQUIRE(W <= 128 && (128 % W) == 0, "dfb_gemm: conv width must divide 128");
-    int TH = 128 / W;
-    if (TH > H) TH = H;
-    DFB_REQUIRE(H % TH == 0 && (128 % (W * TH)) == 0, "dfb_gemm: conv height incompatible with 128-pixel tiles");
-    const int TB = 128 / (W * TH);
-    kp.TH = TH;
-    kp.TB = TB;
-    kp.tiles_per_img = H / TH;
-    kp.n_tiles_m = TB == 1 ? B * kp.tiles_per_img : (B + TB - 1) / TB;
-    boxA[0] = GEMM_BLOCK_K; boxA[1] = (uint32_t)W; boxA[2] = (uint32_t)TH; boxA[3] = (uint32_t)TB;
+    kp.w_tiles = 1;
+    if (W > 128) {
+      // wide images (VAE decoder: 256 / 512 pixels): one tile = 128 consecutive pixels of one row
+      DFB_REQUIRE(W % 128 == 0, "dfb_gemm: conv width above 128 must be a multiple of 128");
+      kp.TH = 1;
+      kp.TB = 1;
+      kp.w_tiles = W / 128;
+      kp.tiles_per_img = H * kp.w_tiles;
+      kp.n_tiles_m = B * kp.tiles_per_img;
+      boxA[0] = GEMM_BLOCK_K; boxA[1] = 128; boxA[2] = 1; boxA[3] = 1;
+    } else {
+      DFB_REQUIRE((128 % W) == 0, "dfb_gemm: conv width must divide 128");
+      int TH = 128 / W;
+      if (TH > H) TH = H;
+      DFB_REQUIRE(H % TH == 0 && (128 % (W * TH)) == 0, "dfb_gemm: conv height incompatible with 128-pixel tiles");
+      const int TB = 128 / (W * TH);
+      kp.TH = TH;
+      kp.TB = TB;
+      kp.tiles_per_img = H / TH;
+      kp.n_tiles_m = TB == 1 ? B * kp.tiles_per_img : (B + TB - 1) / TB;
+      boxA[0] = GEMM_BLOCK_K; boxA[1] = (uint32_t)W; boxA[2] = (uint32_t)TH; boxA[3] = (uint32_t)TB;
+    }
   } else {
     kp.n_tiles_m = (q->M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
     boxA[0] = GEMM_BLOCK_K; boxA[1] = GEMM_BLOCK_M;

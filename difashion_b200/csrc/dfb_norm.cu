@@ -258,6 +258,66 @@ layernorm_kernel(const float* __restrict__ x, int ld_x, const float* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Row softmax of a materialised score matrix: out[r, :] = softmax(scale * in[r, :]).  Used by the VAE decoder's
+// single-head d = 512 attention (one layer, 4096 tokens per image), which runs as GEMMs around this kernel
+// because its head dimension exceeds the flash kernel's TMEM budget.  One block per row, row held in
+// registers (cols <= 256 * 4 * SM_MAX_VEC), fp32 math.
+// ---------------------------------------------------------------------------------------------
+constexpr int SM_MAX_VEC = 8;
+template <typename TOut>
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ in, int in_ld, float scale,
+                                                           TOut* __restrict__ out, int out_ld, int rows, int cols) {
+  __shared__ float red[8];
+  const int nvec = cols >> 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const float4* src = reinterpret_cast<const float4*>(in + (size_t)row * in_ld);
+    float4 v[SM_MAX_VEC];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < SM_MAX_VEC; ++k) {
+      const int j = threadIdx.x + k * 256;
+      if (j < nvec) {
+        v[k] = __ldg(src + j);
+        mx = fmaxf(fmaxf(mx, fmaxf(v[k].x, v[k].y)), fmaxf(v[k].z, v[k].w));
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    __syncthreads();
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+    const float m2 = mx * scale;
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < SM_MAX_VEC; ++k) {
+      const int j = threadIdx.x + k * 256;
+      if (j < nvec) {
+        v[k].x = expf(fmaf(v[k].x, scale, -m2)); v[k].y = expf(fmaf(v[k].y, scale, -m2));
+        v[k].z = expf(fmaf(v[k].z, scale, -m2)); v[k].w = expf(fmaf(v[k].w, scale, -m2));
+        sum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __syncthreads();
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    sum = ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
+    const float inv = 1.f / sum;
+    TOut* orow = out + (size_t)row * out_ld;
+#pragma unroll
+    for (int k = 0; k < SM_MAX_VEC; ++k) {
+      const int j = threadIdx.x + k * 256;
+      if (j < nvec) store4(orow + (j << 2), v[k].x * inv, v[k].y * inv, v[k].z * inv, v[k].w * inv);
+    }
+  }
+}
+
 }  // namespace dfb
 
 using namespace dfb;
@@ -365,6 +425,20 @@ int dfb_layernorm(const float* x, int ld_x, const float* gamma, const float* bet
   if (out_dtype == DFB_DTYPE_F32) DFB_LN_LAUNCH(float);
   else DFB_LN_LAUNCH(__nv_bfloat16);
 #undef DFB_LN_LAUNCH
+  DFB_CHECK_CUDA(cudaGetLastError());
+  return DFB_OK;
+}
+
+int dfb_softmax_rows(const float* in, int in_ld, float scale, void* out, int out_dtype, int out_ld, int rows, int cols,
+                     void* stream) {
+  DFB_REQUIRE(in && out && rows > 0 && cols > 0, "dfb_softmax_rows: bad args");
+  DFB_REQUIRE(cols % 4 == 0 && cols <= 256 * 4 * SM_MAX_VEC && in_ld % 4 == 0 && out_ld % 4 == 0,
+              "dfb_softmax_rows: cols must be a multiple of 4, at most 8192; pitches multiples of 4");
+  int blocks = rows < num_sms() * 8 ? rows : num_sms() * 8;
+  if (out_dtype == DFB_DTYPE_F32)
+    softmax_rows_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(in, in_ld, scale, (float*)out, out_ld, rows, cols);
+  else
+    softmax_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>(in, in_ld, scale, (__nv_bfloat16*)out, out_ld, rows, cols);
   DFB_CHECK_CUDA(cudaGetLastError());
   return DFB_OK;
 }

@@ -297,6 +297,17 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: tor
     return out
 
 
+@_profiled("softmax_rows")
+def softmax_rows(x: torch.Tensor, out: torch.Tensor, scale: float = 1.0):
+    """``out[r, :] = softmax(scale * x[r, :])`` for a materialised fp32 score matrix ``[rows, cols]``."""
+    rows, cols = x.shape
+    assert x.dtype == torch.float32 and x.stride(-1) == 1 and out.stride(-1) == 1 and out.shape == x.shape
+    check(_lib.load().dfb_softmax_rows(x.data_ptr(), x.stride(0), float(scale), out.data_ptr(), _dt(out), out.stride(0),
+                                       rows, cols, _stream()), "dfb_softmax_rows")
+    _count(1)
+    return out
+
+
 # ----------------------------------------------------------------------------------------------
 # streaming kernels
 # ----------------------------------------------------------------------------------------------

@@ -159,6 +159,12 @@ int dfb_groupnorm_fused(const float* src0, int c0, int ld0, const float* partial
 int dfb_layernorm(const float* x, int ld_x, const float* gamma, const float* beta, float eps, void* out, int out_dtype,
                   int ld_out, int rows, int C, void* stream);
 
+/* Row softmax of a materialised score matrix: out[r, :] = softmax(scale * in[r, :]) (fp32 in, bf16/fp32 out).
+ * Replaces the softmax of the VAE decoder's single-head d=512 mid-block attention (AutoencoderKL.decode,
+ * DiFashion/models/difashion.py:579), which runs as dfb_gemm launches around this kernel. */
+int dfb_softmax_rows(const float* in, int in_ld, float scale, void* out, int out_dtype, int out_ld, int rows, int cols,
+                     void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * HBM-streaming kernels of the loop body (DiFashion/models/difashion.py:456-577).
  * ------------------------------------------------------------------------------------------ */

@@ -161,3 +161,30 @@ def test_generation_golden_and_cfg_identity():
     n = gold["inputs"]["init_latents"].shape[0]
     assert rec1[0]["noise_pred_branches"].shape[0] == n
     assert torch.allclose(rec1[0]["noise_pred"], gold["eps_branches_step0"][:n], rtol=1e-4, atol=1e-5)
+
+
+def test_vae_decoder_oracle_structure_and_shapes():
+    """AutoencoderKL decode half: published SD-VAE parameter split, diffusers key names."""
+    from oracle.vae_oracle import make_oracle_vae, tiny_vae_config
+    m = make_oracle_vae()
+    assert sum(p.numel() for p in m.decoder.parameters()) == 49_490_179
+    assert sum(p.numel() for p in m.post_quant_conv.parameters()) == 20
+    # 83 653 863 (published SD VAE total) = encoder 34 163 592 + quant_conv 72 + decoder + post_quant_conv
+    assert 34_163_592 + 72 + 49_490_179 + 20 == 83_653_863
+    sd = m.state_dict()
+    assert len(sd) == 140
+    for k in ("post_quant_conv.weight", "decoder.conv_in.bias", "decoder.mid_block.attentions.0.group_norm.weight",
+              "decoder.mid_block.attentions.0.to_q.bias", "decoder.mid_block.attentions.0.to_out.0.weight",
+              "decoder.up_blocks.2.resnets.0.conv_shortcut.weight", "decoder.up_blocks.0.upsamplers.0.conv.weight",
+              "decoder.up_blocks.3.resnets.2.conv2.bias", "decoder.conv_norm_out.weight", "decoder.conv_out.bias"):
+        assert k in sd, k
+    assert "decoder.up_blocks.3.upsamplers.0.conv.weight" not in sd
+    assert sd["decoder.up_blocks.2.resnets.0.conv1.weight"].shape == (256, 512, 3, 3)
+    assert sd["decoder.up_blocks.3.resnets.0.conv1.weight"].shape == (128, 256, 3, 3)
+    t = make_oracle_vae(tiny_vae_config(), seed=3)
+    z = torch.randn(2, 4, 16, 16, generator=torch.Generator().manual_seed(5))
+    y = t.decode_latents(z)
+    assert y.shape == (2, 3, 128, 128) and torch.isfinite(y).all()
+    assert torch.equal(y, t.decode(z / t.cfg.scaling_factor))
+    # the attention's residual connection and the decoder are deterministic
+    assert torch.equal(y, make_oracle_vae(tiny_vae_config(), seed=3).decode_latents(z))
