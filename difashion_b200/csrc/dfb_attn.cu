@@ -687,6 +687,287 @@ attn_fwd_db_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant_
   }
 }
 
+
+// =================================================================================================
+// Split-KV variant of the double-buffered kernel (block_kv == 64, dp <= 64) — an EXPERIMENT, not the default (see
+// dfb_attention below).  ncu of attn_fwd_db_kernel showed neither the MUFU (63 %) nor the issue slots (57 %)
+// saturated, which suggested latency-bound exponential chains with two softmax warps per scheduler.
+// Here EIGHT softmax warps per CTA (four per scheduler with two CTAs per SM) each own 32 of the 64 columns of
+// every score tile:  warps 0-3 (half a) columns [0,32), warps 4-7 (half b) columns [32,64) of the same 128 rows.
+// The halves are independent online-softmax streams over disjoint key subsets — own reference max, own row sum,
+// own accumulator O_a / O_b in tensor memory — so the main loop has no cross-warp communication at all; the
+// two partial results are merged once in the epilogue:
+//     O = (2^(m_a-m) O_a + 2^(m_b-m) O_b) / (2^(m_a-m) l_a + 2^(m_b-m) l_b),   m = max(m_a, m_b).
+// TMEM columns: S[0] 64 | S[1] 64 | O_a dp | O_b dp  (<= 256: two CTAs per SM).  P_x (bf16) overwrites the first
+// 16 columns of its own half of the score buffer and feeds the TS-form PV MMA.
+//   warps 0..7 softmax, warp 8 TMA producer, warp 9 MMA issuer (control warps at the highest ids).
+// =================================================================================================
+constexpr int ATT_SPLIT_THREADS = 320;
+
+__global__ void __launch_bounds__(ATT_SPLIT_THREADS, 2)
+attn_fwd_split_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnKernelParams p) {
+  constexpr int KV = 64, HK = 32;
+  constexpr int NST_MAX = 3;
+  const int NST = p.kv_stages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int dchunks = p.dp >> 4;
+  const uint32_t q_bytes = (uint32_t)dchunks * ATT_BLOCK_Q * 32u;
+  constexpr uint32_t kv_chunk_bytes = KV * 32u;
+  const uint32_t kv_tile_bytes = (uint32_t)dchunks * kv_chunk_bytes;
+  const uint32_t sQ = smem_base;
+  const uint32_t sKV = sQ + q_bytes;                                         // stage s: K then V
+  const uint32_t sML = sKV + NST * 2 * kv_tile_bytes;                        // (m, l) of half b: [128][2] floats
+  const uint32_t bar_base = sML + ATT_BLOCK_Q * 8u;
+  const uint32_t q_full = bar_base;
+  auto s_full = [&](int i) { return bar_base + 8u + 8u * i; };
+  auto p_full = [&](int i, int h) { return bar_base + 24u + 8u * (2 * i + h); };
+  auto o_done = [&](int i) { return bar_base + 56u + 8u * i; };
+  auto kv_full = [&](int s) { return bar_base + 72u + 8u * s; };
+  auto kv_empty = [&](int s) { return bar_base + 72u + 8u * (NST_MAX + s); };
+  const uint32_t tmem_ptr_smem = bar_base + 72u + 8u * (2 * NST_MAX);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  const int n_tiles = p.n_kv_tiles;
+  constexpr int W_TMA = 8, W_MMA = 9;
+
+  if (warp == W_TMA && lane == 0) {
+    tma_prefetch_desc(&maps.q);
+    tma_prefetch_desc(&maps.k);
+    tma_prefetch_desc(&maps.v);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(s_full(i), 1);
+      mbar_init(p_full(i, 0), 128);
+      mbar_init(p_full(i, 1), 128);
+      mbar_init(o_done(i), 1);
+    }
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(kv_full(s), 1);
+      mbar_init(kv_empty(s), 1);
+    }
+    fence_mbar_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == W_MMA) tmem_alloc(tmem_ptr_smem, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+  const uint32_t tmem_O0 = tmem_base + 2u * KV;                              // O_a, then O_b at + dp
+
+  if (warp == W_TMA) {
+    // ---------------- TMA producer ----------------
+    if (elect_one()) {
+      mbar_expect_tx(q_full, q_bytes);
+      for (int c = 0; c < dchunks; ++c)
+        tma_load_3d(&maps.q, sQ + (uint32_t)c * ATT_BLOCK_Q * 32u, q_full, p.q_col0 + head * p.dp + c * 16,
+                    qt * ATT_BLOCK_Q, b);
+    }
+    __syncwarp();
+    int st = 0;
+    uint32_t ph = 0;
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(kv_empty(st), ph ^ 1u);
+      if (elect_one()) {
+        const uint32_t sK = sKV + (uint32_t)st * 2 * kv_tile_bytes;
+        const uint32_t sV = sK + kv_tile_bytes;
+        mbar_expect_tx(kv_full(st), 2 * kv_tile_bytes);
+        for (int c = 0; c < dchunks; ++c)
+          tma_load_3d(&maps.k, sK + (uint32_t)c * kv_chunk_bytes, kv_full(st), p.k_col0 + head * p.dp + c * 16, j * KV, b);
+        for (int c = 0; c < dchunks; ++c)
+          tma_load_3d(&maps.v, sV + (uint32_t)c * kv_chunk_bytes, kv_full(st), p.v_col0 + head * p.dp + c * 16, j * KV, b);
+      }
+      __syncwarp();
+      if (++st == NST) { st = 0; ph ^= 1u; }
+    }
+  } else if (warp == W_MMA) {
+    // ---------------- MMA issuer (warp-uniform, one elected lane issues) ----------------
+    const uint32_t idesc_qk = make_idesc_f16(ATT_BLOCK_Q, (uint32_t)KV, true, 0, 0);
+    const uint32_t idesc_pv = make_idesc_f16(ATT_BLOCK_Q, (uint32_t)p.dp, true, 0, 1);
+    const uint64_t desc_q0 = make_smem_desc(sQ, 16, 256, SWZ_32B);
+    const uint64_t desc_k0 = make_smem_desc(sKV, 16, 256, SWZ_32B);
+    const uint64_t desc_v0 = make_smem_desc(sKV + kv_tile_bytes, KV * 32u, 256, SWZ_32B);
+    const uint32_t stage_step = (2 * kv_tile_bytes) >> 4;
+    auto issue_qk = [&](int jj) {                 // S[jj & 1] = Q K_jj^T
+      const int st = jj % NST;
+      mbar_wait(kv_full(st), (uint32_t)(jj / NST) & 1u);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t dk = desc_k0 + (uint64_t)((uint32_t)st * stage_step);
+        const uint32_t tS = tmem_base + (uint32_t)(jj & 1) * KV;
+        for (int c = 0; c < dchunks; ++c)
+          umma_f16_ss(tS, desc_q0 + (uint64_t)(c * (ATT_BLOCK_Q * 32 / 16)), dk + (uint64_t)(c * (int)(kv_chunk_bytes >> 4)),
+                      idesc_qk, c != 0);
+        umma_commit(s_full(jj & 1));
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    issue_qk(0);
+    if (n_tiles > 1) issue_qk(1);
+    for (int j = 0; j < n_tiles; ++j) {
+      const int bi = j & 1;
+      const int st = j % NST;
+      const uint64_t dv = desc_v0 + (uint64_t)((uint32_t)st * stage_step);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        mbar_wait(p_full(bi, h), (uint32_t)(j >> 1) & 1u);      // P_h of tile j written over its half of S[bi]
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < HK / 16; ++k)
+            umma_f16_ts(tmem_O0 + (uint32_t)(h * p.dp), tmem_base + (uint32_t)bi * KV + (uint32_t)(h * HK + 8 * k),
+                        dv + (uint64_t)((h * (HK / 16) + k) * (512 / 16)), idesc_pv, (j | k) != 0);
+          if (h == 1) {
+            umma_commit(o_done(bi));
+            umma_commit(kv_empty(st));
+          }
+        }
+        __syncwarp();
+      }
+      if (j + 2 < n_tiles) issue_qk(j + 2);
+    }
+  } else {
+    // ---------------- softmax warps: half = warp / 4 owns score columns [32 half, 32 half + 32) ----------------
+    const int half = warp >> 2;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const int q_row = qt * ATT_BLOCK_Q + row;
+    const uint32_t tO = tmem_O0 + (uint32_t)(half * p.dp) + lane_addr;
+    float m_ref = -INFINITY, l = 0.f;
+    for (int j = 0; j < n_tiles; ++j) {
+      const int bi = j & 1;
+      const uint32_t tS = tmem_base + (uint32_t)bi * KV + (uint32_t)(half * HK) + lane_addr;
+      mbar_wait(s_full(bi), (uint32_t)(j >> 1) & 1u);
+      tc_fence_after();
+      int kv_valid = p.Skv - j * KV - half * HK;
+      kv_valid = kv_valid < 0 ? 0 : (kv_valid > HK ? HK : kv_valid);
+      uint32_t sreg[HK];
+      uint32_t pw[HK / 2];
+      bool careful = (kv_valid != HK) || (j == 0);
+      float mx = -INFINITY;
+      tmem_ld_32x32b_x16(tS, *reinterpret_cast<uint32_t(*)[16]>(&sreg[0]));
+      if (!careful) {
+        // optimistic pass: exponentials against the running reference max while the second 16 columns load
+        float m8[8], l8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { m8[i] = -INFINITY; l8[i] = 0.f; }
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          tmem_ld_wait();
+          if (c == 0) tmem_ld_32x32b_x16(tS + 16u, *reinterpret_cast<uint32_t(*)[16]>(&sreg[16]));
+          float pv[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float sv = __uint_as_float(sreg[c * 16 + i]);
+            m8[i & 7] = fmaxf(m8[i & 7], sv);
+            pv[i] = ex2f(fmaf(sv, p.scale_log2, -m_ref));
+            l8[i & 7] += pv[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pw[c * 8 + i] = pack_bf16x2(pv[2 * i], pv[2 * i + 1]);
+        }
+        mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7]))) * p.scale_log2;
+        careful = __any_sync(0xffffffffu, mx > m_ref + 8.0f);
+        if (!careful) l += ((l8[0] + l8[1]) + (l8[2] + l8[3])) + ((l8[4] + l8[5]) + (l8[6] + l8[7]));
+      } else {
+        tmem_ld_32x32b_x16(tS + 16u, *reinterpret_cast<uint32_t(*)[16]>(&sreg[16]));
+        tmem_ld_wait();
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int i = 0; i < HK; ++i)
+          if (i < kv_valid) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(sreg[i]));
+        mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * p.scale_log2;
+      }
+      if (careful) {
+        // new reference max for this half: rescale O_half (needs every earlier PV retired) and l, redo from registers
+        const bool need = mx > m_ref + 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          const float m_new = need ? mx : m_ref;
+          const float alpha = ex2f(m_ref - m_new);     // m_ref = -inf on the first tile -> 0
+          if (j > 0) {
+            mbar_wait(o_done((j - 1) & 1), (uint32_t)((j - 1) >> 1) & 1u);
+            tc_fence_after();
+            for (int c = 0; c < dchunks; ++c) {
+              uint32_t r[16];
+              tmem_ld_32x32b_x16(tO + (uint32_t)(c * 16), r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+              tmem_st_32x32b_x16(tO + (uint32_t)(c * 16), r);
+            }
+            tmem_st_wait();
+          }
+          l *= alpha;
+          m_ref = m_new;
+        }
+        float l4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < HK / 16; ++c) {
+          float pv[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float e = ex2f(fmaf(__uint_as_float(sreg[c * 16 + i]), p.scale_log2, -m_ref));
+            pv[i] = (c * 16 + i < kv_valid) ? e : 0.f;
+            l4[i & 3] += pv[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pw[c * 8 + i] = pack_bf16x2(pv[2 * i], pv[2 * i + 1]);
+        }
+        l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+      }
+      // P_half (bf16, two per column) over the first 16 columns of this half of the score buffer
+      tmem_st_32x32b_x16(tS, *reinterpret_cast<uint32_t(*)[16]>(&pw[0]));
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(p_full(bi, half));
+    }
+    // ---- epilogue: merge the two halves, O / l -> bf16 ----
+    mbar_wait(o_done((n_tiles - 1) & 1), (uint32_t)((n_tiles - 1) >> 1) & 1u);
+    tc_fence_after();
+    if (half == 1) {
+      asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(sML + (uint32_t)row * 8u), "f"(m_ref), "f"(l) : "memory");
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");          // the 8 softmax warps only
+    if (half == 0) {
+      float m_b, l_b;
+      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(m_b), "=f"(l_b) : "r"(sML + (uint32_t)row * 8u));
+      const float m = fmaxf(m_ref, m_b);
+      const float wa = ex2f(m_ref - m), wb = ex2f(m_b - m);
+      const float inv = 1.0f / fmaf(wa, l, wb * l_b);
+      const float ca = wa * inv, cb = wb * inv;
+      __nv_bfloat16* orow = p.out + (size_t)b * p.out_batch_stride + (size_t)q_row * p.out_ld + p.out_col0 + head * p.dp;
+      for (int c = 0; c < dchunks; ++c) {
+        uint32_t ra[16], rb[16];
+        tmem_ld_32x32b_x16(tO + (uint32_t)(c * 16), ra);
+        tmem_ld_32x32b_x16(tO + (uint32_t)(p.dp + c * 16), rb);
+        tmem_ld_wait();
+        if (q_row < p.Sq) {
+          uint32_t w[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            w[i] = pack_bf16x2(fmaf(__uint_as_float(ra[2 * i]), ca, __uint_as_float(rb[2 * i]) * cb),
+                               fmaf(__uint_as_float(ra[2 * i + 1]), ca, __uint_as_float(rb[2 * i + 1]) * cb));
+          *reinterpret_cast<uint4*>(orow + c * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+          *reinterpret_cast<uint4*>(orow + c * 16 + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
 }  // namespace dfb
 
 using namespace dfb;
@@ -722,7 +1003,12 @@ extern "C" int dfb_attention(const dfb_attn_params* a, void* stream_) {
   kp.out = (__nv_bfloat16*)a->out;
   kp.out_ld = a->out_ld; kp.out_col0 = a->out_col0;
   kp.out_batch_stride = (long long)a->Sq * a->out_ld;
-  uint32_t need_cols = (uint32_t)((use_db ? 2 : 1) * bkv + a->dp), cols = 32;
+  // split-KV kernel (8 softmax warps, two independent halves; dp <= 64): measured 5 % SLOWER than the 4-softmax-warp
+  // double-buffered kernel (1836 vs 1744 cycles per 128x128 tile per SM, profiles/r01_attention_experiments.md) — more
+  // warps do not help because the tile time is set by the MUFU and the TMEM read port, not by issue latency.  Kept
+  // behind dbg_flags bit5 with its parity tests as the record of that experiment.
+  const bool use_split = use_db && bkv == 64 && a->dp <= 64 && (a->dbg_flags & 16) == 0 && (a->dbg_flags & 32) != 0;
+  uint32_t need_cols = (uint32_t)((use_db ? 2 : 1) * bkv + (use_split ? 2 : 1) * a->dp), cols = 32;
   while (cols < need_cols) cols <<= 1;
   DFB_REQUIRE(cols <= 512, "dfb_attention: block_kv + dp exceeds TMEM");
   kp.tmem_cols = cols;
@@ -759,7 +1045,8 @@ extern "C" int dfb_attention(const dfb_attn_params* a, void* stream_) {
   size_t smem;
   if (use_db) {
     // 3 K/V stages when two CTAs still fit per SM with them, else 2
-    const size_t fixed = 1024 + (size_t)dch * ATT_BLOCK_Q * 32 + (p_tmem ? 0 : 2 * (size_t)(bkv / 16) * ATT_BLOCK_Q * 32) + 256;
+    const size_t fixed = 1024 + (size_t)dch * ATT_BLOCK_Q * 32 + (p_tmem ? 0 : 2 * (size_t)(bkv / 16) * ATT_BLOCK_Q * 32) + 256 +
+                         (use_split ? (size_t)ATT_BLOCK_Q * 8 : 0);
     const size_t stage = (size_t)2 * dch * bkv * 32;
     kp.kv_stages = (fixed + 3 * stage + 1024 <= (size_t)113 * 1024 || fixed + 2 * stage + 1024 > (size_t)113 * 1024) ? 3 : 2;
     smem = fixed + (size_t)kp.kv_stages * stage;
@@ -780,10 +1067,13 @@ extern "C" int dfb_attention(const dfb_attn_params* a, void* stream_) {
     DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_db_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_db_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_db_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     attr_set[dev] = true;
   }
   dim3 grid((a->Sq + ATT_BLOCK_Q - 1) / ATT_BLOCK_Q, a->heads, a->B);
-  if (use_db && bkv == 64 && p_tmem)
+  if (use_split)
+    attn_fwd_split_kernel<<<grid, ATT_SPLIT_THREADS, smem, stream>>>(maps, kp);
+  else if (use_db && bkv == 64 && p_tmem)
     attn_fwd_db_kernel<64, true><<<grid, ATT_THREADS, smem, stream>>>(maps, kp);
   else if (use_db && bkv == 64)
     attn_fwd_db_kernel<64, false><<<grid, ATT_THREADS, smem, stream>>>(maps, kp);

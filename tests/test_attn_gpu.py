@@ -29,6 +29,8 @@ CASES = [
     (2, 8, 4096, 4096, 40), (2, 8, 1024, 1024, 80), (2, 8, 256, 256, 160), (3, 8, 64, 64, 160),
     (2, 8, 4096, 77, 40), (2, 8, 1024, 77, 80), (2, 8, 256, 77, 160), (2, 8, 64, 85, 160),
     (2, 2, 16, 16, 32), (3, 2, 4, 4, 64), (3, 2, 256, 77, 32), (1, 1, 200, 300, 16),
+    # dp <= 64 with more than one 64-key tile: ragged tails of 1 / 12 / 33 / 63 keys, dp = 64
+    (1, 2, 130, 97, 32), (2, 3, 256, 160, 64), (1, 2, 100, 225, 40), (2, 2, 300, 127, 48), (1, 4, 128, 65, 40),
 ]
 
 
@@ -73,9 +75,11 @@ def test_attention_fused_qkv_layout_and_large_logits():
 
 
 @pytest.mark.parametrize("B,H,Sq,Skv,d,bkv", [(2, 8, 1024, 1024, 40, 64), (2, 8, 512, 512, 40, 128), (1, 1, 200, 300, 16, 64),
-                                               (2, 8, 256, 256, 160, 64), (2, 4, 384, 1000, 80, 64)])
+                                               (2, 8, 256, 256, 160, 64), (2, 4, 384, 1000, 80, 64), (1, 2, 130, 97, 32),
+                                               (2, 3, 256, 160, 64), (2, 2, 300, 127, 48), (1, 4, 128, 65, 40)])
 def test_attention_variants_smem_p_and_single_buffer(B, H, Sq, Skv, d, bkv):
-    """Non-default variants behind the tuning hooks: P through shared memory (bit4) and the single-buffer kernel (bit3)."""
+    """Non-default variants behind the tuning hooks: P through shared memory (bit4), the single-buffer kernel (bit3)
+    and the split-KV kernel with eight softmax warps (bit5)."""
     from difashion_b200 import ops
     g = torch.Generator().manual_seed(Sq + Skv + d)
     q = torch.randn(B, Sq, H * d, generator=g).bfloat16().cuda()
@@ -85,7 +89,7 @@ def test_attention_variants_smem_p_and_single_buffer(B, H, Sq, Skv, d, bkv):
     qp, kp, vp = (_pad_heads(t, H, d, dp).contiguous() for t in (q, k, v))
     out = torch.full((B, Sq, H * dp), float("nan"), dtype=torch.bfloat16, device="cuda")
     ref = _ref(q, k, v, H, d, d ** -0.5)
-    for flags in (16, 8):
+    for flags in (16, 8, 32):            # 32: the experimental split-KV kernel (8 softmax warps) where dp <= 64
         out.fill_(float("nan"))
         ops.attention(qp, kp, vp, out, heads=H, dp=dp, scale=d ** -0.5, block_kv=bkv, dbg_flags=flags)
         torch.cuda.synchronize()

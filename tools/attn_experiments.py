@@ -15,7 +15,7 @@ def run(flags, bkv=0, reps=5):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
 tiles = B * 8 * 32 * 32 / 148
-for name, flags, bkv in [("double-buffer KV=64 (smem P)", 16, 64), ("double-buffer KV=64, P in TMEM (default)", 0, 64),
+for name, flags, bkv in [("split-KV, 8 softmax warps (experiment)", 32, 64), ("double-buffer KV=64 (smem P)", 16, 64), ("double-buffer KV=64, P in TMEM (default)", 0, 64),
                          ("double-buffer KV=128 (smem P, 1 CTA/SM)", 16, 128), ("double-buffer KV=128, P in TMEM (1 CTA/SM)", 0, 128)]:
     ms = run(flags, bkv)
     print(f"{name:44s} {ms:8.3f} ms -> {ms * 1e-3 * 1.9e9 / tiles:7.0f} cycles per 128x128 tile per SM (@1.9GHz)")
