@@ -41,6 +41,7 @@ struct AttnKernelParams {
   uint32_t v_lbo, v_sbo;          // MN-major V descriptor strides (bytes)
   long long* timeline;            // tuning hook: clock64 stamps of the first softmax thread of CTA (0,0,0)
   int kv_stages;                  // K/V ring depth of the double-buffered kernel (2 or 3)
+  int q_tiles;                    // query tiles per CTA of the short-KV kernel
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -968,6 +969,233 @@ attn_fwd_split_kernel(const __grid_constant__ AttnMaps maps, const __grid_consta
   }
 }
 
+
+// =================================================================================================
+// Short-KV kernel: the cross-attention layers (S_kv = 77 / 85 text tokens: ONE key tile, block_kv = S_kv rounded up
+// to 16).  The generic single-buffer kernel above is latency-bound here (ncu: tensor 7 %, DRAM 13 %): every CTA pays
+// TMEM allocation, barrier init, descriptor fetches and the K/V load for 128 queries' worth of work.  This kernel
+// keeps K/V resident and streams `q_tiles` consecutive 128-row query tiles of one (batch, head) through a
+// software pipeline:
+//   TMA warp     : K/V once; Q tiles through a 2-slot ring
+//   MMA warp     : S[i&1] = Q_i K^T (issued one tile ahead);  O[i&1] = P_i V   (P from tensor memory, TS form)
+//   softmax warps: tile i: two passes over S[i&1] in TMEM (max, then exponentials; P over the score columns),
+//                  then the epilogue of tile i-1 (O[(i-1)&1] / l -> bf16) while PV_i runs.
+// TMEM columns: S[0], S[1] (block_kv each), O[0], O[1] (dp each).
+// =================================================================================================
+// (Holding the 80-column score row in registers — one TMEM pass instead of two — measured 4 % slower: 0.284 vs 0.272 ms
+// at B=128; the two-pass form is kept.)
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attn_short_kv_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnKernelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int dchunks = p.dp >> 4;
+  const int bkv = p.block_kv;
+  const uint32_t q_bytes = (uint32_t)dchunks * ATT_BLOCK_Q * 32u;
+  const uint32_t kv_chunk_bytes = (uint32_t)bkv * 32u;
+  const uint32_t kv_tile_bytes = (uint32_t)dchunks * kv_chunk_bytes;
+  const uint32_t sQ = smem_base;                          // Q ring: 2 slots
+  const uint32_t sK = sQ + 2 * q_bytes;
+  const uint32_t sV = sK + kv_tile_bytes;
+  const uint32_t bar_base = sV + kv_tile_bytes;
+  const uint32_t kv_full = bar_base;
+  auto q_full = [&](int i) { return bar_base + 8u + 8u * i; };
+  auto q_empty = [&](int i) { return bar_base + 24u + 8u * i; };
+  auto s_full = [&](int i) { return bar_base + 40u + 8u * i; };
+  auto p_full = [&](int i) { return bar_base + 56u + 8u * i; };
+  auto o_full = [&](int i) { return bar_base + 72u + 8u * i; };
+  auto o_empty = [&](int i) { return bar_base + 88u + 8u * i; };
+  const uint32_t tmem_ptr_smem = bar_base + 104u;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int n_qtiles = (p.Sq + ATT_BLOCK_Q - 1) / ATT_BLOCK_Q;
+  const int qt0 = blockIdx.x * p.q_tiles;
+  const int nt = min(p.q_tiles, n_qtiles - qt0);          // query tiles of this CTA (>= 1)
+  constexpr int W_TMA = 4, W_MMA = 5;
+
+  if (warp == W_TMA && lane == 0) {
+    tma_prefetch_desc(&maps.q);
+    tma_prefetch_desc(&maps.k);
+    tma_prefetch_desc(&maps.v);
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(q_full(i), 1);
+      mbar_init(q_empty(i), 1);
+      mbar_init(s_full(i), 1);
+      mbar_init(p_full(i), 128);
+      mbar_init(o_full(i), 1);
+      mbar_init(o_empty(i), 128);
+    }
+    fence_mbar_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == W_MMA) tmem_alloc(tmem_ptr_smem, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+  const uint32_t tmem_O0 = tmem_base + 2u * (uint32_t)bkv;
+
+  if (warp == W_TMA) {
+    // ---------------- TMA producer ----------------
+    if (elect_one()) {
+      mbar_expect_tx(kv_full, 2 * kv_tile_bytes);
+      for (int c = 0; c < dchunks; ++c)
+        tma_load_3d(&maps.k, sK + (uint32_t)c * kv_chunk_bytes, kv_full, p.k_col0 + head * p.dp + c * 16, 0, b);
+      for (int c = 0; c < dchunks; ++c)
+        tma_load_3d(&maps.v, sV + (uint32_t)c * kv_chunk_bytes, kv_full, p.v_col0 + head * p.dp + c * 16, 0, b);
+    }
+    __syncwarp();
+    for (int i = 0; i < nt; ++i) {
+      const int sl = i & 1;
+      mbar_wait(q_empty(sl), ((uint32_t)(i >> 1) & 1u) ^ 1u);
+      if (elect_one()) {
+        mbar_expect_tx(q_full(sl), q_bytes);
+        for (int c = 0; c < dchunks; ++c)
+          tma_load_3d(&maps.q, sQ + (uint32_t)sl * q_bytes + (uint32_t)c * ATT_BLOCK_Q * 32u, q_full(sl),
+                      p.q_col0 + head * p.dp + c * 16, (qt0 + i) * ATT_BLOCK_Q, b);
+      }
+      __syncwarp();
+    }
+  } else if (warp == W_MMA) {
+    // ---------------- MMA issuer ----------------
+    const uint32_t idesc_qk = make_idesc_f16(ATT_BLOCK_Q, (uint32_t)bkv, true, 0, 0);
+    const uint32_t idesc_pv = make_idesc_f16(ATT_BLOCK_Q, (uint32_t)p.dp, true, 0, 1);
+    const uint64_t desc_q0 = make_smem_desc(sQ, 16, 256, SWZ_32B);
+    const uint64_t desc_k0 = make_smem_desc(sK, 16, 256, SWZ_32B);
+    const uint64_t desc_v0 = make_smem_desc(sV, kv_chunk_bytes, 256, SWZ_32B);
+    const int pv_steps = bkv >> 4;
+    auto issue_qk = [&](int i) {                  // S[i & 1] = Q_i K^T
+      const int sl = i & 1;
+      mbar_wait(q_full(sl), (uint32_t)(i >> 1) & 1u);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t dq = desc_q0 + (uint64_t)((uint32_t)sl * (q_bytes >> 4));
+        for (int c = 0; c < dchunks; ++c)
+          umma_f16_ss(tmem_base + (uint32_t)(sl * bkv), dq + (uint64_t)(c * (ATT_BLOCK_Q * 32 / 16)),
+                      desc_k0 + (uint64_t)((uint32_t)c * (kv_chunk_bytes >> 4)), idesc_qk, c != 0);
+        umma_commit(s_full(sl));
+        umma_commit(q_empty(sl));
+      }
+      __syncwarp();
+    };
+    mbar_wait(kv_full, 0);
+    issue_qk(0);
+    for (int i = 0; i < nt; ++i) {
+      const int sl = i & 1;
+      if (i + 1 < nt) issue_qk(i + 1);            // S[(i+1)&1] was last read by PV_{i-1}, issued earlier (in-order pipe)
+      mbar_wait(p_full(sl), (uint32_t)(i >> 1) & 1u);
+      if (i >= 2) mbar_wait(o_empty(sl), (uint32_t)((i >> 1) - 1) & 1u);   // epilogue of tile i-2 has drained O[sl]
+      tc_fence_after();
+      if (elect_one()) {
+        for (int k = 0; k < pv_steps; ++k)
+          umma_f16_ts(tmem_O0 + (uint32_t)(sl * p.dp), tmem_base + (uint32_t)(sl * bkv) + (uint32_t)(8 * k),
+                      desc_v0 + (uint64_t)(k * (512 / 16)), idesc_pv, k != 0);
+        umma_commit(o_full(sl));
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---------------- softmax + epilogue warps ----------------
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const int kv_chunks = bkv >> 4;
+    float l_prev = 1.f;
+    auto epilogue = [&](int i, float l) {         // O[i & 1] / l -> bf16 rows of query tile qt0 + i
+      const int sl = i & 1;
+      mbar_wait(o_full(sl), (uint32_t)(i >> 1) & 1u);
+      tc_fence_after();
+      const float inv_l = 1.0f / l;
+      const int q_row = (qt0 + i) * ATT_BLOCK_Q + row;
+      __nv_bfloat16* orow = p.out + (size_t)b * p.out_batch_stride + (size_t)q_row * p.out_ld + p.out_col0 + head * p.dp;
+      for (int c = 0; c < dchunks; ++c) {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(tmem_O0 + (uint32_t)(sl * p.dp) + lane_addr + (uint32_t)(c * 16), r);
+        tmem_ld_wait();
+        if (q_row < p.Sq) {
+          uint32_t w[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) w[k] = pack_bf16x2(__uint_as_float(r[2 * k]) * inv_l, __uint_as_float(r[2 * k + 1]) * inv_l);
+          *reinterpret_cast<uint4*>(orow + c * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+          *reinterpret_cast<uint4*>(orow + c * 16 + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(o_empty(sl));
+    };
+    for (int i = 0; i < nt; ++i) {
+      const int sl = i & 1;
+      const uint32_t tS = tmem_base + (uint32_t)(sl * bkv) + lane_addr;
+      mbar_wait(s_full(sl), (uint32_t)(i >> 1) & 1u);
+      tc_fence_after();
+      float l = 0.f;
+      {
+        // only the last chunk can hold columns >= Skv: the others run without the per-element mask
+        const int nfull = p.Skv >> 4;
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        for (int c = 0; c < kv_chunks; ++c) {
+          uint32_t r[16];
+          tmem_ld_32x32b_x16(tS + (uint32_t)(c * 16), r);
+          tmem_ld_wait();
+          if (c < nfull) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) m4[k & 3] = fmaxf(m4[k & 3], __uint_as_float(r[k]));
+          } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+              if (c * 16 + k < p.Skv) m4[k & 3] = fmaxf(m4[k & 3], __uint_as_float(r[k]));
+          }
+        }
+        const float m2 = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * p.scale_log2;
+        float l4[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int c = 0; c < kv_chunks; ++c) {
+          uint32_t r[16], w[8];
+          tmem_ld_32x32b_x16(tS + (uint32_t)(c * 16), r);
+          tmem_ld_wait();
+          float pv[16];
+          if (c < nfull) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              pv[k] = ex2f(fmaf(__uint_as_float(r[k]), p.scale_log2, -m2));
+              l4[k & 3] += pv[k];
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              const float e = ex2f(fmaf(__uint_as_float(r[k]), p.scale_log2, -m2));
+              pv[k] = (c * 16 + k < p.Skv) ? e : 0.f;
+              l4[k & 3] += pv[k];
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) w[k] = pack_bf16x2(pv[2 * k], pv[2 * k + 1]);
+          // P chunk c (16 bf16 = 8 columns) over score columns [8c, 8c+8): already consumed (8c + 8 <= 16c for c >= 1,
+          // and chunk 0 sits in registers)
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(tS + (uint32_t)(c * 8)),
+                       "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+        }
+        l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(p_full(sl));
+      if (i >= 1) epilogue(i - 1, l_prev);        // overlaps PV_i
+      l_prev = l;
+    }
+    epilogue(nt - 1, l_prev);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
 }  // namespace dfb
 
 using namespace dfb;
@@ -1008,7 +1236,10 @@ extern "C" int dfb_attention(const dfb_attn_params* a, void* stream_) {
   // warps do not help because the tile time is set by the MUFU and the TMEM read port, not by issue latency.  Kept
   // behind dbg_flags bit5 with its parity tests as the record of that experiment.
   const bool use_split = use_db && bkv == 64 && a->dp <= 64 && (a->dbg_flags & 16) == 0 && (a->dbg_flags & 32) != 0;
-  uint32_t need_cols = (uint32_t)((use_db ? 2 : 1) * bkv + (use_split ? 2 : 1) * a->dp), cols = 32;
+  // short-KV kernel (one key tile, K/V resident, query tiles streamed): cross-attention.  dbg_flags bit6 disables it.
+  const bool use_short = !use_db && a->Skv <= bkv && 2 * (bkv + a->dp) <= 512 && a->Sq > ATT_BLOCK_Q && (a->dbg_flags & (8 | 64)) == 0;
+  uint32_t need_cols = use_short ? (uint32_t)(2 * (bkv + a->dp))
+                                 : (uint32_t)((use_db ? 2 : 1) * bkv + (use_split ? 2 : 1) * a->dp), cols = 32;
   while (cols < need_cols) cols <<= 1;
   DFB_REQUIRE(cols <= 512, "dfb_attention: block_kv + dp exceeds TMEM");
   kp.tmem_cols = cols;
@@ -1053,6 +1284,15 @@ extern "C" int dfb_attention(const dfb_attn_params* a, void* stream_) {
   } else {
     smem = 1024 + (size_t)dch * ATT_BLOCK_Q * 32 + (size_t)(bkv / 16) * ATT_BLOCK_Q * 32 + (size_t)ATT_STAGES * 2 * dch * bkv * 32 + 128;
   }
+  const int n_qtiles = (a->Sq + ATT_BLOCK_Q - 1) / ATT_BLOCK_Q;
+  if (use_short) {
+    smem = 1024 + 2 * (size_t)dch * ATT_BLOCK_Q * 32 + (size_t)2 * dch * bkv * 32 + 256;
+    // query tiles per CTA: amortise the per-CTA set-up, but keep >= ~4 CTAs per SM slot for load balance
+    int qtiles = 8;
+    while (qtiles > 1 && (long long)((n_qtiles + qtiles - 1) / qtiles) * a->heads * a->B < 8LL * num_sms()) qtiles >>= 1;
+    if ((a->dbg_flags >> 8) & 0xF) qtiles = (a->dbg_flags >> 8) & 0xF;      // test hook: forced tile count per CTA
+    kp.q_tiles = qtiles;
+  }
   if ((a->dbg_flags & 2) && smem < 120 * 1024) smem = 120 * 1024;      // tuning hook: force one CTA per SM
   DFB_REQUIRE(smem <= 227 * 1024, "dfb_attention: tile configuration exceeds shared memory");
   static bool attr_set[64] = {false};
@@ -1068,10 +1308,14 @@ extern "C" int dfb_attention(const dfb_attn_params* a, void* stream_) {
     DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_db_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_db_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_short_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     attr_set[dev] = true;
   }
   dim3 grid((a->Sq + ATT_BLOCK_Q - 1) / ATT_BLOCK_Q, a->heads, a->B);
-  if (use_split)
+  if (use_short) {
+    dim3 gshort((n_qtiles + kp.q_tiles - 1) / kp.q_tiles, a->heads, a->B);
+    attn_short_kv_kernel<<<gshort, ATT_THREADS, smem, stream>>>(maps, kp);
+  } else if (use_split)
     attn_fwd_split_kernel<<<grid, ATT_SPLIT_THREADS, smem, stream>>>(maps, kp);
   else if (use_db && bkv == 64 && p_tmem)
     attn_fwd_db_kernel<64, true><<<grid, ATT_THREADS, smem, stream>>>(maps, kp);

@@ -75,8 +75,8 @@ def test_attention_fused_qkv_layout_and_large_logits():
 
 
 @pytest.mark.parametrize("B,H,Sq,Skv,d,bkv", [(2, 8, 1024, 1024, 40, 64), (2, 8, 512, 512, 40, 128), (1, 1, 200, 300, 16, 64),
-                                               (2, 8, 256, 256, 160, 64), (2, 4, 384, 1000, 80, 64), (1, 2, 130, 97, 32),
-                                               (2, 3, 256, 160, 64), (2, 2, 300, 127, 48), (1, 4, 128, 65, 40)])
+                                               (2, 8, 256, 256, 160, 64), (2, 4, 384, 1000, 80, 64), (1, 2, 130, 97, 32, 64),
+                                               (2, 3, 256, 160, 64, 64), (2, 2, 300, 127, 48, 64), (1, 4, 128, 65, 40, 64)])
 def test_attention_variants_smem_p_and_single_buffer(B, H, Sq, Skv, d, bkv):
     """Non-default variants behind the tuning hooks: P through shared memory (bit4), the single-buffer kernel (bit3)
     and the split-KV kernel with eight softmax warps (bit5)."""
@@ -95,3 +95,26 @@ def test_attention_variants_smem_p_and_single_buffer(B, H, Sq, Skv, d, bkv):
         torch.cuda.synchronize()
         got = out.reshape(B, Sq, H, dp)[..., :d].reshape(B, Sq, H * d)
         assert rel_l2(got, ref) < 1e-2, err_report(got.reshape(-1, H * d), ref.reshape(-1, H * d), f"attn flags={flags}")
+
+
+@pytest.mark.parametrize("B,H,Sq,Skv,d", [(2, 8, 4096, 77, 40), (3, 4, 1000, 85, 80), (1, 2, 640, 33, 32), (2, 2, 300, 128, 64)])
+def test_cross_attention_short_kv_kernel_streams_query_tiles(B, H, Sq, Skv, d):
+    """Short-KV kernel (K/V resident, query tiles streamed through the S/O double buffers): 1, 3 and 8 tiles per CTA
+    (3 does not divide the tile count: ragged last CTA), ragged last query tile, and the generic kernel (bit6) as control."""
+    from difashion_b200 import ops
+    g = torch.Generator().manual_seed(Sq + Skv + d)
+    q = torch.randn(B, Sq, H * d, generator=g).bfloat16().cuda()
+    k = (1.5 * torch.randn(B, Skv, H * d, generator=g)).bfloat16().cuda()
+    v = torch.randn(B, Skv, H * d, generator=g).bfloat16().cuda()
+    dp = ops.pad16(d)
+    qp, kp, vp = (_pad_heads(t, H, d, dp).contiguous() for t in (q, k, v))
+    ref = _ref(q, k, v, H, d, d ** -0.5)
+    outs = []
+    for flags in (1 << 8, 3 << 8, 8 << 8, 64):
+        out = torch.full((B, Sq, H * dp), float("nan"), dtype=torch.bfloat16, device="cuda")
+        ops.attention(qp, kp, vp, out, heads=H, dp=dp, scale=d ** -0.5, dbg_flags=flags)
+        torch.cuda.synchronize()
+        got = out.reshape(B, Sq, H, dp)[..., :d].reshape(B, Sq, H * d)
+        assert rel_l2(got, ref) < 1e-2, err_report(got.reshape(-1, H * d), ref.reshape(-1, H * d), f"short-kv flags={flags}")
+        outs.append(out.reshape(B, Sq, H, dp)[..., :d].clone())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])      # tiles per CTA must not change a bit

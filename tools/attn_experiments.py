@@ -28,3 +28,21 @@ print("double-buffer KV=64 P-in-TMEM, 2 CTA/SM: softmax thread of CTA(0,0,0): ti
 for j in range(8, 20):
     r = [t[j * 8 + k] - base for k in range(4)]
     print(f"   {j:2d} | " + "  ".join(f"{v:7d}" for v in r) + f"   (wait {r[1]-r[0]}, math {r[2]-r[1]}, fence+arrive {r[3]-r[2]})")
+# ---- cross-attention (S_kv = 77): generic single-tile kernel vs the short-KV kernel that streams query tiles ----
+Bx = int(os.environ.get("BX", "128"))
+q = torch.randn(Bx, 4096, 384, generator=g).bfloat16().cuda()
+kv = torch.randn(Bx, 77, 768, generator=g).bfloat16().cuda()
+ox = torch.empty(Bx, 4096, 384, dtype=torch.bfloat16, device="cuda")
+def runx(flags, reps=5):
+    f = lambda: ops.attention(q, kv[..., :384], kv[..., 384:], ox, heads=8, dp=48, scale=40 ** -0.5, dbg_flags=flags)
+    f(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): f()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+gb = (2 * q.numel() * 2 + kv.numel() * 2) / 1e9
+for name, flags in [("generic single-tile kernel (one CTA per 128 queries)", 64), ("short-KV, 1 tile/CTA", 1 << 8), ("short-KV, 2 tiles/CTA", 2 << 8),
+                    ("short-KV, 4 tiles/CTA", 4 << 8), ("short-KV, 8 tiles/CTA (default)", 0), ("short-KV, 15 tiles/CTA", 15 << 8)]:
+    ms = runx(flags)
+    print(f"cross-attn B={Bx} {name:56s} {ms:8.3f} ms  ({gb / ms * 1e3 / 1e3:6.2f} TB/s of Q+O+KV bytes)")
