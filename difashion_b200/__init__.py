@@ -2,7 +2,8 @@
 
 Public surface (mirrors what ``DiFashion/models/difashion.py`` consumes from diffusers):
 ``B200UNet2DConditionModel``, ``B200AttnProcessor``, ``B200DDIMScheduler``, ``B200PNDMScheduler``,
-``MutualEncoder``, ``B200DiFashionPipeline``, ``B200AutoencoderKL`` (decode half: the step after the loop).  All arithmetic runs in ``libdfb200.so`` (hand-written CUDA,
+``MutualEncoder``, ``B200DiFashionPipeline`` (the loop), and the stages around it: ``B200AutoencoderKL`` (encode / decode),
+``B200CLIPTextModel``, ``B200DiFashion.fashion_generation`` (the whole reference method), ``save_batch_outputs``.  All arithmetic runs in ``libdfb200.so`` (hand-written CUDA,
 C ABI in ``include/dfb200.h``); importing this package never imports the test oracle.
 """
 from .attention import Attention, B200AttnProcessor  # noqa: F401
@@ -11,7 +12,11 @@ from .pipeline import B200DiFashionPipeline, guidance_plan, mutual_index_table, 
 from .schedulers import B200DDIMScheduler, B200PNDMScheduler  # noqa: F401
 from .unet import B200UNet2DConditionModel, UNet2DConditionOutput  # noqa: F401
 from .vae import B200AutoencoderKL, DecoderOutput  # noqa: F401
+from .clip import B200CLIPTextModel  # noqa: F401
+from .generation import B200DiFashion  # noqa: F401
+from .outputs import merge_and_save_images, save_batch_outputs, save_outputs_npy  # noqa: F401
 
 __all__ = ["B200UNet2DConditionModel", "UNet2DConditionOutput", "B200AttnProcessor", "Attention", "B200DDIMScheduler",
            "B200PNDMScheduler", "MutualEncoder", "B200DiFashionPipeline", "guidance_plan", "mutual_index_table",
-           "shard_outfits", "B200AutoencoderKL", "DecoderOutput"]
+           "shard_outfits", "B200AutoencoderKL", "DecoderOutput", "B200CLIPTextModel", "B200DiFashion",
+           "save_batch_outputs", "merge_and_save_images", "save_outputs_npy"]

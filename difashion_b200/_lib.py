@@ -64,6 +64,7 @@ class AttnParams(C.Structure):
         ("dbg_v_lbo", C.c_int32), ("dbg_v_sbo", C.c_int32),
         ("dbg_flags", C.c_int32),
         ("dbg_timeline", C.c_void_p),
+        ("causal", C.c_int32),
     ]
 
 
@@ -110,6 +111,9 @@ _PROTOTYPES = {
     "dfb_space_to_depth": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "dfb_timestep_embedding": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                          C.c_void_p]),
+    "dfb_embed_tokens": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_void_p]),
+    "dfb_image_to_uint8": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p]),
 }
 
 

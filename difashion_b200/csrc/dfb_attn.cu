@@ -42,6 +42,7 @@ struct AttnKernelParams {
   long long* timeline;            // tuning hook: clock64 stamps of the first softmax thread of CTA (0,0,0)
   int kv_stages;                  // K/V ring depth of the double-buffered kernel (2 or 3)
   int q_tiles;                    // query tiles per CTA of the short-KV kernel
+  int causal;                     // key j visible to query i only when j <= i (generic single-buffer kernel only)
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -288,6 +289,8 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ A
           l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
         }
       } else {
+      // causal (CLIP text encoder): this row sees keys j*block_kv + i <= q_row only
+      const int kv_lim = p.causal ? min(kv_valid, q_row - j * p.block_kv + 1) : kv_valid;
       float mx = -INFINITY;
       for (int c = 0; c < kv_chunks; ++c) {
         uint32_t r[16];
@@ -295,7 +298,7 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ A
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-          if (c * 16 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+          if (c * 16 + i < kv_lim) mx = fmaxf(mx, __uint_as_float(r[i]));
       }
       mx *= p.scale_log2;
       const bool need = mx > m_ref + 8.0f;
@@ -329,7 +332,7 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ A
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float e = ex2f(__uint_as_float(r[i]) * p.scale_log2 - m_ref);
-          pv[i] = (c * 16 + i < kv_valid) ? e : 0.f;
+          pv[i] = (c * 16 + i < kv_lim) ? e : 0.f;
           l += pv[i];
         }
         const uint32_t dst = p_row + (uint32_t)c * ATT_BLOCK_Q * 32u;
@@ -1221,7 +1224,9 @@ extern "C" int dfb_attention(const dfb_attn_params* a, void* stream_) {
   DFB_REQUIRE(bkv % 16 == 0 && bkv >= 16 && bkv <= 128, "dfb_attention: block_kv must be a multiple of 16 in [16,128]");
   // kernel family: the double-buffered kernel for multi-tile KV (self-attention), the single-buffer kernel for
   // one-tile / odd-sized KV (cross-attention, tiny shapes).  dbg_flags bit3 forces the single-buffer family.
-  bool use_db = !(a->dbg_flags & 8) && (bkv == 64 || bkv == 128) && a->Skv > bkv;
+  DFB_REQUIRE(a->causal == 0 || a->Sq == a->Skv, "dfb_attention: causal needs Sq == Skv");
+  const bool causal = a->causal != 0;                              // generic single-buffer kernel only
+  bool use_db = !causal && !(a->dbg_flags & 8) && (bkv == 64 || bkv == 128) && a->Skv > bkv;
   if (use_db && a->block_kv <= 0) bkv = 64;                       // default tile of the double-buffered kernel
   if (use_db && bkv == 128 && 2 * 128 + a->dp > 512) use_db = false;
   kp.Sq = a->Sq; kp.Skv = a->Skv; kp.dp = a->dp; kp.block_kv = bkv;
@@ -1237,7 +1242,7 @@ extern "C" int dfb_attention(const dfb_attn_params* a, void* stream_) {
   // behind dbg_flags bit5 with its parity tests as the record of that experiment.
   const bool use_split = use_db && bkv == 64 && a->dp <= 64 && (a->dbg_flags & 16) == 0 && (a->dbg_flags & 32) != 0;
   // short-KV kernel (one key tile, K/V resident, query tiles streamed): cross-attention.  dbg_flags bit6 disables it.
-  const bool use_short = !use_db && a->Skv <= bkv && 2 * (bkv + a->dp) <= 512 && a->Sq > ATT_BLOCK_Q && (a->dbg_flags & (8 | 64)) == 0;
+  const bool use_short = !causal && !use_db && a->Skv <= bkv && 2 * (bkv + a->dp) <= 512 && a->Sq > ATT_BLOCK_Q && (a->dbg_flags & (8 | 64)) == 0;
   uint32_t need_cols = use_short ? (uint32_t)(2 * (bkv + a->dp))
                                  : (uint32_t)((use_db ? 2 : 1) * bkv + (use_split ? 2 : 1) * a->dp), cols = 32;
   while (cols < need_cols) cols <<= 1;
@@ -1246,6 +1251,7 @@ extern "C" int dfb_attention(const dfb_attn_params* a, void* stream_) {
   kp.v_lbo = a->dbg_v_lbo > 0 ? (uint32_t)a->dbg_v_lbo : (uint32_t)bkv * 32u;
   kp.v_sbo = a->dbg_v_sbo > 0 ? (uint32_t)a->dbg_v_sbo : 256u;
   kp.timeline = (long long*)a->dbg_timeline;
+  kp.causal = causal ? 1 : 0;
 
   AttnMaps maps;
   memset(&maps, 0, sizeof(maps));
@@ -1325,9 +1331,9 @@ extern "C" int dfb_attention(const dfb_attn_params* a, void* stream_) {
     attn_fwd_db_kernel<128, true><<<grid, ATT_THREADS, smem, stream>>>(maps, kp);
   else if (use_db)
     attn_fwd_db_kernel<128, false><<<grid, ATT_THREADS, smem, stream>>>(maps, kp);
-  else if (bkv == 128)
+  else if (bkv == 128 && !causal)
     attn_fwd_kernel<128><<<grid, ATT_THREADS, smem, stream>>>(maps, kp);
-  else if (bkv == 64)
+  else if (bkv == 64 && !causal)
     attn_fwd_kernel<64><<<grid, ATT_THREADS, smem, stream>>>(maps, kp);
   else
     attn_fwd_kernel<0><<<grid, ATT_THREADS, smem, stream>>>(maps, kp);

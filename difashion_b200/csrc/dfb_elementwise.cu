@@ -286,6 +286,37 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, TOut* __r
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// CLIPTextEmbeddings: token-table gather + position embedding (float4 per thread, fp32 residual stream out)
+// ---------------------------------------------------------------------------------------------
+__global__ void embed_tokens_kernel(const int32_t* __restrict__ ids, const float* __restrict__ tok, const float* __restrict__ pos,
+                                    float* __restrict__ out, int rows, int S, int D4, int vocab) {
+  const long long total = (long long)rows * D4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / D4), c = (int)(i - (long long)r * D4);
+    int id = ids[r];
+    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);       // ids are validated on the host; never read out of the table
+    const float4 a = __ldg(reinterpret_cast<const float4*>(tok) + (size_t)id * D4 + c);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(pos) + (size_t)(r % S) * D4 + c);
+    reinterpret_cast<float4*>(out)[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// VaeImageProcessor.postprocess (denormalize + uint8): fp32 NHWC [pixels, in_c] -> uint8 [pixels, 3]
+// ---------------------------------------------------------------------------------------------
+__global__ void image_to_uint8_kernel(const float* __restrict__ in, int in_c, uint8_t* __restrict__ out, long long pixels) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < pixels; i += (long long)gridDim.x * blockDim.x) {
+    const float* src = in + i * in_c;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float v = src[c] * 0.5f + 0.5f;                        // (image / 2 + 0.5).clamp(0, 1)
+      v = fminf(fmaxf(v, 0.f), 1.f);
+      out[i * 3 + c] = (uint8_t)rintf(v * 255.f);            // (x * 255).round().astype("uint8"): half to even
+    }
+  }
+}
+
 }  // namespace dfb
 
 using namespace dfb;
@@ -414,6 +445,24 @@ int dfb_timestep_embedding(const float* t, void* out, int out_dtype, int B, int 
     timestep_embedding_kernel<float><<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(t, (float*)out, B, dim, flip_sin_to_cos, freq_shift);
   else
     timestep_embedding_kernel<__nv_bfloat16><<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(t, (__nv_bfloat16*)out, B, dim, flip_sin_to_cos, freq_shift);
+  DFB_CHECK_CUDA(cudaGetLastError());
+  return DFB_OK;
+}
+
+int dfb_embed_tokens(const int32_t* ids, const float* token_table, const float* position_table, float* out, int B, int S,
+                     int D, int vocab, void* stream) {
+  DFB_REQUIRE(ids && token_table && position_table && out, "dfb_embed_tokens: null buffer");
+  DFB_REQUIRE(B > 0 && S > 0 && D > 0 && D % 4 == 0 && vocab > 0, "dfb_embed_tokens: bad shape (D must be a multiple of 4)");
+  DFB_REQUIRE((((uintptr_t)token_table | (uintptr_t)position_table | (uintptr_t)out) & 15) == 0, "dfb_embed_tokens: buffers must be 16B aligned");
+  embed_tokens_kernel<<<grid_for((long long)B * S * (D / 4), 256), 256, 0, (cudaStream_t)stream>>>(ids, token_table, position_table, out,
+                                                                                                 B * S, S, D / 4, vocab);
+  DFB_CHECK_CUDA(cudaGetLastError());
+  return DFB_OK;
+}
+
+int dfb_image_to_uint8(const float* in, int in_c, uint8_t* out, long long pixels, void* stream) {
+  DFB_REQUIRE(in && out && in_c >= 3 && pixels > 0, "dfb_image_to_uint8: bad args");
+  image_to_uint8_kernel<<<grid_for(pixels, 256), 256, 0, (cudaStream_t)stream>>>(in, in_c, out, pixels);
   DFB_CHECK_CUDA(cudaGetLastError());
   return DFB_OK;
 }

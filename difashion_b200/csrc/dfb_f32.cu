@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(SG_THREADS) sgemm_kernel(const SgemmParams p) 
       if (p.act == DFB_ACT_SILU) x = silu_f(x);
       else if (p.act == DFB_ACT_LEAKY_RELU) x = x > 0.f ? x : 0.01f * x;
       else if (p.act == DFB_ACT_TANH) x = tanhf(x);
+      else if (p.act == DFB_ACT_QUICK_GELU) x = x / (1.0f + expf(-1.702f * x));
       if (p.residual) x += p.residual[(size_t)m * p.res_ld + n];
       p.out[(size_t)m * p.out_ld + n] = x;
     }
@@ -135,7 +136,7 @@ template <int DMAX>
 __global__ void __launch_bounds__(AF_Q) attn_f32_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                                        const float* __restrict__ v, float* __restrict__ out, int q_ld, int k_ld,
                                                        int v_ld, int out_ld, int q_col0, int k_col0, int v_col0, int out_col0,
-                                                       int Sq, int Skv, int dp, float scale) {
+                                                       int Sq, int Skv, int dp, float scale, int causal) {
   extern __shared__ float sm[];
   float* qs = sm;                         // [dp][AF_Q]
   float* ks = qs + (size_t)dp * AF_Q;     // [AF_KV][dp]
@@ -164,7 +165,8 @@ __global__ void __launch_bounds__(AF_Q) attn_f32_kernel(const float* __restrict_
       vs[i] = ok ? vb[(size_t)(j0 + r) * v_ld + c] : 0.f;
     }
     __syncthreads();
-    const int nk = min(AF_KV, Skv - j0);
+    int nk = min(AF_KV, Skv - j0);
+    if (causal) nk = min(nk, qi - j0 + 1);          // key j0 + j visible only when j0 + j <= qi
     for (int j = 0; j < nk; ++j) {
       float sdot = 0.f;
       const float* kr = ks + (size_t)j * dp;
@@ -269,7 +271,7 @@ int dfb_attention_f32(const dfb_attn_params* a, void* stream) {
 #define DFB_AF_LAUNCH(D)                                                                                                        \
   attn_f32_kernel<D><<<grid, AF_Q, smem, st>>>((const float*)a->q, (const float*)a->k, (const float*)a->v, (float*)a->out,     \
                                                 a->q_ld, a->k_ld, a->v_ld, a->out_ld, a->q_col0, a->k_col0, a->v_col0,        \
-                                                a->out_col0, a->Sq, a->Skv, a->dp, a->scale)
+                                                a->out_col0, a->Sq, a->Skv, a->dp, a->scale, a->causal)
   if (a->dp <= 32) DFB_AF_LAUNCH(32);
   else if (a->dp <= 64) DFB_AF_LAUNCH(64);
   else if (a->dp <= 96) DFB_AF_LAUNCH(96);

@@ -493,6 +493,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
             for (int e = 0; e < 4; ++e) {
               if (f_act == DFB_ACT_SILU) x[e] = silu_f(x[e]);
               else if (f_act == DFB_ACT_LEAKY_RELU) x[e] = x[e] > 0.f ? x[e] : 0.01f * x[e];
+              else if (f_act == DFB_ACT_QUICK_GELU) x[e] = x[e] / (1.0f + __expf(-1.702f * x[e]));
               else x[e] = tanhf(x[e]);
             }
           }

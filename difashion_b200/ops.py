@@ -182,7 +182,7 @@ def gemm(a: Sequence[torch.Tensor], w: torch.Tensor, n: int, *, out: torch.Tenso
     return out
 
 
-ACT_NONE, ACT_SILU, ACT_LEAKY_RELU, ACT_TANH = 0, 1, 2, 3
+ACT_NONE, ACT_SILU, ACT_LEAKY_RELU, ACT_TANH, ACT_QUICK_GELU = 0, 1, 2, 3, 4
 
 
 # ----------------------------------------------------------------------------------------------
@@ -194,9 +194,11 @@ def pad16(d: int) -> int:
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, heads: int, dp: int,
               scale: float, q_col0: int = 0, k_col0: int = 0, v_col0: int = 0, out_col0: int = 0,
-              block_kv: int = 0, dbg_v_lbo: int = 0, dbg_v_sbo: int = 0, dbg_flags: int = 0, dbg_timeline: Optional[torch.Tensor] = None) -> torch.Tensor:
+              block_kv: int = 0, dbg_v_lbo: int = 0, dbg_v_sbo: int = 0, dbg_flags: int = 0, dbg_timeline: Optional[torch.Tensor] = None,
+              causal: bool = False) -> torch.Tensor:
     """softmax(Q K^T * scale) V per (batch, head); q/k/v/out are bf16 ``[B, S, ld]`` views whose head
-    ``h`` lives in columns ``[col0 + h*dp, col0 + (h+1)*dp)`` (``dp`` = head dim padded to 16)."""
+    ``h`` lives in columns ``[col0 + h*dp, col0 + (h+1)*dp)`` (``dp`` = head dim padded to 16).  ``causal``: key j is
+    visible to query i only when j <= i (CLIP text encoder)."""
     from ._lib import AttnParams
     p = AttnParams()
     for t in (q, k, v, out):
@@ -211,6 +213,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
     p.dbg_v_lbo, p.dbg_v_sbo = dbg_v_lbo, dbg_v_sbo
     p.dbg_flags = dbg_flags
     p.dbg_timeline = _ptr(dbg_timeline)
+    p.causal = 1 if causal else 0
     e0 = _prof_begin()
     if q.dtype == torch.float32:
         check(_lib.load().dfb_attention_f32(C.byref(p), _stream()), "dfb_attention_f32")
@@ -432,3 +435,43 @@ def timestep_embedding(t: torch.Tensor, out: torch.Tensor, flip_sin_to_cos: bool
           "dfb_timestep_embedding")
     _count(1)
     return out
+
+
+@_profiled("embed_tokens")
+def embed_tokens(ids: torch.Tensor, token_table: torch.Tensor, position_table: torch.Tensor, out: torch.Tensor):
+    """CLIPTextEmbeddings: ``out[b*S+s] = token_table[ids[b, s]] + position_table[s]`` (fp32 ``[B*S, D]``)."""
+    b, s = ids.shape
+    d = token_table.shape[1]
+    assert ids.dtype == torch.int32 and ids.is_contiguous() and ids.is_cuda
+    assert token_table.dtype == torch.float32 and token_table.is_contiguous() and position_table.dtype == torch.float32
+    assert position_table.is_contiguous() and position_table.shape[0] >= s and position_table.shape[1] == d
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() == b * s * d
+    check(_lib.load().dfb_embed_tokens(ids.data_ptr(), token_table.data_ptr(), position_table.data_ptr(), out.data_ptr(), b, s, d,
+                                       token_table.shape[0], _stream()), "dfb_embed_tokens")
+    _count(1)
+    return out
+
+
+@_profiled("image_to_uint8")
+def image_to_uint8(img: torch.Tensor, out: torch.Tensor):
+    """VaeImageProcessor.postprocess: fp32 NHWC ``[B, H, W, C>=3]`` in [-1, 1] -> uint8 ``[B, H, W, 3]``."""
+    assert img.dtype == torch.float32 and img.is_contiguous() and img.is_cuda and img.shape[-1] >= 3
+    assert out.dtype == torch.uint8 and out.is_contiguous() and out.numel() == img.numel() // img.shape[-1] * 3
+    check(_lib.load().dfb_image_to_uint8(img.data_ptr(), img.shape[-1], out.data_ptr(), img.numel() // img.shape[-1], _stream()),
+          "dfb_image_to_uint8")
+    _count(1)
+    return out
+
+
+def s2d_taps_pad0(c: int) -> Tuple[Tuple[int, int, int], ...]:
+    """Tap table of the VAE encoder's Downsample2D: ``F.pad(x, (0, 1, 0, 1))`` then a stride-2, pad-0 3x3 conv, over the
+    space-to-depth planes: input row 2*ho + kh -> (plane parity, shift); the zero row / column the pad appends is the
+    TMA out-of-bounds fill."""
+    par = {0: (0, 0), 1: (1, 0), 2: (0, 1)}
+    taps = []
+    for kh in range(3):
+        ph, dh = par[kh]
+        for kw in range(3):
+            pw, dw = par[kw]
+            taps.append((dh, dw, (ph * 2 + pw) * c))
+    return tuple(taps)

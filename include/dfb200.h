@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define DFB200_ABI_VERSION 2
+#define DFB200_ABI_VERSION 3
 
 #define DFB_OK 0
 #define DFB_ERR_INVALID (-1)
@@ -34,6 +34,7 @@ extern "C" {
 #define DFB_ACT_SILU 1
 #define DFB_ACT_LEAKY_RELU 2 /* slope 0.01 (nn.LeakyReLU default, MutualEncoder) */
 #define DFB_ACT_TANH 3
+#define DFB_ACT_QUICK_GELU 4 /* x * sigmoid(1.702 x): CLIPTextModel mlp (hidden_act "quick_gelu") */
 
 const char* dfb_strerror(int rc);
 const char* dfb_last_error(void);
@@ -125,6 +126,8 @@ typedef struct dfb_attn_params {
   int32_t dbg_v_lbo, dbg_v_sbo; /* 0 = default; test hooks for the V descriptor strides     */
   int32_t dbg_flags;      /* 0 = default; tuning hooks: bit1 one CTA per SM, bit3 single-buffer kernel, bit4 P via smem, bit5 split-KV kernel, bit6 no short-KV kernel, bits 8-11 query tiles per CTA of the short-KV kernel */
   void* dbg_timeline;     /* NULL, or device buffer of >= 4096 int64: clock64 stamps of CTA (0,0,0) (tuning)  */
+  int32_t causal;         /* 1: key j is visible to query i only when j <= i (CLIPTextModel's causal mask,
+                             DiFashion/models/difashion.py:339-353); 0 everywhere in the UNet              */
 } dfb_attn_params;
 
 int dfb_attention(const dfb_attn_params* p, void* stream);
@@ -194,6 +197,14 @@ int dfb_pad_cast_rows(const void* in, int in_dtype, void* out, int out_dtype, in
  * stride-2 conv (fp32 NHWC [B,H,W,C] -> [B,H/2,W/2,4C]). */
 int dfb_upsample2x(const float* in, void* out, int out_dtype, int B, int H, int W, int C, void* stream);
 int dfb_space_to_depth(const float* in, void* out, int out_dtype, int B, int H, int W, int C, void* stream);
+/* CLIPTextEmbeddings (transformers CLIPTextModel, called at DiFashion/models/difashion.py:339-341, :352):
+ * out[b*S + s, :] = token_table[ids[b*S + s], :] + position_table[s, :]   (fp32 [B*S, D]; ids int32 in [0, vocab)). */
+int dfb_embed_tokens(const int32_t* ids, const float* token_table, const float* position_table, float* out, int B, int S,
+                     int D, int vocab, void* stream);
+/* VaeImageProcessor.postprocess(image, output_type="pil"/"np") after AutoencoderKL.decode (difashion.py:579-592):
+ * out[p, c] = uint8(round(clamp(in[p * in_c + c] / 2 + 0.5, 0, 1) * 255)), c < 3 (round half to even, as numpy).
+ * in: fp32 NHWC with in_c >= 3 channels per pixel; out: uint8 [pixels, 3] (HWC RGB, what PIL / np.save consume). */
+int dfb_image_to_uint8(const float* in, int in_c, uint8_t* out, long long pixels, void* stream);
 /* diffusers Timesteps (get_timestep_embedding): t fp32 [B] -> [B, dim] = [cos | sin]. */
 int dfb_timestep_embedding(const float* t, void* out, int out_dtype, int B, int dim, int flip_sin_to_cos, float freq_shift,
                            void* stream);

@@ -12,8 +12,10 @@ Follows ``DiFashion/models/difashion.py``:
   slots with weight 1.0 — NOT the mean —, MLP, CFG layout, blend with ``args.eta``,
   history concat, UNet, 4/3/2-branch CFG combine, scheduler step, prev_latents hand-off)
 
-VAE / CLIP stages (``:339-353``, ``:375-376``, ``:435-437``, ``:579-592``) are outside the
-hot path: the oracle takes their outputs (latents, prompt embeddings) as inputs.
+``oracle_generation`` is the hot path (the loop): it takes the VAE / CLIP outputs (latents, prompt embeddings) as
+inputs.  ``oracle_fashion_generation`` restates the whole method with the stages around the loop:
+CLIP prompt encoding ``:339-353``, null-latent / given-item VAE encode ``:375-376``, ``:435-437``, history lookup
+``:378-386``, VAE decode + ``VaeImageProcessor.postprocess`` ``:579-592``, result dictionary ``:598-614``.
 """
 from __future__ import annotations
 
@@ -206,3 +208,62 @@ def oracle_generation(unet, mutual_encoder, scheduler, *, olists, all_latents, c
             record.append(dict(t=int(t), unet_in=unet_in, noise_pred_branches=eps_b, noise_pred=eps,
                                latents=latents.clone()))
     return latents
+
+
+def postprocess_uint8(image: torch.Tensor):
+    """diffusers ``VaeImageProcessor.postprocess(image, output_type="np"/"pil")`` with ``do_denormalize`` all True
+    (difashion.py:586-592): ``(image / 2 + 0.5).clamp(0, 1)`` -> NHWC float32 numpy -> ``(x * 255).round().astype("uint8")``."""
+    x = (image / 2 + 0.5).clamp(0, 1)
+    x = x.cpu().permute(0, 2, 3, 1).float().numpy()
+    return (x * 255).round().astype("uint8")
+
+
+@torch.no_grad()
+def oracle_fashion_generation(unet, mutual_encoder, scheduler, text_encoder, vae, *, uids, oids, input_ids, olists,
+                              outfit_images, category, history, null_img, init_latents, num_inference_steps=50,
+                              category_guidance_scale=7.5, hist_guidance_scale=7.5, mutual_guidance_scale=7.5,
+                              eta_mutual=0.1, use_history=True, use_mutual_guidance=True, ddim_eta=0.0, generator=None,
+                              max_steps: Optional[int] = None, record: Optional[dict] = None):
+    """``DiFashion.fashion_generation(..., return_dict=False)`` (difashion.py:277-616) on the CPU oracles.
+
+    uids/oids [bsz], input_ids [bsz, olen, 77], olists [bsz, olen] (0 = blank), outfit_images [bsz*olen, 3, H, W],
+    category [bsz, olen], history {uid: {cate: latent[4,h,w]}}, null_img [3, H, W], init_latents [N, 4, h, w].
+    Returns (all_results, init_latents) with images as uint8 HWC numpy arrays (what ``output_type="pil"`` wraps)."""
+    fill_idx = torch.nonzero(olists == 0)                                   # :332-337
+    fill_cate = category[fill_idx[:, 0], fill_idx[:, 1]]
+    fill_uids, fill_oids = uids[fill_idx[:, 0]], oids[fill_idx[:, 0]]
+    full_cate = category[fill_idx[:, 0]]
+    fill_input_ids = input_ids[fill_idx[:, 0], fill_idx[:, 1]]
+    category_prompts = text_encoder(fill_input_ids)[0]                      # :339-341
+    from .clip_oracle import null_input_ids
+    null_prompt = text_encoder(null_input_ids(category_prompts.shape[1]))[0]      # :343-352
+    null_latent = vae.encode_mode_scaled(null_img.unsqueeze(0))[0]          # :375-376
+    hist = []                                                               # :378-386
+    for i, cate in enumerate(fill_cate.tolist()):
+        uid = int(uids[fill_idx[i][0]])
+        if use_history and cate in history.get(uid, {}):
+            hist.append(history[uid][cate])
+        else:
+            hist.append(null_latent)
+    hist_latents = torch.stack(hist)
+    all_latents = vae.encode_mode_scaled(outfit_images)                      # :435-437
+    latents = oracle_generation(unet, mutual_encoder, scheduler, olists=olists, all_latents=all_latents,
+                                category_prompts=category_prompts, null_prompt=null_prompt, hist_latents=hist_latents,
+                                null_latent=null_latent, init_latents=init_latents, num_inference_steps=num_inference_steps,
+                                category_guidance_scale=category_guidance_scale, hist_guidance_scale=hist_guidance_scale,
+                                mutual_guidance_scale=mutual_guidance_scale, eta_mutual=eta_mutual, use_history=use_history,
+                                use_mutual_guidance=use_mutual_guidance, ddim_eta=ddim_eta, generator=generator,
+                                max_steps=max_steps)
+    image = vae.decode_latents(latents)                                      # :579
+    images = postprocess_uint8(image)                                        # :586-592
+    if record is not None:
+        record.update(category_prompts=category_prompts, null_prompt=null_prompt, null_latent=null_latent,
+                      hist_latents=hist_latents, all_latents=all_latents, latents=latents, image=image)
+    all_results = {}                                                         # :598-614
+    for i, uid in enumerate(fill_uids.tolist()):
+        oid = int(fill_oids[i])
+        ent = all_results.setdefault(uid, {}).setdefault(oid, dict(images=[], cates=[], full_cates=full_cate[i]))
+        ent["images"].append(images[i])
+        ent["cates"].append(fill_cate[i])
+        ent["outfits"] = olists[fill_idx[i][0]]
+    return all_results, init_latents

@@ -1,4 +1,6 @@
-"""Pure-PyTorch fp32 restatement of the decoder half of diffusers 0.18.2 ``AutoencoderKL`` (SD-1.5 VAE).
+"""Pure-PyTorch fp32 restatement of diffusers 0.18.2 ``AutoencoderKL`` (SD-1.5 VAE): decoder, and (``with_encoder``)
+the encoder half used before the loop — ``vae.encode(images).latent_dist.mode() * scaling_factor`` for the given items
+(``DiFashion/models/difashion.py:435-437``), the white ``null_img`` (``:375-376``) and the history images (``:129-144``).
 
 TEST INFRASTRUCTURE (see ``oracle/__init__.py``) — parity unpinned: diffusers is absent.
 
@@ -34,6 +36,7 @@ import torch.nn.functional as F
 @dataclass
 class VAEConfig:
     latent_channels: int = 4
+    in_channels: int = 3
     out_channels: int = 3
     block_out_channels: Tuple[int, ...] = (128, 256, 512, 512)
     layers_per_block: int = 2
@@ -136,14 +139,84 @@ class VAEDecoder(nn.Module):
         return self.conv_out(F.silu(self.conv_norm_out(h)))
 
 
-class OracleVAE(nn.Module):
-    """``decode`` half of ``AutoencoderKL`` (state-dict keys ``post_quant_conv.*`` / ``decoder.*`` as in diffusers)."""
+class VAEDownsample2D(nn.Module):
+    """diffusers ``Downsample2D(use_conv=True, padding=0)`` as built by ``DownEncoderBlock2D``: asymmetric zero pad
+    (right / bottom only) then a stride-2, pad-0 3x3 conv."""
 
-    def __init__(self, cfg: VAEConfig = None):
+    def __init__(self, c: int):
+        super().__init__()
+        self.conv = nn.Conv2d(c, c, 3, stride=2, padding=0)
+
+    def forward(self, x):
+        return self.conv(F.pad(x, (0, 1, 0, 1), mode="constant", value=0))
+
+
+class _DownBlock(nn.Module):
+    def __init__(self, resnets, downsamplers=None):
+        super().__init__()
+        self.resnets = nn.ModuleList(resnets)
+        if downsamplers is not None:
+            self.downsamplers = nn.ModuleList(downsamplers)
+
+
+class VAEEncoder(nn.Module):
+    """diffusers 0.18.2 ``Encoder`` (``double_z=True``): ``conv_in`` 3x3 3->128; 4 ``DownEncoderBlock2D`` (2 resnets each,
+    channels 128, 256, 512, 512, ``Downsample2D`` after the first three); the same ``UNetMidBlock2D`` as the decoder;
+    ``conv_norm_out`` GroupNorm(32, 512, eps 1e-6) -> SiLU -> ``conv_out`` 3x3 512 -> 2*latent_channels."""
+
+    def __init__(self, cfg: VAEConfig):
+        super().__init__()
+        boc, g = tuple(cfg.block_out_channels), cfg.norm_num_groups
+        self.conv_in = nn.Conv2d(cfg.in_channels, boc[0], 3, padding=1)
+        downs, prev = [], boc[0]
+        for i, c in enumerate(boc):
+            res = [VAEResnetBlock2D(prev if j == 0 else c, c, g) for j in range(cfg.layers_per_block)]
+            downs.append(_DownBlock(res, [VAEDownsample2D(c)] if i < len(boc) - 1 else None))
+            prev = c
+        self.down_blocks = nn.ModuleList(downs)
+        top = boc[-1]
+        self.mid_block = _Block([VAEResnetBlock2D(top, top, g), VAEResnetBlock2D(top, top, g)], [VAEAttention(top, g)])
+        self.conv_norm_out = nn.GroupNorm(g, top, eps=1e-6)
+        self.conv_out = nn.Conv2d(top, 2 * cfg.latent_channels, 3, padding=1)
+
+    def forward(self, x):
+        h = self.conv_in(x)
+        for blk in self.down_blocks:
+            for r in blk.resnets:
+                h = r(h)
+            if hasattr(blk, "downsamplers"):
+                h = blk.downsamplers[0](h)
+        m = self.mid_block
+        h = m.resnets[1](m.attentions[0](m.resnets[0](h)))
+        return self.conv_out(F.silu(self.conv_norm_out(h)))
+
+
+class OracleVAE(nn.Module):
+    """``AutoencoderKL`` (state-dict keys ``post_quant_conv.*`` / ``decoder.*`` and, ``with_encoder=True``,
+    ``quant_conv.*`` / ``encoder.*`` as in diffusers)."""
+
+    def __init__(self, cfg: VAEConfig = None, with_encoder: bool = False):
         super().__init__()
         self.cfg = cfg or VAEConfig()
+        if with_encoder:
+            self.encoder = VAEEncoder(self.cfg)
+            self.quant_conv = nn.Conv2d(2 * self.cfg.latent_channels, 2 * self.cfg.latent_channels, 1)
         self.post_quant_conv = nn.Conv2d(self.cfg.latent_channels, self.cfg.latent_channels, 1)
         self.decoder = VAEDecoder(self.cfg)
+
+    @torch.no_grad()
+    def encode_moments(self, x: torch.Tensor):
+        """``AutoencoderKL.encode(x).latent_dist`` -> (mean, logvar): ``moments = quant_conv(encoder(x))``,
+        ``mean, logvar = chunk(moments, 2, dim=1)``, ``logvar = clamp(logvar, -30, 20)``
+        (``DiagonalGaussianDistribution``)."""
+        mean, logvar = torch.chunk(self.quant_conv(self.encoder(x)), 2, dim=1)
+        return mean, torch.clamp(logvar, -30.0, 20.0)
+
+    @torch.no_grad()
+    def encode_mode_scaled(self, x: torch.Tensor) -> torch.Tensor:
+        """The reference call ``vae.encode(x).latent_dist.mode() * vae.config.scaling_factor``
+        (difashion.py:129-130, :375-376, :435-437): the mode of the diagonal Gaussian is its mean."""
+        return self.encode_moments(x)[0] * self.cfg.scaling_factor
 
     @torch.no_grad()
     def decode(self, z: torch.Tensor) -> torch.Tensor:
@@ -155,9 +228,9 @@ class OracleVAE(nn.Module):
         return self.decode(latents / self.cfg.scaling_factor)
 
 
-def make_oracle_vae(cfg: VAEConfig = None, seed: int = 0) -> OracleVAE:
+def make_oracle_vae(cfg: VAEConfig = None, seed: int = 0, with_encoder: bool = False) -> OracleVAE:
     torch.manual_seed(seed)
-    m = OracleVAE(cfg).eval()
+    m = OracleVAE(cfg, with_encoder=with_encoder).eval()
     for p in m.parameters():
         p.requires_grad_(False)
     return m

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_library_loads_and_exports_every_declared_symbol():
     from difashion_b200 import _lib
     lib = _lib.load()
-    assert lib.dfb_abi_version() == 2
+    assert lib.dfb_abi_version() == 3
     header = open(os.path.join(ROOT, "include", "dfb200.h")).read()
     declared = set(re.findall(r"\b(dfb_[a-z0-9_]+)\s*\(", header))
     assert declared, "no declarations parsed"
@@ -278,3 +278,93 @@ def test_mutual_encoder_names_and_init():
     assert float(m.mlp[0].bias.abs().max()) == 0.0
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(torch.randn(1, 4, 16, 16))
+
+
+# ------------------------------------------------------------------------------------------------
+# stages around the loop
+# ------------------------------------------------------------------------------------------------
+def test_space_to_depth_pad0_tap_table_is_the_vae_encoder_downsample():
+    """Downsample2D of the VAE encoder: F.pad(x, (0, 1, 0, 1)) + stride-2 pad-0 conv == taps over space-to-depth planes."""
+    from difashion_b200 import ops
+    torch.manual_seed(3)
+    B, H, W, C = 2, 8, 8, 64
+    x = torch.randn(B, H, W, C)
+    w = torch.randn(3, C, 3, 3)
+    s2d = torch.zeros(B, H // 2, W // 2, 4 * C)
+    for h in range(H):
+        for ww in range(W):
+            p = (h & 1) * 2 + (ww & 1)
+            s2d[:, h // 2, ww // 2, p * C:(p + 1) * C] = x[:, h, ww]
+    got = _emulate_gemm([(s2d.bfloat16(), ops.s2d_taps_pad0(C), C)], None, ops.pack_conv3x3(w), 3, (B, H // 2, W // 2))
+    xp = F.pad(x.bfloat16().double().permute(0, 3, 1, 2), (0, 1, 0, 1))
+    ref = F.conv2d(xp, w.bfloat16().double(), stride=2, padding=0).permute(0, 2, 3, 1)
+    assert torch.allclose(got, ref, atol=1e-9)
+
+
+def test_clip_and_vae_module_surfaces_without_gpu():
+    from difashion_b200 import B200AutoencoderKL, B200CLIPTextModel
+    from oracle.clip_oracle import CLIPTextConfigLite, OracleCLIPTextModel, null_input_ids, tiny_clip_config
+    from oracle.vae_oracle import make_oracle_vae, tiny_vae_config
+    # transformers / diffusers key names: one state dict feeds oracle and product
+    cfg = tiny_clip_config()
+    o = OracleCLIPTextModel(cfg)
+    m = B200CLIPTextModel(vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size, intermediate_size=cfg.intermediate_size,
+                          num_hidden_layers=cfg.num_hidden_layers, num_attention_heads=cfg.num_attention_heads)
+    sd = dict(o.state_dict())
+    sd["text_model.embeddings.position_ids"] = torch.arange(77)[None]          # buffer of older checkpoints
+    m.load_transformers_state_dict(sd)
+    assert list(m.state_dict().keys()) == list(o.state_dict().keys())
+    full = B200CLIPTextModel()
+    assert sum(p.numel() for p in full.parameters()) == 123_060_480 and len(full.state_dict()) == 196
+    assert torch.equal(full.null_input_ids(), null_input_ids())
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 77, dtype=torch.long))
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 77, dtype=torch.long), attention_mask=torch.ones(1, 77))
+    with pytest.raises(NotImplementedError):
+        B200CLIPTextModel(hidden_act="gelu")
+    # VAE: full and decoder-only state dicts
+    vcfg = tiny_vae_config(block_out_channels=(64, 64, 128, 128))
+    kw = dict(block_out_channels=tuple(vcfg.block_out_channels), layers_per_block=vcfg.layers_per_block, norm_num_groups=vcfg.norm_num_groups)
+    both = make_oracle_vae(vcfg, with_encoder=True)
+    v = B200AutoencoderKL(**kw)
+    v.load_diffusers_state_dict(both.state_dict())
+    assert v._encoder_loaded and list(v.state_dict().keys()) == list(both.state_dict().keys())
+    v2 = B200AutoencoderKL(**kw)
+    v2.load_diffusers_state_dict(make_oracle_vae(vcfg).state_dict())
+    assert not v2._encoder_loaded
+    with pytest.raises(RuntimeError):
+        v2.pack_encoder("cuda")
+    with pytest.raises(RuntimeError):
+        v2.load_diffusers_state_dict({k: t for k, t in make_oracle_vae(vcfg).state_dict().items() if "conv_out" not in k})
+    assert sum(p.numel() for p in B200AutoencoderKL().parameters()) == 83_653_863
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        v.encode(torch.zeros(1, 3, 64, 64))
+
+
+def test_output_wire_format(tmp_path):
+    """inf4eval.save_batch_outputs layout: images/<uid>/<oid>/<i>.jpg (+ all.jpg for GOR), image_paths in the saved
+    dictionary, np.save of the dictionary as a 0-d object array."""
+    import numpy as np
+    from PIL import Image
+    from difashion_b200 import merge_and_save_images, save_batch_outputs, save_outputs_npy
+    rng = np.random.default_rng(0)
+    mk = lambda: rng.integers(0, 256, size=(32, 32, 3), dtype=np.uint8)
+    outs = {7: {101: dict(images=[mk(), mk(), mk(), mk()], cates=[torch.tensor(1), torch.tensor(2), torch.tensor(3), torch.tensor(4)],
+                          full_cates=torch.tensor([1, 2, 3, 4]), outfits=torch.zeros(4, dtype=torch.long))},
+            9: {102: dict(images=[Image.fromarray(mk())], cates=[torch.tensor(5)], full_cates=torch.tensor([5, 6, 7, 8]),
+                          outfits=torch.tensor([11, 0, 7, 9]))}}
+    gen = str(tmp_path / "GOR-checkpoint-1-cate12.0-mutual5.0-hist4.0")
+    all_out, all_grd = save_batch_outputs({}, {}, outs, gen, "GOR", save_grd=False)
+    for i in range(4):
+        assert os.path.exists(os.path.join(gen, "images", "7", "101", f"{i}.jpg"))
+    merged = Image.open(os.path.join(gen, "images", "7", "101", "all.jpg"))
+    assert merged.size == (64, 64)                                   # ceil(sqrt(4)) = 2 columns of 32 px
+    assert Image.open(os.path.join(gen, "images", "9", "102", "all.jpg")).size == (32, 32)
+    assert "images" not in all_out[7][101] and len(all_out[7][101]["image_paths"]) == 4 and all_grd == {}
+    path = save_outputs_npy(gen, all_out)
+    back = np.load(path, allow_pickle=True).item()
+    assert back[9][102]["image_paths"] == [os.path.join(gen, "images", "9", "102", "0.jpg")]
+    assert torch.equal(back[9][102]["outfits"], torch.tensor([11, 0, 7, 9]))
+    merge_and_save_images([mk() for _ in range(5)], str(tmp_path / "m.jpg"))
+    assert Image.open(str(tmp_path / "m.jpg")).size == (96, 96)      # 3 columns, white background

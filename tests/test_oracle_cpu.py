@@ -12,6 +12,7 @@ from oracle.unet_oracle import (Attention, OracleUNet2DConditionModel, UNetConfi
                                 timestep_embedding)
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
+from tests.util import rel_l2
 
 
 def _count(cfg):
@@ -188,3 +189,91 @@ def test_vae_decoder_oracle_structure_and_shapes():
     assert torch.equal(y, t.decode(z / t.cfg.scaling_factor))
     # the attention's residual connection and the decoder are deterministic
     assert torch.equal(y, make_oracle_vae(tiny_vae_config(), seed=3).decode_latents(z))
+
+
+# ------------------------------------------------------------------------------------------------
+# stages around the loop: CLIP text encoder, VAE encoder, post-processing
+# ------------------------------------------------------------------------------------------------
+def test_clip_oracle_matches_transformers_golden():
+    """PINNED: tests/golden/clip_tiny.pt was produced by the real transformers.CLIPTextModel
+    (tools/make_golden_clip.py); the restatement must reproduce it from the same state dict."""
+    from oracle.clip_oracle import CLIPTextConfigLite, OracleCLIPTextModel
+    gold = torch.load(os.path.join(GOLD, "clip_tiny.pt"))
+    m = OracleCLIPTextModel(CLIPTextConfigLite(**gold["config"])).eval()
+    m.load_state_dict(gold["state_dict"], strict=True)
+    y = m(gold["input_ids"])[0]
+    assert y.shape == gold["last_hidden_state"].shape
+    assert rel_l2(y, gold["last_hidden_state"]) < 2e-6
+    # causal: the hidden state at position i does not depend on tokens after i
+    ids2 = gold["input_ids"].clone()
+    ids2[:, 40:] = 7
+    y2 = m(ids2)[0]
+    assert torch.allclose(y2[:, :40], y[:, :40], atol=1e-6) and not torch.allclose(y2[:, 40:], y[:, 40:], atol=1e-3)
+
+
+def test_clip_oracle_matches_transformers_live():
+    """Same check against transformers imported right here (skipped where the package is absent)."""
+    tr = pytest.importorskip("transformers")
+    from oracle.clip_oracle import make_oracle_clip, tiny_clip_config
+    cfg = tiny_clip_config()
+    o = make_oracle_clip(cfg, seed=2)
+    hf = tr.CLIPTextModel(tr.CLIPTextConfig(
+        vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size, intermediate_size=cfg.intermediate_size,
+        num_hidden_layers=cfg.num_hidden_layers, num_attention_heads=cfg.num_attention_heads,
+        max_position_embeddings=cfg.max_position_embeddings, hidden_act="quick_gelu", layer_norm_eps=cfg.layer_norm_eps,
+        projection_dim=cfg.hidden_size, pad_token_id=1, bos_token_id=0, eos_token_id=2)).eval()
+    res = hf.load_state_dict(o.state_dict(), strict=False)
+    assert not res.unexpected_keys and all(k.endswith("position_ids") for k in res.missing_keys)
+    ids = torch.randint(0, cfg.vocab_size, (3, 77), generator=torch.Generator().manual_seed(4))
+    with torch.no_grad():
+        ref = hf(ids)[0]
+    assert rel_l2(o(ids)[0], ref) < 2e-6
+
+
+def test_clip_sd15_structure():
+    """SD-1.5 text encoder: 123 060 480 parameters, 196 tensors, transformers key names; the empty prompt's ids."""
+    from oracle.clip_oracle import BOS_TOKEN_ID, EOS_TOKEN_ID, CLIPTextConfigLite, OracleCLIPTextModel, null_input_ids
+    m = OracleCLIPTextModel(CLIPTextConfigLite())
+    sd = m.state_dict()
+    assert sum(p.numel() for p in m.parameters()) == 123_060_480 and len(sd) == 196
+    for k in ("text_model.embeddings.token_embedding.weight", "text_model.embeddings.position_embedding.weight",
+              "text_model.encoder.layers.11.self_attn.q_proj.bias", "text_model.encoder.layers.0.mlp.fc1.weight",
+              "text_model.encoder.layers.5.layer_norm2.weight", "text_model.final_layer_norm.bias"):
+        assert k in sd, k
+    ids = null_input_ids()
+    assert ids.shape == (1, 77) and ids[0, 0] == BOS_TOKEN_ID and bool((ids[0, 1:] == EOS_TOKEN_ID).all())
+
+
+def test_vae_encoder_oracle_structure_and_shapes():
+    """AutoencoderKL encode half: published SD-VAE parameter split (encoder 34 163 592 + quant_conv 72; total
+    83 653 863), diffusers key names, asymmetric-pad down-sampling, mode() * scaling_factor."""
+    import torch.nn.functional as F
+    from oracle.vae_oracle import VAEDownsample2D, make_oracle_vae, tiny_vae_config
+    m = make_oracle_vae(with_encoder=True)
+    assert sum(p.numel() for p in m.encoder.parameters()) == 34_163_592
+    assert sum(p.numel() for p in m.quant_conv.parameters()) == 72
+    assert sum(p.numel() for p in m.parameters()) == 83_653_863 and len(m.state_dict()) == 248
+    sd = m.state_dict()
+    for k in ("encoder.conv_in.weight", "encoder.down_blocks.0.downsamplers.0.conv.bias", "encoder.down_blocks.1.resnets.0.conv_shortcut.weight",
+              "encoder.mid_block.attentions.0.to_v.weight", "encoder.conv_norm_out.bias", "encoder.conv_out.weight", "quant_conv.weight"):
+        assert k in sd, k
+    assert "encoder.down_blocks.3.downsamplers.0.conv.weight" not in sd
+    assert sd["encoder.conv_out.weight"].shape == (8, 512, 3, 3) and sd["encoder.down_blocks.2.resnets.0.conv1.weight"].shape == (512, 256, 3, 3)
+    d = VAEDownsample2D(4)
+    x = torch.randn(1, 4, 6, 6)
+    ref = F.conv2d(F.pad(x, (0, 1, 0, 1)), d.conv.weight, d.conv.bias, stride=2)
+    assert torch.equal(d(x), ref) and ref.shape == (1, 4, 3, 3)
+    t = make_oracle_vae(tiny_vae_config(block_out_channels=(64, 64, 128, 128)), seed=3, with_encoder=True)
+    img = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(6))
+    mean, logvar = t.encode_moments(img)
+    assert mean.shape == logvar.shape == (2, 4, 8, 8) and float(logvar.max()) <= 20.0 and float(logvar.min()) >= -30.0
+    assert torch.equal(t.encode_mode_scaled(img), mean * t.cfg.scaling_factor)
+
+
+def test_postprocess_uint8_rounding():
+    """VaeImageProcessor.postprocess arithmetic: denormalise, clamp, round half to even, uint8 HWC."""
+    from oracle.generation_oracle import postprocess_uint8
+    x = torch.tensor([-1.5, -1.0, -1.0 + 1.0 / 255.0, 0.0, 1.0 / 255.0, 1.0, 3.0]).view(1, 1, 1, 7).repeat(1, 3, 1, 1)
+    u = postprocess_uint8(x)
+    assert u.shape == (1, 1, 7, 3) and u.dtype.name == "uint8"
+    assert u[0, 0, :, 0].tolist() == [0, 0, 0, 128, 128, 255, 255]          # 0.5/255 -> 0 and 127.5 -> 128: half to even

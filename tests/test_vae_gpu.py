@@ -89,3 +89,66 @@ def test_softmax_rows():
         ops.softmax_rows(x, out, 0.37)
         ref = torch.softmax(0.37 * x.double(), dim=-1)
         assert rel_l2(out, ref) < tol
+
+
+# ------------------------------------------------------------------------------------------------
+# encode half: vae.encode(images).latent_dist.mode() * scaling_factor
+# ------------------------------------------------------------------------------------------------
+def _mk_full(which, seed=0):
+    from oracle.vae_oracle import VAEConfig, make_oracle_vae, tiny_vae_config
+    from difashion_b200.vae import B200AutoencoderKL
+    cfg = tiny_vae_config(block_out_channels=(64, 64, 128, 128)) if which == "tiny" else VAEConfig()
+    oracle = make_oracle_vae(cfg, seed=seed, with_encoder=True)
+    vae = B200AutoencoderKL(block_out_channels=tuple(cfg.block_out_channels), layers_per_block=cfg.layers_per_block,
+                            norm_num_groups=cfg.norm_num_groups, scaling_factor=cfg.scaling_factor)
+    vae.load_diffusers_state_dict(oracle.state_dict())
+    return oracle, vae.cuda()
+
+
+def test_stride2_pad0_conv_through_space_to_depth():
+    """The VAE encoder's Downsample2D (pad right/bottom, stride 2, pad 0) on the implicit-GEMM kernel."""
+    import torch.nn.functional as F
+    from difashion_b200 import ops
+    g = torch.Generator().manual_seed(13)
+    for (B, H, W, C), dt, tol in (((2, 32, 32, 64), torch.bfloat16, 1e-5), ((1, 512, 512, 128), torch.bfloat16, 1e-5),
+                                  ((2, 16, 16, 64), torch.float32, 2e-6)):
+        x = torch.randn(B, C, H, W, generator=g)
+        w = torch.randn(C, C, 3, 3, generator=g) * (9 * C) ** -0.5
+        bias = torch.randn(C, generator=g)
+        s2d = torch.empty(B, H // 2, W // 2, 4 * C, dtype=dt, device="cuda")
+        ops.space_to_depth(x.permute(0, 2, 3, 1).contiguous().cuda(), s2d)
+        out = torch.empty(B, H // 2, W // 2, C, dtype=torch.float32, device="cuda")
+        ops.gemm([s2d], ops.pack_conv3x3(w.cuda(), dt), C, out=out, taps=[ops.s2d_taps_pad0(C)], a_c=[C], conv_geom=(B, H // 2, W // 2),
+                 bias=bias.cuda())
+        torch.cuda.synchronize()
+        ref = F.conv2d(F.pad(x.to(dt).double(), (0, 1, 0, 1)), w.to(dt).double(), bias.double(), stride=2)
+        assert rel_l2(out.permute(0, 3, 1, 2).cpu(), ref) < tol
+
+
+@pytest.mark.parametrize("which,B,hw,precision,tol", [("tiny", 3, 64, "bf16", 2e-2), ("tiny", 2, 128, "fp32", 1e-4),
+                                                      ("full", 1, 512, "bf16", 2e-2), ("full", 1, 256, "fp32", 1e-4)])
+def test_vae_encode_matches_oracle(which, B, hw, precision, tol):
+    oracle, vae = _mk_full(which)
+    vae.set_precision(precision)
+    img = torch.randn(B, 3, hw, hw, generator=torch.Generator().manual_seed(17)).clamp(-1, 1)
+    img[0] = 1.0                                                            # the white null image (difashion.py:375)
+    ref = oracle.encode_mode_scaled(img)
+    got = vae.encode_latents(img.cuda())
+    dist = vae.encode(img.cuda()).latent_dist
+    torch.cuda.synchronize()
+    e, e2 = rel_l2(got.cpu(), ref), rel_l2(dist.mode().cpu() * vae.config.scaling_factor, ref)
+    print(f"\n[vae encode {which} {precision} B={B} {hw}x{hw}] latent rel-L2 {e:.3e} (encode().latent_dist.mode() * sf: {e2:.3e})")
+    assert got.shape == ref.shape == (B, 4, hw // 8, hw // 8) and got.dtype == torch.float32
+    assert e <= tol and e2 <= tol
+    mean, logvar = oracle.encode_moments(img)
+    assert rel_l2(dist.logvar.cpu(), logvar) <= 5 * tol and dist.sample(torch.Generator(device="cuda").manual_seed(1)).shape == got.shape
+    # encode -> decode -> uint8 goes through dfb_image_to_uint8
+    u8 = vae.decode_latents_uint8(got)
+    from oracle.generation_oracle import postprocess_uint8
+    ref_u8 = postprocess_uint8(oracle.decode_latents(ref))
+    diff = (u8.cpu().numpy().astype("int16") - ref_u8.astype("int16"))
+    assert u8.shape == (B, hw, hw, 3) and u8.dtype == torch.uint8
+    if precision == "fp32":
+        assert abs(diff).max() <= 1 and (diff != 0).mean() < 2e-3
+    else:
+        assert abs(diff).mean() < 3.0
