@@ -20,7 +20,7 @@ namespace dfb {
 
 constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_K = 64;                     // one 128-byte swizzle atom of bf16
-constexpr int GEMM_STAGES = 4;
+constexpr int GEMM_MAX_STAGES = 8;                   // ring depth is chosen per launch from the stage size (see dfb_gemm)
 constexpr int GEMM_MAX_BLOCK_N = 256;
 constexpr int GEMM_A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;          // 16 KB
 constexpr int GEMM_B_BYTES = GEMM_MAX_BLOCK_N * GEMM_BLOCK_K * 2;      // 32 KB (max)
@@ -28,7 +28,7 @@ constexpr int GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES;          // 48 KB
 constexpr int GEMM_EPI_WARPS = 8;
 constexpr int GEMM_EPI_STAGE_BYTES = 4096;                              // per-warp 32x32 fp32 transpose tile
 constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
-constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int GEMM_SMEM_BYTES = 4 * GEMM_STAGE_BYTES + GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;   // 227 KB budget
 constexpr int GEMM_TMEM_COLS = 512;
 
 struct GemmMaps {
@@ -38,6 +38,7 @@ struct GemmMaps {
 
 struct GemmKernelParams {
   int M, N, block_n, n_tiles_m, n_tiles_n;
+  int stages, stage_bytes;                    // smem ring: depth and stride (A 16 KB + B block_n x 128 B per stage)
   int conv, TH, TB, tiles_per_img, w_tiles;   // w_tiles > 1: images wider than 128 pixels, one tile = 128 pixels of a row
   int nseg;
   int seg_ntaps[2];
@@ -65,13 +66,16 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
   constexpr bool kGeneric = (MODE & EPI_GENERIC) != 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + GEMM_STAGES * GEMM_STAGE_BYTES + GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES;
-  // barrier layout (8 bytes each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem ptr
+  const int STAGES = p.stages;
+  const uint32_t STAGE_BYTES = (uint32_t)p.stage_bytes;
+  const uint32_t epi_base = smem_base + (uint32_t)STAGES * STAGE_BYTES;
+  const uint32_t bar_base = epi_base + GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES;
+  // barrier layout (8 bytes each): full[MAX_STAGES], empty[MAX_STAGES], tmem_full[2], tmem_empty[2], tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (GEMM_STAGES + s); };
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * GEMM_STAGES + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * GEMM_STAGES + 2 + s); };
-  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * GEMM_STAGES + 4);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (GEMM_MAX_STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * GEMM_MAX_STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * GEMM_MAX_STAGES + 2 + s); };
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * GEMM_MAX_STAGES + 4);
 
   // Roles: warps 0..EW-1 epilogue (TMEM lane quarter = warp & 3), warp EW TMA producer, warp EW+1 MMA issuer.
   // The issue arbiter favours the highest warp id of a scheduler, so the two single-lane control warps sit
@@ -86,7 +90,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
     tma_prefetch_desc(&maps.a[0]);
     if (p.nseg > 1) tma_prefetch_desc(&maps.a[1]);
     tma_prefetch_desc(&maps.b);
-    for (int s = 0; s < GEMM_STAGES; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
@@ -136,7 +140,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
           for (int cb = 0; cb < p.seg_ncblk[s]; ++cb, ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             if (elect_one()) {
-              const uint32_t sa = smem_base + stage * GEMM_STAGE_BYTES;
+              const uint32_t sa = smem_base + (uint32_t)stage * STAGE_BYTES;
               const uint32_t sb = sa + GEMM_A_BYTES;
               mbar_expect_tx(full_bar(stage), tx_bytes);
               if (p.conv)
@@ -146,7 +150,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
               tma_load_2d(&maps.b, sb, full_bar(stage), kb * GEMM_BLOCK_K, nt * p.block_n);
             }
             __syncwarp();
-            if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1u; }
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
       }
@@ -169,7 +173,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
       for (int kb = 0; kb < nk; ++kb) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint64_t da = desc_a0 + (uint64_t)((uint32_t)(stage * GEMM_STAGE_BYTES) >> 4);
+        const uint64_t da = desc_a0 + (uint64_t)(((uint32_t)stage * STAGE_BYTES) >> 4);
         const uint64_t db = da + (uint64_t)(GEMM_A_BYTES >> 4);
         if (elect_one()) {
 #pragma unroll
@@ -182,7 +186,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
           if (kb == nk - 1) umma_commit(tfull_bar(as));   // accumulator ready for the epilogue
         }
         __syncwarp();
-        if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1u; }
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else {
@@ -194,7 +198,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
     const int ew = warp;
     const int quarter = warp & 3;              // TMEM lane quarter this warp may access
     const int half = ew >> 2;                  // which share of the chunks (0 .. EW/4-1)
-    const uint32_t stg = smem_base + GEMM_STAGES * GEMM_STAGE_BYTES + (uint32_t)ew * (GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES / EW);
+    const uint32_t stg = epi_base + (uint32_t)ew * (GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES / EW);
     // run-time flags in generic mode, compile-time constants otherwise
     const bool f_geglu = kGeneric ? (p.geglu != 0) : ((MODE & EPI_GEGLU) != 0);
     const bool f_out32 = kGeneric ? (p.out_fp32 != 0) : ((MODE & EPI_OUT_F32) != 0);
@@ -561,6 +565,16 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
   }
 }
 
+// tuning hook: DFB_GEMM_STAGES=<n> caps the smem ring depth (read once)
+static int q_stages_override() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DFB_GEMM_STAGES");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
 static int choose_block_n(int N) {
   static const int cands[] = {256, 224, 192, 160, 128, 96, 64, 32};
   int best = 32, best_waste = 1 << 30;
@@ -593,6 +607,17 @@ extern "C" int dfb_gemm(const dfb_gemm_params* q, void* stream_) {
   int bn = q->block_n > 0 ? q->block_n : choose_block_n(q->N);
   DFB_REQUIRE(bn % 32 == 0 && bn >= 32 && bn <= GEMM_MAX_BLOCK_N, "dfb_gemm: block_n must be a multiple of 32 in [32,256]");
   kp.block_n = bn;
+  // smem ring: stage = A tile (16 KB) + B tile (block_n x 128 B, a multiple of 1 KB because block_n % 32 == 0, which keeps
+  // every operand 1024-byte aligned for the 128-byte swizzle); as many stages as the 227 KB budget holds (4 at
+  // block_n 256 ... 8 at block_n <= 64): narrow tiles have short MMA phases per stage, so they need a deeper ring to
+  // cover the same TMA latency.
+  kp.stage_bytes = GEMM_A_BYTES + bn * GEMM_BLOCK_K * 2;
+  {
+    const int budget = GEMM_SMEM_BYTES - GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES - 1024 - 256;
+    int st = budget / kp.stage_bytes;
+    if (q_stages_override() > 0) st = st < q_stages_override() ? st : q_stages_override();
+    kp.stages = st > GEMM_MAX_STAGES ? GEMM_MAX_STAGES : (st < 2 ? 2 : st);
+  }
   kp.n_tiles_n = (q->N + bn - 1) / bn;
   kp.conv = q->conv ? 1 : 0;
   kp.nseg = q->nseg;

@@ -57,7 +57,12 @@ def test_vae_decode_chunked_batch_and_deprecated_keys():
         for a, b in ren.items():
             k = k.replace(f"attentions.0.{a}.", f"attentions.0.{b}.")
         old[k] = v
-    old["encoder.conv_in.weight"] = torch.zeros(1)          # a full checkpoint also carries the encoder
+    from oracle.vae_oracle import make_oracle_vae
+    for k, v in make_oracle_vae(oracle.cfg, seed=9, with_encoder=True).state_dict().items():
+        if k.startswith(("encoder.", "quant_conv.")):         # a full checkpoint also carries the encoder
+            for a, b in ren.items():
+                k = k.replace(f"attentions.0.{a}.", f"attentions.0.{b}.")
+            old[k] = v
     cfg = oracle.cfg
     vae2 = B200AutoencoderKL(block_out_channels=tuple(cfg.block_out_channels), layers_per_block=cfg.layers_per_block,
                              norm_num_groups=cfg.norm_num_groups).cuda()
