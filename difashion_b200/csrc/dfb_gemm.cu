@@ -575,12 +575,35 @@ static int q_stages_override() {
   return v;
 }
 
+// tuning hook: DFB_GEMM_BN="640:224,320:160" overrides the automatic N tile for the listed N (read once)
+static int bn_override(int N) {
+  static int keys[8], vals[8], n = -1;
+  if (n < 0) {
+    n = 0;
+    const char* e = getenv("DFB_GEMM_BN");
+    while (e && *e && n < 8) {
+      int k = 0, v = 0;
+      if (sscanf(e, "%d:%d", &k, &v) == 2) { keys[n] = k; vals[n] = v; ++n; }
+      e = strchr(e, ',');
+      if (e) ++e;
+    }
+  }
+  for (int i = 0; i < n; ++i)
+    if (keys[i] == N) return vals[i];
+  return 0;
+}
+
 static int choose_block_n(int N) {
+  if (bn_override(N) > 0) return bn_override(N);
+  // cost of one row of output tiles ~ n_tiles * (block_n + 48): executed MMA columns plus a per-tile charge for
+  // re-reading the A tile (L2 -> smem) and the epilogue hand-off.  Measured on B200 (profiles/r01_gemm_tile_tuning.md):
+  // N = 640 runs 1 % faster per UNet step as 3 x 224 (5 % zero columns) than as 4 x 160; every other N of the UNet
+  // keeps its zero-waste tile.
   static const int cands[] = {256, 224, 192, 160, 128, 96, 64, 32};
-  int best = 32, best_waste = 1 << 30;
+  int best = 32, best_cost = 1 << 30;
   for (int bn : cands) {
-    const int waste = ((N + bn - 1) / bn) * bn - N;
-    if (waste < best_waste) { best_waste = waste; best = bn; }
+    const int cost = ((N + bn - 1) / bn) * (bn + 48);
+    if (cost < best_cost) { best_cost = cost; best = bn; }
   }
   return best;
 }
@@ -608,14 +631,15 @@ extern "C" int dfb_gemm(const dfb_gemm_params* q, void* stream_) {
   DFB_REQUIRE(bn % 32 == 0 && bn >= 32 && bn <= GEMM_MAX_BLOCK_N, "dfb_gemm: block_n must be a multiple of 32 in [32,256]");
   kp.block_n = bn;
   // smem ring: stage = A tile (16 KB) + B tile (block_n x 128 B, a multiple of 1 KB because block_n % 32 == 0, which keeps
-  // every operand 1024-byte aligned for the 128-byte swizzle); as many stages as the 227 KB budget holds (4 at
-  // block_n 256 ... 8 at block_n <= 64): narrow tiles have short MMA phases per stage, so they need a deeper ring to
-  // cover the same TMA latency.
+  // every operand 1024-byte aligned for the 128-byte swizzle).
   kp.stage_bytes = GEMM_A_BYTES + bn * GEMM_BLOCK_K * 2;
   {
     const int budget = GEMM_SMEM_BYTES - GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES - 1024 - 256;
     int st = budget / kp.stage_bytes;
-    if (q_stages_override() > 0) st = st < q_stages_override() ? st : q_stages_override();
+    // default depth 4: deeper rings fit for narrow tiles but measured no better (N = 320 convs 8 % slower at 5 stages,
+    // profiles/r01_gemm_tile_tuning.md); DFB_GEMM_STAGES=<n> overrides the cap for tuning
+    const int cap = q_stages_override() > 0 ? q_stages_override() : 4;
+    st = st < cap ? st : cap;
     kp.stages = st > GEMM_MAX_STAGES ? GEMM_MAX_STAGES : (st < 2 ? 2 : st);
   }
   kp.n_tiles_n = (q->N + bn - 1) / bn;
