@@ -202,6 +202,7 @@ def main():
     ap.add_argument("--outfits", type=int, default=16, help="outfits per GPU (16 -> 256 UNet rows: BASELINE configs[1])")
     ap.add_argument("--skv", type=int, default=77, help="text tokens (85 = 77 + 8 history tokens, configs[3])")
     ap.add_argument("--max-rows", type=int, default=256, help="UNet rows per micro-batch")
+    ap.add_argument("--streams", type=int, default=1, help="CUDA streams the row chunks of a step are spread over (needs max-rows < rows)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-step", action="store_true", help="print per-kernel-kind time of one eager step")
@@ -234,7 +235,7 @@ def main():
     unet = B200UNet2DConditionModel()
     me = MutualEncoder()
     unet.pack(dev)
-    pipe = B200DiFashionPipeline(unet, me, B200DDIMScheduler(), eta_mutual=0.1, max_rows=args.max_rows)
+    pipe = B200DiFashionPipeline(unet, me, B200DDIMScheduler(), eta_mutual=0.1, max_rows=args.max_rows, streams=args.streams)
     # weak scaling: every rank owns `outfits` whole outfits (distinct seeds = distinct outfits)
     inp = synthetic_inputs(args.outfits, args.skv, seed=123 + rank)
     rows = args.outfits * ROWS_PER_OUTFIT

@@ -49,6 +49,7 @@ class GemmParams(C.Structure):
         ("act", C.c_int32),
         ("block_n", C.c_int32),
         ("gn_partial", C.c_void_p),
+        ("cta_group", C.c_int32),
     ]
 
 

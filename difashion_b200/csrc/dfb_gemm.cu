@@ -60,7 +60,11 @@ enum : int { EPI_OUT_F32 = 1, EPI_RES_F32 = 2, EPI_ROWBIAS = 4, EPI_GEGLU = 8, E
 
 // EW = number of epilogue warps (8, or 16 for the instruction-heavy GEGLU epilogue): EW/4 warps share a
 // TMEM lane quarter and take 32-column chunks round-robin.
-template <int MODE, int EW = GEMM_EPI_WARPS>
+// CTA2: CTA-pair mode (cluster of 2, tcgen05.mma.cta_group::2): one work item is a 256 x block_n tile; CTA `rank` owns
+// M tile 2*pm + rank (its 128 rows of A, its 128 accumulator rows, its epilogue) and loads half of the B tile; the
+// leader (rank 0) issues the MMAs for both.  Per SM the tensor core then reads A (16 KB) + HALF a B tile per k-block
+// from shared memory instead of A + a whole one, which is what bounds the 1-CTA kernel at block_n <= 224.
+template <int MODE, int EW = GEMM_EPI_WARPS, bool CTA2 = false>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ GemmKernelParams p) {
   constexpr bool kGeneric = (MODE & EPI_GENERIC) != 0;
@@ -83,7 +87,13 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   constexpr int W_TMA = EW, W_MMA = EW + 1;
-  const int num_tiles = p.n_tiles_m * p.n_tiles_n;
+  // work items: tiles (1-CTA) or tile pairs (CTA2), strided over the CTAs / clusters of the persistent grid
+  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
+  const int n_units = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int unit0 = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int num_items = (CTA2 ? (p.n_tiles_m + 1) / 2 : p.n_tiles_m) * p.n_tiles_n;
+  auto item_mt = [&](int item) { const int q = item / p.n_tiles_n; return CTA2 ? 2 * q + (int)rank : q; };
+  auto item_nt = [&](int item) { return item % p.n_tiles_n; };
   const int nk = p.seg_ntaps[0] * p.seg_ncblk[0] + (p.nseg > 1 ? p.seg_ntaps[1] * p.seg_ncblk[1] : 0);
 
   if (warp == W_TMA && lane == 0) {
@@ -96,14 +106,18 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), EW);   // one arrive per epilogue warp
+      mbar_init(tempty_bar(s), CTA2 ? 2 * EW : EW);   // one arrive per epilogue warp (of both CTAs, on the leader's barrier)
     }
     fence_mbar_init();
     fence_proxy_async_smem();
   }
-  if (warp == W_MMA) tmem_alloc(tmem_ptr_smem, GEMM_TMEM_COLS);
+  if (warp == W_MMA) {
+    if constexpr (CTA2) tmem_alloc_pair(tmem_ptr_smem, GEMM_TMEM_COLS);
+    else tmem_alloc(tmem_ptr_smem, GEMM_TMEM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();     // barriers initialised and tensor memory allocated in BOTH CTAs
+  else __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
@@ -112,10 +126,12 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
     // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
     int stage = 0;
     uint32_t phase = 0;
-    const uint32_t tx_bytes = GEMM_A_BYTES + (uint32_t)p.block_n * GEMM_BLOCK_K * 2;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int mt = tile / p.n_tiles_n;
-      const int nt = tile - mt * p.n_tiles_n;
+    // CTA2: each CTA loads its A tile and HALF of the B tile; all bytes are counted on the leader's full barrier
+    const uint32_t b_rows = CTA2 ? (uint32_t)p.block_n >> 1 : (uint32_t)p.block_n;
+    const uint32_t tx_bytes = (CTA2 ? 2u : 1u) * (GEMM_A_BYTES + b_rows * GEMM_BLOCK_K * 2);
+    for (int item = unit0; item < num_items; item += n_units) {
+      const int mt = item_mt(item);
+      const int nt = item_nt(item);
       int b0 = 0, h0 = 0, w0 = 0;
       if (p.conv) {
         if (p.TB == 1) {
@@ -142,12 +158,22 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
             if (elect_one()) {
               const uint32_t sa = smem_base + (uint32_t)stage * STAGE_BYTES;
               const uint32_t sb = sa + GEMM_A_BYTES;
-              mbar_expect_tx(full_bar(stage), tx_bytes);
-              if (p.conv)
-                tma_load_4d(tm, sa, full_bar(stage), coff + cb * GEMM_BLOCK_K, w0 + dw, h0 + dh, b0);
-              else
-                tma_load_2d(tm, sa, full_bar(stage), coff + cb * GEMM_BLOCK_K, mt * GEMM_BLOCK_M);
-              tma_load_2d(&maps.b, sb, full_bar(stage), kb * GEMM_BLOCK_K, nt * p.block_n);
+              if constexpr (CTA2) {
+                const uint32_t lbar = mapa_shared(full_bar(stage), 0);      // the leader's full barrier
+                if (rank == 0) mbar_expect_tx(full_bar(stage), tx_bytes);
+                if (p.conv)
+                  tma_load_4d_pair(tm, sa, lbar, coff + cb * GEMM_BLOCK_K, w0 + dw, h0 + dh, b0);
+                else
+                  tma_load_2d_pair(tm, sa, lbar, coff + cb * GEMM_BLOCK_K, mt * GEMM_BLOCK_M);
+                tma_load_2d_pair(&maps.b, sb, lbar, kb * GEMM_BLOCK_K, nt * p.block_n + (int)(rank * b_rows));
+              } else {
+                mbar_expect_tx(full_bar(stage), tx_bytes);
+                if (p.conv)
+                  tma_load_4d(tm, sa, full_bar(stage), coff + cb * GEMM_BLOCK_K, w0 + dw, h0 + dh, b0);
+                else
+                  tma_load_2d(tm, sa, full_bar(stage), coff + cb * GEMM_BLOCK_K, mt * GEMM_BLOCK_M);
+                tma_load_2d(&maps.b, sb, full_bar(stage), kb * GEMM_BLOCK_K, nt * p.block_n);
+              }
             }
             __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -155,16 +181,16 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
         }
       }
     }
-  } else if (warp == W_MMA) {
-    // ===================== MMA issuer =====================
+  } else if (warp == W_MMA && (!CTA2 || rank == 0)) {
+    // ===================== MMA issuer (CTA2: the leader CTA only) =====================
     // The whole warp runs the (warp-uniform) loop so that descriptors live in uniform registers; one
     // elected lane issues tcgen05.mma / tcgen05.commit.
     int stage = 0;
     uint32_t phase = 0;
-    const uint32_t idesc = make_idesc_f16(GEMM_BLOCK_M, (uint32_t)p.block_n, true);
+    const uint32_t idesc = make_idesc_f16(CTA2 ? 2 * GEMM_BLOCK_M : GEMM_BLOCK_M, (uint32_t)p.block_n, true);
     const uint64_t desc_a0 = make_smem_desc(smem_base, 16, 1024, SWZ_128B);
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int item = unit0; item < num_items; item += n_units, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(tempty_bar(as), aphase ^ 1u);
@@ -180,16 +206,22 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
           for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in the
             // (addr >> 4) start-address field
-            umma_f16_ss(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            if constexpr (CTA2) umma_f16_ss_pair(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            else umma_f16_ss(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
           }
-          umma_commit(empty_bar(stage));       // frees the smem slot when these MMAs retire
-          if (kb == nk - 1) umma_commit(tfull_bar(as));   // accumulator ready for the epilogue
+          if constexpr (CTA2) {
+            umma_commit_pair(empty_bar(stage));                     // frees the smem slot of BOTH CTAs
+            if (kb == nk - 1) umma_commit_pair(tfull_bar(as));      // accumulators ready for both epilogues
+          } else {
+            umma_commit(empty_bar(stage));       // frees the smem slot when these MMAs retire
+            if (kb == nk - 1) umma_commit(tfull_bar(as));   // accumulator ready for the epilogue
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
-  } else {
+  } else if (warp < EW) {
     // ===================== epilogue warps (0..EW-1) =====================
     // Two warps per TMEM lane quarter; each takes every other 32-column chunk.  Accumulators go
     // TMEM -> registers (thread = row) -> a per-warp swizzled smem tile -> registers in a
@@ -213,7 +245,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
     constexpr bool kPipeRes = !kGeneric && (MODE & EPI_RES_F32) != 0;
     constexpr int CSTEP = EW / 4;
     float4 resn[8];
-    int pf_tile = -1, pf_c = -1;
+    int pf_item = -1, pf_c = -1;
     auto load_res = [&](int mt_, int nt_, int c_, float4 (&dst)[8]) {
       const int r0 = mt_ * GEMM_BLOCK_M + quarter * 32 + (lane >> 3);
       const int col_ = nt_ * p.block_n + c_ * 32 + 4 * (lane & 7);
@@ -226,9 +258,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
       }
     };
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int mt = tile / p.n_tiles_n;
-      const int nt = tile - mt * p.n_tiles_n;
+    const uint32_t tempty_leader0 = CTA2 ? mapa_shared(tempty_bar(0), 0) : 0u;     // the leader's tmem_empty barriers
+    for (int item = unit0; item < num_items; item += n_units, ++it) {
+      const int mt = item_mt(item);
+      const int nt = item_nt(item);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int row0 = mt * GEMM_BLOCK_M + quarter * 32;
@@ -306,24 +339,24 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
           const bool lane_ok = col < p.N;
           float4 resv[8];
           if constexpr (kPipeRes) {
-            if (pf_tile == tile && pf_c == c) {
+            if (pf_item == item && pf_c == c) {
 #pragma unroll
               for (int itr = 0; itr < 8; ++itr) resv[itr] = resn[itr];
             } else {
               load_res(mt, nt, c, resv);
             }
             // this warp's next chunk: same tile, or its first chunk of the CTA's next tile
-            int ntile = tile, nc = c + CSTEP;
+            int nitem = item, nc = c + CSTEP;
             if (nc >= p.block_n / 32 || nt * p.block_n + nc * 32 >= p.N) {
-              ntile = tile + (int)gridDim.x;
+              nitem = item + n_units;
               nc = (half + it + 1) % CSTEP;
             }
-            pf_tile = -1;
-            if (ntile < num_tiles) {
-              const int nmt = ntile / p.n_tiles_n, nnt = ntile - nmt * p.n_tiles_n;
+            pf_item = -1;
+            if (nitem < num_items) {
+              const int nmt = item_mt(nitem), nnt = item_nt(nitem);
               if (nc < p.block_n / 32 && nnt * p.block_n + nc * 32 < p.N) {
                 load_res(nmt, nnt, nc, resn);
-                pf_tile = ntile;
+                pf_item = nitem;
                 pf_c = nc;
               }
             }
@@ -553,15 +586,20 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
       if (!waited) { mbar_wait(tfull_bar(as), aphase); tc_fence_after(); }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (lane == 0) {
+        if constexpr (CTA2) mbar_arrive_cluster(tempty_leader0 + 8u * (uint32_t)as);
+        else mbar_arrive(tempty_bar(as));
+      }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();     // the peer's shared / tensor memory stays alive until the leader's MMAs retired
+  else __syncthreads();
   if (warp == W_MMA) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, GEMM_TMEM_COLS);
+    if constexpr (CTA2) tmem_dealloc_pair(tmem_base, GEMM_TMEM_COLS);
+    else tmem_dealloc(tmem_base, GEMM_TMEM_COLS);
   }
 }
 
@@ -591,6 +629,17 @@ static int bn_override(int N) {
   for (int i = 0; i < n; ++i)
     if (keys[i] == N) return vals[i];
   return 0;
+}
+
+// tuning hook: DFB_GEMM_CTA_GROUP=1|2 forces the 1-CTA / CTA-pair kernel wherever the caller leaves it automatic
+static int cta_group_override() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DFB_GEMM_CTA_GROUP");
+    v = e ? atoi(e) : 0;
+    if (v < 0 || v > 2) v = 0;
+  }
+  return v;
 }
 
 static int choose_block_n(int N) {
@@ -628,6 +677,7 @@ extern "C" int dfb_gemm(const dfb_gemm_params* q, void* stream_) {
   kp.M = q->M;
   kp.N = q->N;
   int bn = q->block_n > 0 ? q->block_n : choose_block_n(q->N);
+  DFB_REQUIRE(q->cta_group >= 0 && q->cta_group <= 2, "dfb_gemm: cta_group must be 0 (auto), 1 or 2");
   DFB_REQUIRE(bn % 32 == 0 && bn >= 32 && bn <= GEMM_MAX_BLOCK_N, "dfb_gemm: block_n must be a multiple of 32 in [32,256]");
   kp.block_n = bn;
   // smem ring: stage = A tile (16 KB) + B tile (block_n x 128 B, a multiple of 1 KB because block_n % 32 == 0, which keeps
@@ -677,6 +727,13 @@ extern "C" int dfb_gemm(const dfb_gemm_params* q, void* stream_) {
     boxA[0] = GEMM_BLOCK_K; boxA[1] = GEMM_BLOCK_M;
   }
 
+  // CTA-pair mode (cluster of 2, cta_group::2 MMA): when the problem has at least two waves of 256-row work items;
+  // smaller problems keep the finer 1-CTA tiling.  q->cta_group / DFB_GEMM_CTA_GROUP force either.
+  const int n_pair_items = ((kp.n_tiles_m + 1) / 2) * kp.n_tiles_n;
+  int cta_group = q->cta_group > 0 ? q->cta_group : cta_group_override();
+  if (cta_group == 0) cta_group = (kp.n_tiles_m >= 2 && n_pair_items >= num_sms()) ? 2 : 1;
+  const bool pair = cta_group == 2;
+
   int kp_total = 0;
   for (int s = 0; s < q->nseg; ++s) {
     DFB_REQUIRE(q->a[s] != nullptr, "dfb_gemm: null A segment");
@@ -714,7 +771,7 @@ extern "C" int dfb_gemm(const dfb_gemm_params* q, void* stream_) {
   {
     uint64_t dims[2] = {(uint64_t)q->w_ld, (uint64_t)q->N};
     uint64_t str[1] = {(uint64_t)q->w_ld * 2};
-    uint32_t box[2] = {GEMM_BLOCK_K, (uint32_t)bn};
+    uint32_t box[2] = {GEMM_BLOCK_K, (uint32_t)(pair ? bn / 2 : bn)};       // CTA pair: each CTA loads half of the B tile
     int rc = make_tmap(&maps.b, q->w, 2, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != DFB_OK) return rc;
   }
@@ -763,15 +820,38 @@ extern "C" int dfb_gemm(const dfb_gemm_params* q, void* stream_) {
     }
   }
   const int num_tiles = kp.n_tiles_m * kp.n_tiles_n;
-  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  if (pair) {
+    const int clusters = n_pair_items < num_sms() / 2 ? n_pair_items : num_sms() / 2;
+    grid = 2 * clusters;
+  }
   static bool attr_done[64] = {false};
   int dev = 0;
   DFB_CHECK_CUDA(cudaGetDevice(&dev));
+  cudaLaunchConfig_t lc;
+  memset(&lc, 0, sizeof(lc));
+  cudaLaunchAttribute lattr[1];
+  lattr[0].id = cudaLaunchAttributeClusterDimension;
+  lattr[0].val.clusterDim.x = 2;
+  lattr[0].val.clusterDim.y = 1;
+  lattr[0].val.clusterDim.z = 1;
+  lc.gridDim = dim3((unsigned)grid, 1, 1);
+  lc.dynamicSmemBytes = GEMM_SMEM_BYTES;
+  lc.stream = stream;
+  lc.attrs = lattr;
+  lc.numAttrs = 1;
 #define DFB_GEMM_CASE(M_)                                                                                        \
   case M_: {                                                                                                     \
     constexpr int EW_ = ((M_) == EPI_GEGLU) ? 16 : GEMM_EPI_WARPS;                                                 \
-    if (first) DFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<(M_), EW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES)); \
-    if (launch) gemm_tcgen05_kernel<(M_), EW_><<<grid, 64 + 32 * EW_, GEMM_SMEM_BYTES, stream>>>(maps, kp);        \
+    if (first) {                                                                                                 \
+      DFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<(M_), EW_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES)); \
+      DFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<(M_), EW_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));  \
+    }                                                                                                            \
+    if (launch && !pair) gemm_tcgen05_kernel<(M_), EW_, false><<<grid, 64 + 32 * EW_, GEMM_SMEM_BYTES, stream>>>(maps, kp); \
+    if (launch && pair) {                                                                                        \
+      lc.blockDim = dim3(64 + 32 * EW_, 1, 1);                                                                   \
+      DFB_CHECK_CUDA(cudaLaunchKernelEx(&lc, gemm_tcgen05_kernel<(M_), EW_, true>, maps, kp));                   \
+    }                                                                                                            \
   } break;
   const bool need_attr = dev >= 0 && dev < 64 && !attr_done[dev];
   for (int pass = need_attr ? 0 : 1; pass < 2; ++pass) {

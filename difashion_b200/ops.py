@@ -113,7 +113,7 @@ def gemm(a: Sequence[torch.Tensor], w: torch.Tensor, n: int, *, out: torch.Tenso
          a_c: Optional[Sequence[int]] = None, conv_geom: Optional[Tuple[int, int, int]] = None,
          bias: Optional[torch.Tensor] = None, rowbias: Optional[torch.Tensor] = None,
          rows_per_batch: int = 1, residual: Optional[torch.Tensor] = None, geglu: bool = False,
-         block_n: int = 0, act: int = 0, gn_partial: Optional[torch.Tensor] = None) -> torch.Tensor:
+         block_n: int = 0, act: int = 0, gn_partial: Optional[torch.Tensor] = None, cta_group: int = 0) -> torch.Tensor:
     """``out = epilogue(A @ w.T)`` on tcgen05 tensor cores (see ``dfb_gemm`` in include/dfb200.h).
 
     a:    1 or 2 bf16 operands; each ``[M, C]`` (plain) or ``[B, H, W, C]`` (conv), last dim
@@ -167,6 +167,7 @@ def gemm(a: Sequence[torch.Tensor], w: torch.Tensor, n: int, *, out: torch.Tenso
     p.geglu = 1 if geglu else 0
     p.act = act
     p.block_n = block_n
+    p.cta_group = cta_group
     if gn_partial is not None:
         assert gn_partial.dtype == torch.float32 and gn_partial.numel() >= (m_rows // 32) * (n // 2) * 2
         p.gn_partial = gn_partial.data_ptr()

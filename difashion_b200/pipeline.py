@@ -77,6 +77,8 @@ class _Chunk:
     kv_store: dict = field(default_factory=dict)
     graph: Optional[torch.cuda.CUDAGraph] = None
     eps: Optional[torch.Tensor] = None
+    ws: Optional[Workspace] = None             # per-stream workspace when the chunks of a step run concurrently
+    launches: int = 0
 
 
 class _State:
@@ -94,12 +96,17 @@ class B200DiFashionPipeline:
 
     def __init__(self, unet: B200UNet2DConditionModel, mutual_encoder: Optional[MutualEncoder], scheduler,
                  eta_mutual: float = 0.1, use_history: bool = True, use_mutual_guidance: bool = True,
-                 max_rows: int = 256, use_cuda_graph: bool = True):
+                 max_rows: int = 256, use_cuda_graph: bool = True, streams: int = 1):
         self.unet, self.mutual_encoder, self.scheduler = unet, mutual_encoder, scheduler
         self.eta_mutual = float(eta_mutual)
         self.use_history, self.use_mutual_guidance = use_history, use_mutual_guidance
         self.max_rows = int(max_rows)
         self.use_cuda_graph = use_cuda_graph
+        # streams > 1: the row chunks of one step run on that many CUDA streams inside ONE graph (fork / join), each
+        # stream with its own workspace, so that the HBM-bound kernels of one chunk (GroupNorm / LayerNorm / layout
+        # kernels: no shared memory, they co-reside with a persistent GEMM CTA) overlap the tensor-bound kernels of
+        # another.  Needs use_cuda_graph and >= 2 chunks (max_rows < rows of the batch).
+        self.streams = max(1, int(streams))
         self._states = {}
         self.last_step_launches = 0          # kernels launched per denoising step (counted at capture / eager run)
 
@@ -110,9 +117,10 @@ class B200DiFashionPipeline:
         x = st.latents[ch.n0:ch.n1]
         m = st.m[ch.n0:ch.n1] if st.m is not None else None
         hist = st.hist[ch.n0:ch.n1] if st.hist is not None else None
-        x_in = st.ws.get("pipe_x_in", (st.nb * n, st.size, st.size, 8), self.unet._op_dtype)
+        ws = ch.ws if ch.ws is not None else st.ws
+        x_in = ws.get("pipe_x_in", (st.nb * n, st.size, st.size, 8), self.unet._op_dtype)
         ops.mutual_blend(x, m, hist, st.null, self.eta_mutual, st.use_m, st.use_h, x_in)
-        return self.unet.forward_nhwc(x_in, st.t_dev[: st.nb * n], ch.ctx_bf16, ch.kv_store, st.ws)
+        return self.unet.forward_nhwc(x_in, st.t_dev[: st.nb * n], ch.ctx_bf16, ch.kv_store, ws)
 
     def _mutual(self, st):
         if st.m is None:
@@ -122,7 +130,7 @@ class B200DiFashionPipeline:
 
     def _state(self, dev, n, n_given, olen, size, nb, S, D, plan) -> "_State":
         key = (str(dev), n, n_given, olen, size, nb, S, D, tuple(map(tuple, plan[:3])), self.use_history,
-               self.use_mutual_guidance, self.max_rows, str(self.unet._op_dtype))
+               self.use_mutual_guidance, self.max_rows, str(self.unet._op_dtype), self.streams)
         st = self._states.get(key)
         if st is not None:
             return st
@@ -152,6 +160,12 @@ class B200DiFashionPipeline:
             rows = nb * (n1 - n0)
             st.chunks.append(_Chunk(n0, n1, torch.empty(rows, S, D, dtype=torch.float32, device=dev),
                                     torch.empty(rows, S, D, dtype=self.unet._op_dtype, device=dev)))
+        st.multi = self.streams > 1 and self.use_cuda_graph and len(st.chunks) > 1
+        if st.multi:
+            st.side = [torch.cuda.Stream(device=dev) for _ in range(self.streams)]
+            for i, ch in enumerate(st.chunks):
+                ch.ws = self.unet.workspace(("pipe", nb, min(n, per), size, str(self.unet._op_dtype), "stream", i % self.streams), dev)
+        st.step_graph = None
         st.warm = False
         self._states[key] = st
         return st
@@ -218,8 +232,31 @@ class B200DiFashionPipeline:
         self._mutual(st)
         step_launches = ops.launch_count() - c0
         eps_all = []
+        if st.multi:
+            # one graph for the UNet of every chunk: fork onto the side streams, join back (see __init__)
+            if st.step_graph is None:
+                for ch in st.chunks:
+                    ch.eps = torch.empty_like(self._chunk_forward(ch, st))      # warm-up; the chunk's own eps buffer
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    cur = torch.cuda.current_stream()
+                    for s_ in st.side:
+                        s_.wait_stream(cur)
+                    for i, ch in enumerate(st.chunks):
+                        c1 = ops.launch_count()
+                        with torch.cuda.stream(st.side[i % self.streams]):
+                            ch.eps.copy_(self._chunk_forward(ch, st))    # the result is a workspace buffer shared by the stream's chunks
+                        ch.launches = ops.launch_count() - c1
+                    for s_ in st.side:
+                        cur.wait_stream(s_)
+                st.step_graph = g
+            st.step_graph.replay()
         for ch in st.chunks:
-            if self.use_cuda_graph and ch.graph is None:
+            if st.multi:
+                eps = ch.eps
+                step_launches += ch.launches
+            elif self.use_cuda_graph and ch.graph is None:
                 # warm-up (allocates workspaces, sets kernel attributes), then capture this chunk's step
                 self._chunk_forward(ch, st)
                 torch.cuda.synchronize()
@@ -228,7 +265,9 @@ class B200DiFashionPipeline:
                 with torch.cuda.graph(g):
                     ch.eps = self._chunk_forward(ch, st)
                 ch.graph, ch.launches = g, ops.launch_count() - c1
-            if ch.graph is not None:
+            if st.multi:
+                pass
+            elif ch.graph is not None:
                 ch.graph.replay()
                 eps = ch.eps
                 step_launches += ch.launches

@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define DFB200_ABI_VERSION 3
+#define DFB200_ABI_VERSION 4
 
 #define DFB_OK 0
 #define DFB_ERR_INVALID (-1)
@@ -91,6 +91,8 @@ typedef struct dfb_gemm_params {
   float* gn_partial;     /* NULL, or fp32 [M/32, N/2, 2]: per (32-row block, channel pair) sum and sum of
                             squares of the fp32 output, emitted from the epilogue for a following GroupNorm
                             (dfb_groupnorm_fused); needs fp32 output, M % 32 == 0, N % 4 == 0            */
+  int32_t cta_group;     /* 0 = automatic; 1 = one CTA per 128-row tile; 2 = CTA pair (cluster of 2 on one TPC,
+                            tcgen05.mma.cta_group::2 over 256 rows, each CTA feeding half of the B tile)  */
 } dfb_gemm_params;
 
 int dfb_gemm(const dfb_gemm_params* p, void* stream);

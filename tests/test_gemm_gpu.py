@@ -189,3 +189,87 @@ def test_gemm_geglu_many_tiles_matches_exact_erf_gelu():
     # the erf-GELU approximation error (<= 2.7e-5 abs) must stay far below the bf16 output rounding
     err = (out.double() - ref).abs()
     assert float((err - 2.0 ** -8 * ref.abs()).max()) < 2e-4
+
+
+# ------------------------------------------------------------------------------------------------
+# CTA-pair kernel (cluster of 2, tcgen05.mma.cta_group::2): forced with cta_group=2 on shapes of every size, incl.
+# an odd number of 128-row tiles (the second CTA of the last pair owns a tile that is entirely out of range)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K,bn", [(256, 64, 64, 0), (128, 32, 64, 32), (384, 320, 320, 0), (1000, 640, 1280, 0), (77, 100, 768, 0),
+                                     (4096, 1280, 320, 0), (40000, 320, 384, 0), (3 * 128 * 74 + 5, 256, 128, 0)])
+def test_pair_plain_gemm_fp32_out(M, N, K, bn):
+    ops = _ops()
+    a = _rand((M, K), 1).bfloat16().cuda()
+    w = _rand((N, K), 2, K ** -0.5).cuda()
+    wp = ops.pack_linear(w)
+    out = torch.empty(M, N, dtype=torch.float32, device="cuda")
+    ref1 = torch.empty_like(out)
+    ops.gemm([a], wp, N, out=out, block_n=bn, cta_group=2)
+    ops.gemm([a], wp, N, out=ref1, block_n=bn, cta_group=1)
+    torch.cuda.synchronize()
+    ref = a.double() @ wp[:, :K].double().t()
+    assert rel_l2(out, ref) < 1e-5, err_report(out, ref, f"pair gemm {M}x{N}x{K}")
+    assert torch.equal(out, ref1)                      # same MMA order per output row: bitwise the 1-CTA result
+
+
+def test_pair_epilogues_residual_rowbias_geglu_gn_partials():
+    ops = _ops()
+    # fp32 residual (pipelined prefetch across work items) + bias, in place, many tiles
+    M, N, K = 148 * 128 * 3 + 64, 320, 384
+    a = _rand((M, K), 3).bfloat16().cuda()
+    w = ops.pack_linear(_rand((N, K), 4, K ** -0.5).cuda())
+    bias, res = _rand((N,), 5).cuda(), _rand((M, N), 6).cuda()
+    ref = a.double() @ w.double().t() + bias.double() + res.double()
+    out = res.clone()
+    ops.gemm([a], w, N, out=out, bias=bias, residual=out, cta_group=2)
+    assert rel_l2(out, ref) < 1e-5, err_report(out, ref, "pair residual")
+    outb = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    ops.gemm([a], w, N, out=outb, bias=bias, cta_group=2)
+    assert rel_l2(outb, a.double() @ w.double().t() + bias.double()) < 3e-3
+    # row bias + GroupNorm partial statistics
+    B, S = 6, 1024
+    a2 = _rand((B * S, 320), 7).bfloat16().cuda()
+    w2 = ops.pack_linear(_rand((320, 320), 8, 320 ** -0.5).cuda())
+    rb = _rand((B, 320), 9).cuda()
+    o1, o2 = torch.empty(B * S, 320, dtype=torch.float32, device="cuda"), torch.empty(B * S, 320, dtype=torch.float32, device="cuda")
+    p1 = torch.zeros(ops.gn_partial_shape(B * S, 320), dtype=torch.float32, device="cuda")
+    p2 = torch.zeros_like(p1)
+    ops.gemm([a2], w2, 320, out=o1, rowbias=rb, rows_per_batch=S, gn_partial=p1, cta_group=1)
+    ops.gemm([a2], w2, 320, out=o2, rowbias=rb, rows_per_batch=S, gn_partial=p2, cta_group=2)
+    assert torch.equal(o1, o2) and torch.equal(p1, p2)
+    assert rel_l2(o2, a2.double() @ w2.double().t() + rb.double().repeat_interleave(S, 0)) < 1e-5
+    # GEGLU (16 epilogue warps) and an activation (generic epilogue)
+    C = 320
+    a3 = _rand((3000, C), 10).bfloat16().cuda()
+    wg, bg = ops.pack_geglu(_rand((8 * C, C), 11, C ** -0.5), _rand((8 * C,), 12, 0.1))
+    g1, g2 = torch.empty(3000, 4 * C, dtype=torch.bfloat16, device="cuda"), torch.empty(3000, 4 * C, dtype=torch.bfloat16, device="cuda")
+    ops.gemm([a3], wg.cuda(), 8 * C, out=g1, bias=bg.cuda(), geglu=True, cta_group=1)
+    ops.gemm([a3], wg.cuda(), 8 * C, out=g2, bias=bg.cuda(), geglu=True, cta_group=2)
+    assert torch.equal(g1, g2)
+    s1, s2 = torch.empty(3000, 320, dtype=torch.bfloat16, device="cuda"), torch.empty(3000, 320, dtype=torch.bfloat16, device="cuda")
+    ops.gemm([a3], w2, 320, out=s1, bias=bias, act=ops.ACT_SILU, cta_group=1)
+    ops.gemm([a3], w2, 320, out=s2, bias=bias, act=ops.ACT_SILU, cta_group=2)
+    torch.cuda.synchronize()
+    assert torch.equal(s1, s2)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(3, 64, 64, 64, 320), (5, 32, 32, 128, 640), (7, 16, 16, 64, 96), (37, 8, 8, 64, 128), (1, 4, 256, 64, 64)])
+def test_pair_conv3x3_with_shortcut_segment(B, H, W, Cin, Cout):
+    """Implicit-GEMM conv (4-D TMA windows, zero fill = padding) + 1x1 shortcut segment on the CTA-pair kernel;
+    odd tile counts and images packed several per tile."""
+    ops = _ops()
+    x = _rand((B, Cin, H, W), 13).bfloat16().cuda()
+    xs = _rand((B, 64, H, W), 14).bfloat16().cuda()
+    w = _rand((Cout, Cin, 3, 3), 15, (9 * Cin) ** -0.5).cuda()
+    wsc = _rand((Cout, 64, 1, 1), 16, 0.125).cuda()
+    bias = _rand((Cout,), 17).cuda()
+    wp = torch.cat([ops.pack_conv3x3(w), ops.pack_linear(wsc)], 1).contiguous()
+    xn, xsn = x.permute(0, 2, 3, 1).contiguous(), xs.permute(0, 2, 3, 1).contiguous()
+    o1 = torch.empty(B, H, W, Cout, dtype=torch.float32, device="cuda")
+    o2 = torch.empty_like(o1)
+    ops.gemm([xn, xsn], wp, Cout, out=o1, taps=[ops.TAPS_3X3, ops.TAP_CENTER], conv_geom=(B, H, W), bias=bias, cta_group=1)
+    ops.gemm([xn, xsn], wp, Cout, out=o2, taps=[ops.TAPS_3X3, ops.TAP_CENTER], conv_geom=(B, H, W), bias=bias, cta_group=2)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.double(), w.bfloat16().double(), padding=1) + F.conv2d(xs.double(), wsc.bfloat16().double()) + bias.double()[None, :, None, None]
+    assert rel_l2(o2.permute(0, 3, 1, 2), ref) < 1e-5, err_report(o2.reshape(-1, Cout), ref.permute(0, 2, 3, 1).reshape(-1, Cout), "pair conv")
+    assert torch.equal(o1, o2)

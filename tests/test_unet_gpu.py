@@ -219,3 +219,22 @@ def test_attn_processor_on_foreign_attention_module():
         got = proc(attn_cuda, x.cuda(), encoder_hidden_states=None if ctx is None else ctx.cuda())
         assert got.shape == ref.shape and got.dtype == torch.float32
         assert rel_l2(got.cpu(), ref) <= 1e-2
+
+
+def test_multi_stream_chunks_bitwise_equal_single_stream():
+    """streams=2: the row chunks of a step run concurrently on two streams inside one graph (own workspaces);
+    kernels are deterministic and rows independent, so the latents are bitwise those of the sequential path."""
+    from difashion_b200.mutual import MutualEncoder
+    from difashion_b200.pipeline import B200DiFashionPipeline
+    from difashion_b200.schedulers import B200DDIMScheduler
+    oracle, unet = _mk("tiny")
+    cfg = oracle.cfg
+    me = MutualEncoder(latent_size=cfg.sample_size, hid_dim=64).cuda()
+    olists = torch.zeros(5, 4, dtype=torch.long)                       # 20 items -> 80 rows; max_rows 16 -> 5 chunks
+    inp = _gen_inputs(cfg, olists)
+    outs = []
+    for streams in (1, 2, 3):
+        pipe = B200DiFashionPipeline(unet, me, B200DDIMScheduler(), max_rows=16, streams=streams)
+        outs.append(pipe.generate(**inp, num_inference_steps=50, max_steps=4, device="cuda").clone())
+        assert (streams > 1) == bool(pipe._states[next(iter(pipe._states))].multi)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
