@@ -1,8 +1,9 @@
 // Persistent warp-specialised tcgen05 GEMM / implicit-GEMM convolution for sm_100a.
 //
-//   warp EW     : TMA producer  (A tile 128x64 bf16 via 2-D or 4-D tiled tensor map, OOB = zero
-//                 gives the 3x3 'same' padding for free; B tile block_n x 64)
-//   warp EW+1   : TMEM allocator + single-lane tcgen05.mma issuer (M=128, N=block_n, K=16)
+//   warp EW     : TMA producer A (tile 128x64 bf16 via 2-D or 4-D tiled tensor map, OOB = zero
+//                 gives the 3x3 'same' padding for free)
+//   warp EW+1   : TMA producer B (tile block_n x 64)
+//   warp EW+2   : TMEM allocator + single-lane tcgen05.mma issuer (M=128, N=block_n, K=16)
 //   warps 0..EW-1: epilogue (tcgen05.ld -> registers -> swizzled smem transpose -> row-coalesced
 //                 bias / time-embedding row bias / activation / residual / GEGLU -> bf16 or fp32
 //                 global stores touching full 128-byte rows)
@@ -27,7 +28,7 @@ constexpr int GEMM_B_BYTES = GEMM_MAX_BLOCK_N * GEMM_BLOCK_K * 2;      // 32 KB 
 constexpr int GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES;          // 48 KB
 constexpr int GEMM_EPI_WARPS = 8;
 constexpr int GEMM_EPI_STAGE_BYTES = 4096;                              // per-warp 32x32 fp32 transpose tile
-constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
+constexpr int GEMM_THREADS = 96 + 32 * GEMM_EPI_WARPS;
 constexpr int GEMM_SMEM_BYTES = 4 * GEMM_STAGE_BYTES + GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;   // 227 KB budget
 constexpr int GEMM_TMEM_COLS = 512;
 
@@ -65,7 +66,7 @@ enum : int { EPI_OUT_F32 = 1, EPI_RES_F32 = 2, EPI_ROWBIAS = 4, EPI_GEGLU = 8, E
 // leader (rank 0) issues the MMAs for both.  Per SM the tensor core then reads A (16 KB) + HALF a B tile per k-block
 // from shared memory instead of A + a whole one, which is what bounds the 1-CTA kernel at block_n <= 224.
 template <int MODE, int EW = GEMM_EPI_WARPS, bool CTA2 = false>
-__global__ void __launch_bounds__(64 + 32 * EW, 1)
+__global__ void __launch_bounds__(96 + 32 * EW, 1)
 gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ GemmKernelParams p) {
   constexpr bool kGeneric = (MODE & EPI_GENERIC) != 0;
   extern __shared__ uint8_t smem_raw[];
@@ -86,7 +87,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
   // above the issue-heavy epilogue warps (otherwise their TMA / MMA issue is starved).
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  constexpr int W_TMA = EW, W_MMA = EW + 1;
+  // Two TMA producer warps (A tiles / B tiles): ncu showed ONE producer warp spending ~65 % of its time on the ~64
+  // dependent uniform-datapath instructions of a k-block (address arithmetic, R2UR moves, elect, two UTMALDG), i.e.
+  // ~400 cycles per k-block against 320 cycles of MMA at block_n = 160 — the narrow tiles were producer-issue-bound.
+  constexpr int W_TMA = EW, W_TMA_B = EW + 1, W_MMA = EW + 2;
   // work items: tiles (1-CTA) or tile pairs (CTA2), strided over the CTAs / clusters of the persistent grid
   const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
   const int n_units = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -101,7 +105,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
     if (p.nseg > 1) tma_prefetch_desc(&maps.a[1]);
     tma_prefetch_desc(&maps.b);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), 2);          // one arrive.expect_tx per producer warp (A, B)
       mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -126,9 +130,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
     // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
     int stage = 0;
     uint32_t phase = 0;
-    // CTA2: each CTA loads its A tile and HALF of the B tile; all bytes are counted on the leader's full barrier
-    const uint32_t b_rows = CTA2 ? (uint32_t)p.block_n >> 1 : (uint32_t)p.block_n;
-    const uint32_t tx_bytes = (CTA2 ? 2u : 1u) * (GEMM_A_BYTES + b_rows * GEMM_BLOCK_K * 2);
+    // A tiles.  CTA2: each CTA loads its own A tile; the bytes of both are counted on the leader's full barrier
+    const uint32_t tx_bytes = (CTA2 ? 2u : 1u) * GEMM_A_BYTES;
     for (int item = unit0; item < num_items; item += n_units) {
       const int mt = item_mt(item);
       const int nt = item_nt(item);
@@ -157,7 +160,6 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
             mbar_wait(empty_bar(stage), phase ^ 1u);
             if (elect_one()) {
               const uint32_t sa = smem_base + (uint32_t)stage * STAGE_BYTES;
-              const uint32_t sb = sa + GEMM_A_BYTES;
               if constexpr (CTA2) {
                 const uint32_t lbar = mapa_shared(full_bar(stage), 0);      // the leader's full barrier
                 if (rank == 0) mbar_expect_tx(full_bar(stage), tx_bytes);
@@ -165,20 +167,42 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
                   tma_load_4d_pair(tm, sa, lbar, coff + cb * GEMM_BLOCK_K, w0 + dw, h0 + dh, b0);
                 else
                   tma_load_2d_pair(tm, sa, lbar, coff + cb * GEMM_BLOCK_K, mt * GEMM_BLOCK_M);
-                tma_load_2d_pair(&maps.b, sb, lbar, kb * GEMM_BLOCK_K, nt * p.block_n + (int)(rank * b_rows));
               } else {
                 mbar_expect_tx(full_bar(stage), tx_bytes);
                 if (p.conv)
                   tma_load_4d(tm, sa, full_bar(stage), coff + cb * GEMM_BLOCK_K, w0 + dw, h0 + dh, b0);
                 else
                   tma_load_2d(tm, sa, full_bar(stage), coff + cb * GEMM_BLOCK_K, mt * GEMM_BLOCK_M);
-                tma_load_2d(&maps.b, sb, full_bar(stage), kb * GEMM_BLOCK_K, nt * p.block_n);
               }
             }
             __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
+      }
+    }
+  } else if (warp == W_TMA_B) {
+    // ===================== TMA producer, B tiles (CTA2: this CTA's half of the tile) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t b_rows = CTA2 ? (uint32_t)p.block_n >> 1 : (uint32_t)p.block_n;
+    const uint32_t tx_bytes = (CTA2 ? 2u : 1u) * b_rows * GEMM_BLOCK_K * 2;
+    for (int item = unit0; item < num_items; item += n_units) {
+      const int n0 = item_nt(item) * p.block_n + (int)(rank * b_rows);
+      for (int kb = 0; kb < nk; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        if (elect_one()) {
+          const uint32_t sb = smem_base + (uint32_t)stage * STAGE_BYTES + GEMM_A_BYTES;
+          if constexpr (CTA2) {
+            if (rank == 0) mbar_expect_tx(full_bar(stage), tx_bytes);
+            tma_load_2d_pair(&maps.b, sb, mapa_shared(full_bar(stage), 0), kb * GEMM_BLOCK_K, n0);
+          } else {
+            mbar_expect_tx(full_bar(stage), tx_bytes);
+            tma_load_2d(&maps.b, sb, full_bar(stage), kb * GEMM_BLOCK_K, n0);
+          }
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == W_MMA && (!CTA2 || rank == 0)) {
@@ -727,11 +751,18 @@ extern "C" int dfb_gemm(const dfb_gemm_params* q, void* stream_) {
     boxA[0] = GEMM_BLOCK_K; boxA[1] = GEMM_BLOCK_M;
   }
 
-  // CTA-pair mode (cluster of 2, cta_group::2 MMA): when the problem has at least two waves of 256-row work items;
-  // smaller problems keep the finer 1-CTA tiling.  q->cta_group / DFB_GEMM_CTA_GROUP force either.
+  // CTA-pair mode (cluster of 2, cta_group::2 MMA).  Measured per shape on B200 (profiles/r01_gemm_tile_tuning.md): it
+  // pays for deep problems (K >= 2048: every 3x3 conv; the N = 640 / 1280 convs go from 0.99-1.43 to 1.36-1.60 PFLOP/s)
+  // and for wide ones with K >= 512, and LOSES on the short-K GEMMs (K <= 384: five or six k-blocks per tile, the
+  // coupled epilogues of the two CTAs sit on the critical path; N = 320 with K = 1280 likewise), which stay on the
+  // 1-CTA kernel, as do problems with less than two waves of 256-row work items.  q->cta_group /
+  // DFB_GEMM_CTA_GROUP force either.
   const int n_pair_items = ((kp.n_tiles_m + 1) / 2) * kp.n_tiles_n;
+  long long k_total = 0;
+  for (int s = 0; s < q->nseg; ++s) k_total += (long long)q->ntaps[s] * q->a_c[s];
   int cta_group = q->cta_group > 0 ? q->cta_group : cta_group_override();
-  if (cta_group == 0) cta_group = (kp.n_tiles_m >= 2 && n_pair_items >= num_sms()) ? 2 : 1;
+  if (cta_group == 0)
+    cta_group = (kp.n_tiles_m >= 2 && n_pair_items >= num_sms() && (k_total >= 2048 || (q->N >= 512 && k_total >= 512))) ? 2 : 1;
   const bool pair = cta_group == 2;
 
   int kp_total = 0;
@@ -847,9 +878,9 @@ extern "C" int dfb_gemm(const dfb_gemm_params* q, void* stream_) {
       DFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<(M_), EW_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES)); \
       DFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<(M_), EW_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));  \
     }                                                                                                            \
-    if (launch && !pair) gemm_tcgen05_kernel<(M_), EW_, false><<<grid, 64 + 32 * EW_, GEMM_SMEM_BYTES, stream>>>(maps, kp); \
+    if (launch && !pair) gemm_tcgen05_kernel<(M_), EW_, false><<<grid, 96 + 32 * EW_, GEMM_SMEM_BYTES, stream>>>(maps, kp); \
     if (launch && pair) {                                                                                        \
-      lc.blockDim = dim3(64 + 32 * EW_, 1, 1);                                                                   \
+      lc.blockDim = dim3(96 + 32 * EW_, 1, 1);                                                                   \
       DFB_CHECK_CUDA(cudaLaunchKernelEx(&lc, gemm_tcgen05_kernel<(M_), EW_, true>, maps, kp));                   \
     }                                                                                                            \
   } break;

@@ -41,6 +41,18 @@ for rep in range(2):                           # launch 0 = warm-up, launch 1 = 
         w = ops.pack_conv3x3(rn(640, 640, 3, 3) * (9 * 640) ** -0.5).to(dev)
         out = torch.empty(R, 32, 32, 640, dtype=torch.float32, device=dev)
         ops.gemm([x], w, 640, out=out, taps=[ops.TAPS_3X3], conv_geom=(R, 32, 32), bias=rn(640).to(dev))
+    if "conv320" in which:                     # ResNet conv 320->320 at 64x64 (N = 320: two 160-column tiles), 1-CTA and CTA pair
+        x = rn(R, 64, 64, 320).bfloat16().to(dev)
+        w = ops.pack_conv3x3(rn(320, 320, 3, 3) * (9 * 320) ** -0.5).to(dev)
+        out = torch.empty(R, 64, 64, 320, dtype=torch.float32, device=dev)
+        for cg in (1, 2):
+            ops.gemm([x], w, 320, out=out, taps=[ops.TAPS_3X3], conv_geom=(R, 64, 64), bias=rn(320).to(dev), cta_group=cg)
+    if "conv640" in which:                     # ResNet conv 640->640 at 32x32 (N = 640: three 224-column tiles), 1-CTA and CTA pair
+        x = rn(R, 32, 32, 640).bfloat16().to(dev)
+        w = ops.pack_conv3x3(rn(640, 640, 3, 3) * (9 * 640) ** -0.5).to(dev)
+        out = torch.empty(R, 32, 32, 640, dtype=torch.float32, device=dev)
+        for cg in (1, 2):
+            ops.gemm([x], w, 640, out=out, taps=[ops.TAPS_3X3], conv_geom=(R, 32, 32), bias=rn(640).to(dev), cta_group=cg)
     if "attn" in which:                        # self-attention at 64x64: S = 4096, 8 heads, d = 40 -> 48
         B = max(1, R // 4)
         qkv = rn(B, 4096, 3 * 384).bfloat16().to(dev)
