@@ -178,7 +178,11 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local_smem_addr, uint32
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+  // .relaxed: the barrier only hands tensor-memory columns back to the MMA issuer (tcgen05.wait::ld has completed and
+  // tcgen05.fence::before_thread_sync orders the async proxy); the default .release at cluster scope compiles to
+  // MEMBAR.ALL.GPU + ERRBAR, which made every epilogue warp drain its global stores at the end of each tile (ncu: 7 %
+  // of all samples on the N = 320 conv, and the reason the HBM-bound short-K GEMMs lost in pair mode).
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 // TMA loads of a CTA pair: data lands in the executing CTA's shared memory, the transaction bytes are counted on
 // `cluster_bar` (a shared::cluster address: the leader's barrier)

@@ -666,6 +666,15 @@ static int cta_group_override() {
   return v;
 }
 
+static int q_stages_pair_override() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DFB_GEMM_STAGES_PAIR");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
 static int choose_block_n(int N) {
   if (bn_override(N) > 0) return bn_override(N);
   // cost of one row of output tiles ~ n_tiles * (block_n + 48): executed MMA columns plus a per-tile charge for
@@ -704,18 +713,6 @@ extern "C" int dfb_gemm(const dfb_gemm_params* q, void* stream_) {
   DFB_REQUIRE(q->cta_group >= 0 && q->cta_group <= 2, "dfb_gemm: cta_group must be 0 (auto), 1 or 2");
   DFB_REQUIRE(bn % 32 == 0 && bn >= 32 && bn <= GEMM_MAX_BLOCK_N, "dfb_gemm: block_n must be a multiple of 32 in [32,256]");
   kp.block_n = bn;
-  // smem ring: stage = A tile (16 KB) + B tile (block_n x 128 B, a multiple of 1 KB because block_n % 32 == 0, which keeps
-  // every operand 1024-byte aligned for the 128-byte swizzle).
-  kp.stage_bytes = GEMM_A_BYTES + bn * GEMM_BLOCK_K * 2;
-  {
-    const int budget = GEMM_SMEM_BYTES - GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES - 1024 - 256;
-    int st = budget / kp.stage_bytes;
-    // default depth 4: deeper rings fit for narrow tiles but measured no better (N = 320 convs 8 % slower at 5 stages,
-    // profiles/r01_gemm_tile_tuning.md); DFB_GEMM_STAGES=<n> overrides the cap for tuning
-    const int cap = q_stages_override() > 0 ? q_stages_override() : 4;
-    st = st < cap ? st : cap;
-    kp.stages = st > GEMM_MAX_STAGES ? GEMM_MAX_STAGES : (st < 2 ? 2 : st);
-  }
   kp.n_tiles_n = (q->N + bn - 1) / bn;
   kp.conv = q->conv ? 1 : 0;
   kp.nseg = q->nseg;
@@ -751,19 +748,29 @@ extern "C" int dfb_gemm(const dfb_gemm_params* q, void* stream_) {
     boxA[0] = GEMM_BLOCK_K; boxA[1] = GEMM_BLOCK_M;
   }
 
-  // CTA-pair mode (cluster of 2, cta_group::2 MMA).  Measured per shape on B200 (profiles/r01_gemm_tile_tuning.md): it
-  // pays for deep problems (K >= 2048: every 3x3 conv; the N = 640 / 1280 convs go from 0.99-1.43 to 1.36-1.60 PFLOP/s)
-  // and for wide ones with K >= 512, and LOSES on the short-K GEMMs (K <= 384: five or six k-blocks per tile, the
-  // coupled epilogues of the two CTAs sit on the critical path; N = 320 with K = 1280 likewise), which stay on the
-  // 1-CTA kernel, as do problems with less than two waves of 256-row work items.  q->cta_group /
-  // DFB_GEMM_CTA_GROUP force either.
+  // CTA-pair mode (cluster of 2, cta_group::2 MMA): every problem with at least two waves of 256-row work items.
+  // Measured per shape on B200 (profiles/r01_gemm_tile_tuning.md): the N = 640 / 1280 convs go from 0.99-1.43 to
+  // 1.36-1.60 PFLOP/s; the HBM-bound short-K GEMMs are neutral once the remote tmem_empty arrive is .relaxed.
+  // q->cta_group / DFB_GEMM_CTA_GROUP force either kernel.
   const int n_pair_items = ((kp.n_tiles_m + 1) / 2) * kp.n_tiles_n;
   long long k_total = 0;
   for (int s = 0; s < q->nseg; ++s) k_total += (long long)q->ntaps[s] * q->a_c[s];
   int cta_group = q->cta_group > 0 ? q->cta_group : cta_group_override();
-  if (cta_group == 0)
-    cta_group = (kp.n_tiles_m >= 2 && n_pair_items >= num_sms() && (k_total >= 2048 || (q->N >= 512 && k_total >= 512))) ? 2 : 1;
+  if (cta_group == 0) cta_group = (kp.n_tiles_m >= 2 && n_pair_items >= num_sms()) ? 2 : 1;
   const bool pair = cta_group == 2;
+  // smem ring: stage = A tile (16 KB) + this CTA's B tile (block_n x 128 B, half of that in a CTA pair; a multiple of
+  // 1 KB because block_n % 32 == 0, which keeps every operand 1024-byte aligned for the 128-byte swizzle).
+  kp.stage_bytes = GEMM_A_BYTES + (pair ? bn / 2 : bn) * GEMM_BLOCK_K * 2;
+  {
+    const int budget = GEMM_SMEM_BYTES - GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES - 1024 - 256;
+    int st = budget / kp.stage_bytes;
+    // 1-CTA kernel: depth 4 (deeper rings fit for narrow tiles but measured no better, profiles/r01_gemm_tile_tuning.md).
+    // CTA pair: the half-size B tiles leave room for 5 (block_n 256) to 8 stages, and with two producer warps the deeper
+    // ring pays (268-270 vs 273 ms per step at depth 8 vs 4).  DFB_GEMM_STAGES / DFB_GEMM_STAGES_PAIR override the caps.
+    const int cap = pair ? (q_stages_pair_override() > 0 ? q_stages_pair_override() : 8) : (q_stages_override() > 0 ? q_stages_override() : 4);
+    st = st < cap ? st : cap;
+    kp.stages = st > GEMM_MAX_STAGES ? GEMM_MAX_STAGES : (st < 2 ? 2 : st);
+  }
 
   int kp_total = 0;
   for (int s = 0; s < q->nseg; ++s) {
