@@ -9,7 +9,8 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdfb200.so")
+# DFB200_LIB=<path>: load another build of the library (A/B runs of kernel variants on one GPU box)
+LIB_PATH = os.environ.get("DFB200_LIB") or os.path.join(_HERE, "libdfb200.so")
 
 DTYPE_BF16 = 0
 DTYPE_F32 = 1

@@ -127,82 +127,77 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
   if (warp == W_TMA) {
-    // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
-    int stage = 0;
-    uint32_t phase = 0;
-    // A tiles.  CTA2: each CTA loads its own A tile; the bytes of both are counted on the leader's full barrier
-    const uint32_t tx_bytes = (CTA2 ? 2u : 1u) * GEMM_A_BYTES;
-    for (int item = unit0; item < num_items; item += n_units) {
-      const int mt = item_mt(item);
-      const int nt = item_nt(item);
-      int b0 = 0, h0 = 0, w0 = 0;
-      if (p.conv) {
-        if (p.TB == 1) {
-          b0 = mt / p.tiles_per_img;
-          const int r = mt - b0 * p.tiles_per_img;
-          if (p.w_tiles > 1) {
-            h0 = r / p.w_tiles;
-            w0 = (r - h0 * p.w_tiles) * GEMM_BLOCK_M;
-          } else {
-            h0 = r * p.TH;
-          }
-        } else {
-          b0 = mt * p.TB;
-        }
-      }
-      int kb = 0;
-      for (int s = 0; s < p.nseg; ++s) {
-        const void* tm = &maps.a[s];
-        for (int tap = 0; tap < p.seg_ntaps[s]; ++tap) {
-          const int ti = s * 9 + tap;
-          const int dh = p.tap_dh[ti], dw = p.tap_dw[ti], coff = p.tap_coff[ti];
-          for (int cb = 0; cb < p.seg_ncblk[s]; ++cb, ++kb) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
-            if (elect_one()) {
-              const uint32_t sa = smem_base + (uint32_t)stage * STAGE_BYTES;
-              if constexpr (CTA2) {
-                const uint32_t lbar = mapa_shared(full_bar(stage), 0);      // the leader's full barrier
-                if (rank == 0) mbar_expect_tx(full_bar(stage), tx_bytes);
-                if (p.conv)
-                  tma_load_4d_pair(tm, sa, lbar, coff + cb * GEMM_BLOCK_K, w0 + dw, h0 + dh, b0);
-                else
-                  tma_load_2d_pair(tm, sa, lbar, coff + cb * GEMM_BLOCK_K, mt * GEMM_BLOCK_M);
-              } else {
-                mbar_expect_tx(full_bar(stage), tx_bytes);
-                if (p.conv)
-                  tma_load_4d(tm, sa, full_bar(stage), coff + cb * GEMM_BLOCK_K, w0 + dw, h0 + dh, b0);
-                else
-                  tma_load_2d(tm, sa, full_bar(stage), coff + cb * GEMM_BLOCK_K, mt * GEMM_BLOCK_M);
-              }
+    // ===================== TMA producer, A tiles: ONE lane runs the loop =====================
+    // (ncu: with the warp-uniform loop + elect_one per k-block this warp spent most of its time resolving the ~9
+    // branches / reconvergence points of an iteration, ~250-400 cycles per k-block against 320 cycles of MMA at
+    // block_n = 160; a single-lane loop has no elect, no BSSY/BSYNC, no __syncwarp.)
+    // CTA2: each CTA loads its own A tile; the bytes of both are counted on the leader's full barrier.
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = (CTA2 ? 2u : 1u) * GEMM_A_BYTES;
+      const uint32_t fbar0 = CTA2 ? mapa_shared(full_bar(0), 0) : full_bar(0);      // (the leader's) full barriers
+      for (int item = unit0; item < num_items; item += n_units) {
+        const int mt = item_mt(item);
+        int b0 = 0, h0 = 0, w0 = 0;
+        if (p.conv) {
+          if (p.TB == 1) {
+            b0 = mt / p.tiles_per_img;
+            const int r = mt - b0 * p.tiles_per_img;
+            if (p.w_tiles > 1) {
+              h0 = r / p.w_tiles;
+              w0 = (r - h0 * p.w_tiles) * GEMM_BLOCK_M;
+            } else {
+              h0 = r * p.TH;
             }
-            __syncwarp();
-            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          } else {
+            b0 = mt * p.TB;
+          }
+        }
+        const int row0 = mt * GEMM_BLOCK_M;
+        for (int s = 0; s < p.nseg; ++s) {
+          const void* tm = &maps.a[s];
+          const int ncb = p.seg_ncblk[s];
+          for (int tap = 0; tap < p.seg_ntaps[s]; ++tap) {
+            const int ti = s * 9 + tap;
+            const int cw = w0 + p.tap_dw[ti], ch = h0 + p.tap_dh[ti];
+            int cc = p.tap_coff[ti];
+            for (int cb = 0; cb < ncb; ++cb, cc += GEMM_BLOCK_K) {
+              mbar_wait(empty_bar(stage), phase ^ 1u);
+              const uint32_t sa = smem_base + (uint32_t)stage * STAGE_BYTES;
+              const uint32_t fb = fbar0 + 8u * (uint32_t)stage;
+              if (!CTA2 || rank == 0) mbar_expect_tx(full_bar(stage), tx_bytes);
+              if constexpr (CTA2) {
+                if (p.conv) tma_load_4d_pair(tm, sa, fb, cc, cw, ch, b0);
+                else tma_load_2d_pair(tm, sa, fb, cc, row0);
+              } else {
+                if (p.conv) tma_load_4d(tm, sa, fb, cc, cw, ch, b0);
+                else tma_load_2d(tm, sa, fb, cc, row0);
+              }
+              if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
           }
         }
       }
     }
   } else if (warp == W_TMA_B) {
-    // ===================== TMA producer, B tiles (CTA2: this CTA's half of the tile) =====================
-    int stage = 0;
-    uint32_t phase = 0;
-    const uint32_t b_rows = CTA2 ? (uint32_t)p.block_n >> 1 : (uint32_t)p.block_n;
-    const uint32_t tx_bytes = (CTA2 ? 2u : 1u) * b_rows * GEMM_BLOCK_K * 2;
-    for (int item = unit0; item < num_items; item += n_units) {
-      const int n0 = item_nt(item) * p.block_n + (int)(rank * b_rows);
-      for (int kb = 0; kb < nk; ++kb) {
-        mbar_wait(empty_bar(stage), phase ^ 1u);
-        if (elect_one()) {
+    // ===================== TMA producer, B tiles (CTA2: this CTA's half of the tile); one lane =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t b_rows = CTA2 ? (uint32_t)p.block_n >> 1 : (uint32_t)p.block_n;
+      const uint32_t tx_bytes = (CTA2 ? 2u : 1u) * b_rows * GEMM_BLOCK_K * 2;
+      const uint32_t fbar0 = CTA2 ? mapa_shared(full_bar(0), 0) : full_bar(0);
+      for (int item = unit0; item < num_items; item += n_units) {
+        const int n0 = item_nt(item) * p.block_n + (int)(rank * b_rows);
+        for (int kb = 0; kb < nk; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sb = smem_base + (uint32_t)stage * STAGE_BYTES + GEMM_A_BYTES;
-          if constexpr (CTA2) {
-            if (rank == 0) mbar_expect_tx(full_bar(stage), tx_bytes);
-            tma_load_2d_pair(&maps.b, sb, mapa_shared(full_bar(stage), 0), kb * GEMM_BLOCK_K, n0);
-          } else {
-            mbar_expect_tx(full_bar(stage), tx_bytes);
-            tma_load_2d(&maps.b, sb, full_bar(stage), kb * GEMM_BLOCK_K, n0);
-          }
+          if (!CTA2 || rank == 0) mbar_expect_tx(full_bar(stage), tx_bytes);
+          if constexpr (CTA2) tma_load_2d_pair(&maps.b, sb, fbar0 + 8u * (uint32_t)stage, kb * GEMM_BLOCK_K, n0);
+          else tma_load_2d(&maps.b, sb, fbar0 + 8u * (uint32_t)stage, kb * GEMM_BLOCK_K, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == W_MMA && (!CTA2 || rank == 0)) {
