@@ -397,7 +397,12 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ A
 // PT: the probabilities go back into tensor memory (over the score buffer they came from) and O += P V reads
 // its A operand from TMEM (tcgen05.mma TS form): no P round trip through shared memory, no proxy fence, and the
 // PV MMA no longer pays the 4 KB-per-instruction shared-memory A fetch.
-template <int KV, bool PT>
+// NM ("no max"): the fast path does not track the tile maximum (one FMNMX per score less: 3.5 instead of 4.5 issue slots
+// per element).  Every exponential is >= 0, so the tile's row sum bounds its largest term: a sum <= 2^12 over 64 columns
+// means no term above 2^12, and a sum > 2^12 implies a term above 2^6, i.e. a score more than 6 (log2 units) above the
+// reference max -> the careful path finds the true maximum in the registers and rescales (its threshold is 6 instead
+// of 8 here, so a trigger always rescales and cannot repeat on the next tile).
+template <int KV, bool PT, bool NM = false>
 __global__ void __launch_bounds__(ATT_THREADS, KV == 64 ? 2 : 1)
 attn_fwd_db_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnKernelParams p) {
   constexpr int NST_MAX = 3;
@@ -569,7 +574,7 @@ attn_fwd_db_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const float sv = __uint_as_float(sreg[c * 32 + h * 16 + i]);
-              m8[i & 7] = fmaxf(m8[i & 7], sv);
+              if constexpr (!NM) m8[i & 7] = fmaxf(m8[i & 7], sv);
               pv[i] = ex2f(fmaf(sv, p.scale_log2, -m_ref));
               l8[i & 7] += pv[i];
             }
@@ -585,9 +590,20 @@ attn_fwd_db_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant_
             }
           }
         }
-        mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7]))) * p.scale_log2;
-        careful = __any_sync(0xffffffffu, mx > m_ref + 8.0f);
-        if (!careful) l += ((l8[0] + l8[1]) + (l8[2] + l8[3])) + ((l8[4] + l8[5]) + (l8[6] + l8[7]));
+        const float tsum = ((l8[0] + l8[1]) + (l8[2] + l8[3])) + ((l8[4] + l8[5]) + (l8[6] + l8[7]));
+        if constexpr (NM) {
+          careful = __any_sync(0xffffffffu, !(tsum <= 4096.0f));        // also catches inf / nan
+          if (careful) {                                                   // rare: true maximum from the registers
+            float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+            for (int i = 0; i < KV; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(sreg[i]));
+            mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * p.scale_log2;
+          }
+        } else {
+          mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7]))) * p.scale_log2;
+          careful = __any_sync(0xffffffffu, mx > m_ref + 8.0f);
+        }
+        if (!careful) l += tsum;
       } else {
 #pragma unroll
         for (int c = 0; c < KV / 32; ++c)
@@ -601,7 +617,7 @@ attn_fwd_db_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant_
       }
       if (careful) {
         // new reference max: rescale O (needs every earlier PV retired) and l, redo the tile from registers
-        const bool need = mx > m_ref + 8.0f;
+        const bool need = mx > m_ref + (NM ? 6.0f : 8.0f);
         if (__any_sync(0xffffffffu, need)) {
           const float m_new = need ? mx : m_ref;
           const float alpha = ex2f(m_ref - m_new);     // m_ref = -inf on the first tile -> 0
@@ -1312,6 +1328,7 @@ extern "C" int dfb_attention(const dfb_attn_params* a, void* stream_) {
     DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_db_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_db_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_db_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_db_kernel<64, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_db_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_short_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
@@ -1323,6 +1340,8 @@ extern "C" int dfb_attention(const dfb_attn_params* a, void* stream_) {
     attn_short_kv_kernel<<<gshort, ATT_THREADS, smem, stream>>>(maps, kp);
   } else if (use_split)
     attn_fwd_split_kernel<<<grid, ATT_SPLIT_THREADS, smem, stream>>>(maps, kp);
+  else if (use_db && bkv == 64 && p_tmem && (a->dbg_flags & 128))
+    attn_fwd_db_kernel<64, true, true><<<grid, ATT_THREADS, smem, stream>>>(maps, kp);
   else if (use_db && bkv == 64 && p_tmem)
     attn_fwd_db_kernel<64, true><<<grid, ATT_THREADS, smem, stream>>>(maps, kp);
   else if (use_db && bkv == 64)

@@ -126,7 +126,7 @@ typedef struct dfb_attn_params {
   float scale;            /* softmax scale (true head_dim ** -0.5)                          */
   int32_t block_kv;       /* KV tile (multiple of 16, <= 128); 0 = automatic                */
   int32_t dbg_v_lbo, dbg_v_sbo; /* 0 = default; test hooks for the V descriptor strides     */
-  int32_t dbg_flags;      /* 0 = default; tuning hooks: bit1 one CTA per SM, bit3 single-buffer kernel, bit4 P via smem, bit5 split-KV kernel, bit6 no short-KV kernel, bits 8-11 query tiles per CTA of the short-KV kernel */
+  int32_t dbg_flags;      /* 0 = default; tuning hooks: bit1 one CTA per SM, bit3 single-buffer kernel, bit4 P via smem, bit5 split-KV kernel, bit6 no short-KV kernel, bit7 "no max" fast path (experiment), bits 8-11 query tiles per CTA of the short-KV kernel */
   void* dbg_timeline;     /* NULL, or device buffer of >= 4096 int64: clock64 stamps of CTA (0,0,0) (tuning)  */
   int32_t causal;         /* 1: key j is visible to query i only when j <= i (CLIPTextModel's causal mask,
                              DiFashion/models/difashion.py:339-353); 0 everywhere in the UNet              */
