@@ -40,6 +40,8 @@ struct GemmMaps {
 struct GemmKernelParams {
   int M, N, block_n, n_tiles_m, n_tiles_n;
   int stages, stage_bytes;                    // smem ring: depth and stride (A 16 KB + B block_n x 128 B per stage)
+  int n_sub, acc_ring;                        // MMA column sub-tiles per work item (block_n = n_sub * sub_n <= 512) and
+                                              // accumulator ring depth in tensor memory (2 when 2 * block_n <= 512, else 1)
   int conv, TH, TB, tiles_per_img, w_tiles;   // w_tiles > 1: images wider than 128 pixels, one tile = 128 pixels of a row
   int nseg;
   int seg_ntaps[2];
@@ -185,8 +187,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t b_rows = CTA2 ? (uint32_t)p.block_n >> 1 : (uint32_t)p.block_n;
-      const uint32_t tx_bytes = (CTA2 ? 2u : 1u) * b_rows * GEMM_BLOCK_K * 2;
+      // per MMA sub-tile (sub_n columns) this CTA holds sub_n rows of B, or its half of them in a CTA pair
+      const uint32_t sub_n = (uint32_t)p.block_n / (uint32_t)p.n_sub;
+      const uint32_t b_rows = CTA2 ? sub_n >> 1 : sub_n;
+      const uint32_t tx_bytes = (CTA2 ? 2u : 1u) * (uint32_t)p.n_sub * b_rows * GEMM_BLOCK_K * 2;
       const uint32_t fbar0 = CTA2 ? mapa_shared(full_bar(0), 0) : full_bar(0);
       for (int item = unit0; item < num_items; item += n_units) {
         const int n0 = item_nt(item) * p.block_n + (int)(rank * b_rows);
@@ -194,8 +198,11 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sb = smem_base + (uint32_t)stage * STAGE_BYTES + GEMM_A_BYTES;
           if (!CTA2 || rank == 0) mbar_expect_tx(full_bar(stage), tx_bytes);
-          if constexpr (CTA2) tma_load_2d_pair(&maps.b, sb, fbar0 + 8u * (uint32_t)stage, kb * GEMM_BLOCK_K, n0);
-          else tma_load_2d(&maps.b, sb, fbar0 + 8u * (uint32_t)stage, kb * GEMM_BLOCK_K, n0);
+          for (int sub = 0; sub < p.n_sub; ++sub) {
+            const uint32_t dst = sb + (uint32_t)sub * b_rows * (GEMM_BLOCK_K * 2);
+            if constexpr (CTA2) tma_load_2d_pair(&maps.b, dst, fbar0 + 8u * (uint32_t)stage, kb * GEMM_BLOCK_K, n0 + sub * (int)sub_n);
+            else tma_load_2d(&maps.b, dst, fbar0 + 8u * (uint32_t)stage, kb * GEMM_BLOCK_K, n0 + sub * (int)sub_n);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -206,12 +213,15 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
     // elected lane issues tcgen05.mma / tcgen05.commit.
     int stage = 0;
     uint32_t phase = 0;
-    const uint32_t idesc = make_idesc_f16(CTA2 ? 2 * GEMM_BLOCK_M : GEMM_BLOCK_M, (uint32_t)p.block_n, true);
+    const uint32_t sub_n = (uint32_t)p.block_n / (uint32_t)p.n_sub;
+    const uint32_t idesc = make_idesc_f16(CTA2 ? 2 * GEMM_BLOCK_M : GEMM_BLOCK_M, sub_n, true);
     const uint64_t desc_a0 = make_smem_desc(smem_base, 16, 1024, SWZ_128B);
+    const uint32_t sub_b_step = ((CTA2 ? sub_n >> 1 : sub_n) * (GEMM_BLOCK_K * 2)) >> 4;     // descriptor units between B sub-tiles
+    const bool ring2 = p.acc_ring == 2;
     int it = 0;
     for (int item = unit0; item < num_items; item += n_units, ++it) {
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
+      const int as = ring2 ? (it & 1) : 0;
+      const uint32_t aphase = ring2 ? ((it >> 1) & 1) : (it & 1);
       mbar_wait(tempty_bar(as), aphase ^ 1u);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)as * GEMM_MAX_BLOCK_N;
@@ -227,6 +237,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
             // (addr >> 4) start-address field
             if constexpr (CTA2) umma_f16_ss_pair(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
             else umma_f16_ss(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            if (p.n_sub == 2) {       // second column sub-tile of a wide (257..512) tile: same A tile, next B rows, next TMEM columns
+              if constexpr (CTA2) umma_f16_ss_pair(tmem_d + sub_n, da + (uint64_t)(2 * k), db + (uint64_t)(sub_b_step + 2 * k), idesc, (kb | k) != 0);
+              else umma_f16_ss(tmem_d + sub_n, da + (uint64_t)(2 * k), db + (uint64_t)(sub_b_step + 2 * k), idesc, (kb | k) != 0);
+            }
           }
           if constexpr (CTA2) {
             umma_commit_pair(empty_bar(stage));                     // frees the smem slot of BOTH CTAs
@@ -281,8 +295,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
     for (int item = unit0; item < num_items; item += n_units, ++it) {
       const int mt = item_mt(item);
       const int nt = item_nt(item);
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
+      const int as = p.acc_ring == 2 ? (it & 1) : 0;
+      const uint32_t aphase = p.acc_ring == 2 ? ((it >> 1) & 1) : (it & 1);
       const int row0 = mt * GEMM_BLOCK_M + quarter * 32;
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * GEMM_MAX_BLOCK_N;
       const bool full_rows = row0 + 32 <= p.M;                 // warp-uniform: no row masking needed
@@ -670,6 +684,15 @@ static int q_stages_pair_override() {
   return v;
 }
 
+static bool wide_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DFB_GEMM_WIDE");
+    v = e ? atoi(e) : 1;
+  }
+  return v != 0;
+}
+
 static int choose_block_n(int N) {
   if (bn_override(N) > 0) return bn_override(N);
   // cost of one row of output tiles ~ n_tiles * (block_n + 48): executed MMA columns plus a per-tile charge for
@@ -706,9 +729,8 @@ extern "C" int dfb_gemm(const dfb_gemm_params* q, void* stream_) {
   kp.N = q->N;
   int bn = q->block_n > 0 ? q->block_n : choose_block_n(q->N);
   DFB_REQUIRE(q->cta_group >= 0 && q->cta_group <= 2, "dfb_gemm: cta_group must be 0 (auto), 1 or 2");
-  DFB_REQUIRE(bn % 32 == 0 && bn >= 32 && bn <= GEMM_MAX_BLOCK_N, "dfb_gemm: block_n must be a multiple of 32 in [32,256]");
-  kp.block_n = bn;
-  kp.n_tiles_n = (q->N + bn - 1) / bn;
+  DFB_REQUIRE(bn % 32 == 0 && bn >= 32 && (bn <= GEMM_MAX_BLOCK_N || (bn <= 2 * GEMM_MAX_BLOCK_N && bn % 64 == 0)),
+              "dfb_gemm: block_n must be a multiple of 32 in [32,256], or a multiple of 64 in (256,512] (two MMA sub-tiles)");
   kp.conv = q->conv ? 1 : 0;
   kp.nseg = q->nseg;
 
@@ -747,9 +769,20 @@ extern "C" int dfb_gemm(const dfb_gemm_params* q, void* stream_) {
   // Measured per shape on B200 (profiles/r01_gemm_tile_tuning.md): the N = 640 / 1280 convs go from 0.99-1.43 to
   // 1.36-1.60 PFLOP/s; the HBM-bound short-K GEMMs are neutral once the remote tmem_empty arrive is .relaxed.
   // q->cta_group / DFB_GEMM_CTA_GROUP force either kernel.
-  const int n_pair_items = ((kp.n_tiles_m + 1) / 2) * kp.n_tiles_n;
   long long k_total = 0;
   for (int s = 0; s < q->nseg; ++s) k_total += (long long)q->ntaps[s] * q->a_c[s];
+  // Wide tile for 256 < N <= 512 (the UNet's N = 320 convs): ONE tile of all N columns as two MMA sub-tiles that share
+  // the A tile in shared memory (half the A loads and producer work per flop of the 2 x 160 tiling).  Its accumulators
+  // take 2 * N / 2 ... N <= 512 columns, i.e. the ring is one deep and the epilogue no longer overlaps the next main
+  // loop — worth it only for deep problems (K >= 2048: the epilogue is ~5 % of the main loop).  DFB_GEMM_WIDE=0 disables.
+  if (q->block_n <= 0 && wide_enabled() && q->N > GEMM_MAX_BLOCK_N && q->N <= 2 * GEMM_MAX_BLOCK_N && q->N % 64 == 0 &&
+      k_total >= 2048 && (kp.n_tiles_m + 1) / 2 >= num_sms())
+    bn = q->N;
+  kp.block_n = bn;
+  kp.n_sub = bn > GEMM_MAX_BLOCK_N ? 2 : 1;
+  kp.acc_ring = 2 * bn <= GEMM_TMEM_COLS ? 2 : 1;
+  kp.n_tiles_n = (q->N + bn - 1) / bn;
+  const int n_pair_items = ((kp.n_tiles_m + 1) / 2) * kp.n_tiles_n;
   int cta_group = q->cta_group > 0 ? q->cta_group : cta_group_override();
   if (cta_group == 0) cta_group = (kp.n_tiles_m >= 2 && n_pair_items >= num_sms()) ? 2 : 1;
   const bool pair = cta_group == 2;
@@ -804,7 +837,8 @@ extern "C" int dfb_gemm(const dfb_gemm_params* q, void* stream_) {
   {
     uint64_t dims[2] = {(uint64_t)q->w_ld, (uint64_t)q->N};
     uint64_t str[1] = {(uint64_t)q->w_ld * 2};
-    uint32_t box[2] = {GEMM_BLOCK_K, (uint32_t)(pair ? bn / 2 : bn)};       // CTA pair: each CTA loads half of the B tile
+    const int sub_n = bn / kp.n_sub;
+    uint32_t box[2] = {GEMM_BLOCK_K, (uint32_t)(pair ? sub_n / 2 : sub_n)};  // per MMA sub-tile; CTA pair: each CTA loads half of it
     int rc = make_tmap(&maps.b, q->w, 2, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != DFB_OK) return rc;
   }

@@ -273,3 +273,39 @@ def test_pair_conv3x3_with_shortcut_segment(B, H, W, Cin, Cout):
     ref = F.conv2d(x.double(), w.bfloat16().double(), padding=1) + F.conv2d(xs.double(), wsc.bfloat16().double()) + bias.double()[None, :, None, None]
     assert rel_l2(o2.permute(0, 3, 1, 2), ref) < 1e-5, err_report(o2.reshape(-1, Cout), ref.permute(0, 2, 3, 1).reshape(-1, Cout), "pair conv")
     assert torch.equal(o1, o2)
+
+
+@pytest.mark.parametrize("M,N,K,bn,cg", [(1000, 320, 640, 320, 2), (1000, 320, 640, 320, 1), (4096, 512, 256, 512, 2), (300, 384, 128, 384, 1),
+                                        (128 * 150 * 2 + 17, 320, 384, 320, 2), (5000, 640, 320, 320, 2)])
+def test_wide_tiles_two_mma_subtiles(M, N, K, bn, cg):
+    """block_n in (256, 512]: one work item = two MMA column sub-tiles sharing the A tile, accumulator ring one deep."""
+    ops = _ops()
+    a = _rand((M, K), 21).bfloat16().cuda()
+    w = ops.pack_linear(_rand((N, K), 22, K ** -0.5).cuda())
+    bias, res = _rand((N,), 23).cuda(), _rand((M, N), 24).cuda()
+    out, ref1 = torch.empty(M, N, dtype=torch.float32, device="cuda"), torch.empty(M, N, dtype=torch.float32, device="cuda")
+    ops.gemm([a], w, N, out=out, bias=bias, residual=res, block_n=bn, cta_group=cg)
+    ops.gemm([a], w, N, out=ref1, bias=bias, residual=res, block_n=160 if N % 160 == 0 else 128, cta_group=1)
+    torch.cuda.synchronize()
+    ref = a.double() @ w[:, :K].double().t() + bias.double() + res.double()
+    assert rel_l2(out, ref) < 1e-5, err_report(out, ref, f"wide tile {M}x{N}x{K} bn={bn} cg={cg}")
+    assert torch.equal(out, ref1)
+
+
+def test_wide_tile_is_the_automatic_choice_for_deep_n320_convs():
+    """The UNet's N = 320 3x3 convs (K >= 2880) at full size take the 256 x 320 CTA-pair tile; result bitwise that of
+    the forced 2 x 160 tiling; GroupNorm partials included."""
+    ops = _ops()
+    B, H, W, C = 40, 64, 64, 320
+    x = _rand((B, H, W, C), 25).bfloat16().cuda()
+    w = ops.pack_conv3x3(_rand((C, C, 3, 3), 26, (9 * C) ** -0.5).cuda())
+    bias = _rand((C,), 27).cuda()
+    o1, o2 = torch.empty(B, H, W, C, dtype=torch.float32, device="cuda"), torch.empty(B, H, W, C, dtype=torch.float32, device="cuda")
+    p1 = torch.zeros(ops.gn_partial_shape(B * H * W, C), dtype=torch.float32, device="cuda")
+    p2 = torch.zeros_like(p1)
+    ops.gemm([x], w, C, out=o1, taps=[ops.TAPS_3X3], conv_geom=(B, H, W), bias=bias, gn_partial=p1)                    # automatic
+    ops.gemm([x], w, C, out=o2, taps=[ops.TAPS_3X3], conv_geom=(B, H, W), bias=bias, gn_partial=p2, block_n=160, cta_group=1)
+    torch.cuda.synchronize()
+    assert torch.equal(o1, o2) and torch.equal(p1, p2)
+    ref = F.conv2d(x[:2].cpu().permute(0, 3, 1, 2).double(), _rand((C, C, 3, 3), 26, (9 * C) ** -0.5).bfloat16().double(), bias.cpu().double(), padding=1)
+    assert rel_l2(o1[:2].permute(0, 3, 1, 2).cpu(), ref) < 1e-5
