@@ -15,6 +15,7 @@ from .vae import B200AutoencoderKL, DecoderOutput  # noqa: F401
 from .clip import B200CLIPTextModel  # noqa: F401
 from .generation import B200DiFashion  # noqa: F401
 from .outputs import merge_and_save_images, save_batch_outputs, save_outputs_npy  # noqa: F401
+from . import checkpoint  # noqa: F401  (the reference's on-disk model / checkpoint layout)
 
 __all__ = ["B200UNet2DConditionModel", "UNet2DConditionOutput", "B200AttnProcessor", "Attention", "B200DDIMScheduler",
            "B200PNDMScheduler", "MutualEncoder", "B200DiFashionPipeline", "guidance_plan", "mutual_index_table",

@@ -121,6 +121,23 @@ class B200CLIPTextModel(nn.Module):
         self._op_dtype = torch.float32 if precision == "fp32" else torch.bfloat16
         return self
 
+    @classmethod
+    def from_pretrained(cls, path: str, subfolder: Optional[str] = None, **kw):
+        """``CLIPTextModel.from_pretrained(dir, subfolder="text_encoder")`` (difashion.py:70-72): transformers layout,
+        ``config.json`` + ``model.safetensors`` or ``pytorch_model.bin``."""
+        from . import checkpoint as ck
+        d = ck.model_dir(path, subfolder)
+        cfg = ck.read_config(d)
+        m = cls(**{k: v for k, v in cfg.items() if k in SD15_TEXT_ENCODER_CONFIG})
+        m.load_transformers_state_dict(ck.read_state_dict(d, ck.TRANSFORMERS_STEMS))
+        return m
+
+    def save_pretrained(self, save_directory: str, safe_serialization: bool = True, **kw):
+        from . import checkpoint as ck
+        ck.write_config(save_directory, dict(self._config), "CLIPTextModel")
+        ck.write_state_dict(save_directory, self.state_dict(), "model" if safe_serialization else "pytorch_model",
+                            safe_serialization)
+
     def load_transformers_state_dict(self, sd: Dict[str, torch.Tensor]):
         """Load a ``CLIPTextModel`` state dict (the ``position_ids`` buffer of older checkpoints is skipped)."""
         return self.load_state_dict({k: v for k, v in sd.items() if not k.endswith("position_ids")}, strict=True)

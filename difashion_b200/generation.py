@@ -47,6 +47,72 @@ class B200DiFashion:
                                           use_mutual_guidance=use_mutual_guidance, max_rows=max_rows,
                                           use_cuda_graph=use_cuda_graph)
         self._prompt_cache: Dict[bytes, torch.Tensor] = {}
+        self.tokenizer = None           # optional CLIPTokenizer (difashion.py:66-68); only its empty-prompt ids are used here
+
+    # ------------------------------------------------------------------------------------------
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path: str, checkpoint: Optional[str] = None, *, cate_num: int = 50,
+                        category_emb_size: int = 64, hid_dim: int = 256, scheduler: str = "pndm", device=None,
+                        load_tokenizer: bool = True, **kw) -> "B200DiFashion":
+        """What ``DiFashion.__init__`` does (difashion.py:52-101) from a local Stable-Diffusion directory: scheduler,
+        text encoder, VAE and UNet from their sub-folders, ``conv_in`` widened 4 -> 8 with zero-initialised history
+        channels (``:82-93``), a fresh xavier-normal ``MutualEncoder`` (``:95-101``) sized from the VAE / UNet configs;
+        then, when ``checkpoint`` is given, ``load_model_hook`` (inf4eval.py:556-581).  ``scheduler``: ``"pndm"`` (the
+        reference's hard-wired class) or ``"ddim"`` (BASELINE's metric) — both read ``scheduler/scheduler_config.json``."""
+        from . import checkpoint as ck
+        from .schedulers import B200DDIMScheduler, B200PNDMScheduler
+        root = pretrained_model_name_or_path
+        sched_cls = {"pndm": B200PNDMScheduler, "ddim": B200DDIMScheduler}[scheduler]
+        noise_scheduler = sched_cls.from_pretrained(root, subfolder="scheduler")
+        text_encoder = B200CLIPTextModel.from_pretrained(root, subfolder="text_encoder")
+        vae = B200AutoencoderKL.from_pretrained(root, subfolder="vae")
+        unet = ck.widen_conv_in(B200UNet2DConditionModel.from_pretrained(root, subfolder="unet"), 8)
+        fashion_encoder = MutualEncoder(cate_num=cate_num, cate_emb_size=category_emb_size,
+                                        latent_channels=vae.config.latent_channels, latent_size=unet.config.sample_size,
+                                        hid_dim=hid_dim)
+        if device is not None:
+            for m in (text_encoder, vae, unet, fashion_encoder):
+                m.to(device)
+        self = cls(unet, vae, text_encoder, fashion_encoder, noise_scheduler, **kw)
+        if load_tokenizer:
+            import os
+            if os.path.isdir(os.path.join(root, "tokenizer")):
+                from transformers import CLIPTokenizer
+                self.tokenizer = CLIPTokenizer.from_pretrained(root, subfolder="tokenizer")
+        if checkpoint is not None:
+            self.load_checkpoint(checkpoint)
+        return self
+
+    @classmethod
+    def from_args(cls, args, logger=None, cate_num: int = 50, device=None, **kw) -> "B200DiFashion":
+        """The reference constructor's signature, ``DiFashion(args, logger, cate_num, device)`` (difashion.py:52-58), reading
+        the same ``args`` fields (``pretrained_model_name_or_path``, ``category_emb_size``, ``hid_dim``, ``eta``)."""
+        if logger is not None:
+            logger.info("load scheduler / CLIPTextModel / VAE / UNet for the B200 path...")
+        return cls.from_pretrained(args.pretrained_model_name_or_path, cate_num=cate_num,
+                                   category_emb_size=getattr(args, "category_emb_size", 64),
+                                   hid_dim=getattr(args, "hid_dim", 256), eta=getattr(args, "eta", 0.1), device=device, **kw)
+
+    def load_checkpoint(self, input_dir: str) -> "B200DiFashion":
+        """``load_model_hook`` (inf4eval.py:556-581): ``<input_dir>/unet`` and ``<input_dir>/fashion_encoder`` (diffusers
+        ``save_pretrained`` directories) replace the weights AND the configs of the live modules, in place."""
+        loaded = B200UNet2DConditionModel.from_pretrained(input_dir, subfolder="unet")
+        if loaded.conv_in.weight.shape[1] != self.unet.conv_in.weight.shape[1]:
+            raise RuntimeError(f"checkpoint UNet has {loaded.conv_in.weight.shape[1]} input channels, the model "
+                               f"{self.unet.conv_in.weight.shape[1]}")
+        self.unet.register_to_config(**loaded.config)
+        self.unet.load_state_dict(loaded.state_dict())
+        enc = MutualEncoder.from_pretrained(input_dir, subfolder="fashion_encoder")
+        self.fashion_encoder.register_to_config(**enc.config)
+        self.fashion_encoder.load_state_dict(enc.state_dict())
+        self._prompt_cache.clear()
+        return self
+
+    def save_checkpoint(self, output_dir: str, safe_serialization: bool = False) -> None:
+        """``save_model_hook`` (inf4eval.py:543-554)."""
+        import os
+        self.fashion_encoder.save_pretrained(os.path.join(output_dir, "fashion_encoder"), safe_serialization=safe_serialization)
+        self.unet.save_pretrained(os.path.join(output_dir, "unet"), safe_serialization=safe_serialization)
 
     @property
     def device(self):
@@ -57,7 +123,11 @@ class B200DiFashion:
         """``text_encoder(fill_input_ids)[0]`` and the empty prompt (difashion.py:339-352).  Only <= 50 category prompts
         exist (data_utils.py:102-106), so distinct id rows are encoded once and cached across calls."""
         ids = fill_input_ids.to("cpu", torch.int64)
-        null_ids = self.text_encoder.null_input_ids(ids.shape[1])
+        if self.tokenizer is not None:          # tokenizer([""], padding="max_length", ...) — difashion.py:343-350
+            null_ids = torch.as_tensor(self.tokenizer([""], padding="max_length", max_length=ids.shape[1], truncation=True)["input_ids"],
+                                       dtype=torch.int64)
+        else:
+            null_ids = self.text_encoder.null_input_ids(ids.shape[1])
         uniq, inverse = torch.unique(torch.cat([ids, null_ids], 0), dim=0, return_inverse=True)
         missing = [i for i in range(uniq.shape[0]) if uniq[i].numpy().tobytes() not in self._prompt_cache]
         if missing:

@@ -12,12 +12,16 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from .config import FrozenConfig
 
 
 class MutualEncoder(nn.Module):
     def __init__(self, cate_num: int = 50, cate_emb_size: int = 64, latent_channels: int = 4, latent_size: int = 64,
                  hid_dim: int = 256):
         super().__init__()
+        # @register_to_config of the reference ctor (difashion.py:25-26): what save_pretrained writes to config.json
+        self._config = FrozenConfig(dict(cate_num=cate_num, cate_emb_size=cate_emb_size, latent_channels=latent_channels,
+                                         latent_size=latent_size, hid_dim=hid_dim))
         self.category_embedding = nn.Embedding(cate_num, cate_emb_size)  # useless embedding (difashion.py:28)
         self.latent_channels, self.latent_size, self.hid_dim = latent_channels, latent_size, hid_dim
         d = latent_channels * latent_size * latent_size
@@ -37,6 +41,33 @@ class MutualEncoder(nn.Module):
     @property
     def d(self) -> int:
         return self.latent_channels * self.latent_size * self.latent_size
+
+    @property
+    def config(self) -> FrozenConfig:
+        return self._config
+
+    def register_to_config(self, **kw):
+        """``model.fashion_encoder.register_to_config(**load_model.config)`` (inf4eval.py:579)."""
+        d = dict(self._config)
+        d.update({k: v for k, v in kw.items() if not k.startswith("_")})
+        self._config = FrozenConfig(d)
+
+    def save_pretrained(self, save_directory: str, safe_serialization: bool = False, **kw):
+        """diffusers ``ModelMixin.save_pretrained`` layout, as ``save_model_hook`` writes ``<ckpt>/fashion_encoder``
+        (inf4eval.py:550)."""
+        from . import checkpoint as ck
+        ck.write_config(save_directory, dict(self._config), "MutualEncoder")
+        ck.write_state_dict(save_directory, self.state_dict(), ck.DIFFUSERS_STEM, safe_serialization)
+
+    @classmethod
+    def from_pretrained(cls, path: str, subfolder: Optional[str] = None, **kw):
+        """``MutualEncoder.from_pretrained(input_dir, subfolder="fashion_encoder")`` (inf4eval.py:578)."""
+        from . import checkpoint as ck
+        d = ck.model_dir(path, subfolder)
+        cfg = ck.read_config(d)
+        m = cls(**{k: cfg[k] for k in ("cate_num", "cate_emb_size", "latent_channels", "latent_size", "hid_dim") if k in cfg})
+        m.load_state_dict(ck.read_state_dict(d), strict=True)
+        return m
 
     def pack(self, device, dtype: torch.dtype = torch.bfloat16):
         key = (str(device), str(dtype), tuple((p.data_ptr(), p._version) for p in self.mlp.parameters()))

@@ -50,6 +50,21 @@ class _SchedulerBase:
     def _a(self, t: int) -> float:
         return float(self.alphas_cumprod[t]) if t >= 0 else float(self.final_alpha_cumprod)
 
+    @classmethod
+    def from_pretrained(cls, path: str, subfolder: Optional[str] = None, **kw):
+        """``PNDMScheduler.from_pretrained(dir, subfolder="scheduler")`` (difashion.py:64): reads ``scheduler_config.json``
+        (the same file serves either class, as diffusers' ``from_config`` allows)."""
+        from . import checkpoint as ck
+        cfg = ck.read_config(ck.model_dir(path, subfolder), "scheduler_config.json")
+        if cfg.get("trained_betas") is not None:
+            raise NotImplementedError("trained_betas")
+        if cfg.get("timestep_spacing", "leading") != "leading":
+            raise NotImplementedError(f"timestep_spacing={cfg['timestep_spacing']!r} (diffusers 0.18.2 / SD configs use 'leading')")
+        if cfg.get("clip_sample", False) and cls.__name__ == "B200DDIMScheduler":
+            raise NotImplementedError("clip_sample=True")
+        cfg.update(kw)
+        return cls(**{k: v for k, v in cfg.items() if k not in ("trained_betas",)})
+
     def scale_model_input(self, sample: torch.Tensor, timestep=None) -> torch.Tensor:
         return sample
 

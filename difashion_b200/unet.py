@@ -260,26 +260,30 @@ class B200UNet2DConditionModel(nn.Module):
     def enable_gradient_checkpointing(self):
         """Accepted for API compatibility (inf4eval.py:587); inference-only module."""
 
-    def save_pretrained(self, save_directory: str, **kw):
-        import json
-        import os
-        os.makedirs(save_directory, exist_ok=True)
-        cfg = dict(self._config)
-        cfg["_class_name"] = "UNet2DConditionModel"
-        with open(os.path.join(save_directory, "config.json"), "w") as f:
-            json.dump(cfg, f, indent=2)
-        torch.save(self.state_dict(), os.path.join(save_directory, "diffusion_pytorch_model.bin"))
+    def save_pretrained(self, save_directory: str, safe_serialization: bool = False, **kw):
+        """``config.json`` + ``diffusion_pytorch_model.(bin | safetensors)`` — diffusers 0.18.2's layout, what
+        ``save_model_hook`` writes under ``<ckpt>/unet`` (inf4eval.py:543-554)."""
+        from . import checkpoint as ck
+        ck.write_config(save_directory, dict(self._config), "UNet2DConditionModel")
+        ck.write_state_dict(save_directory, self.state_dict(), ck.DIFFUSERS_STEM, safe_serialization)
 
     @classmethod
     def from_pretrained(cls, path: str, subfolder: Optional[str] = None, **kw):
-        import json
-        import os
-        d = os.path.join(path, subfolder) if subfolder else path
-        with open(os.path.join(d, "config.json")) as f:
-            cfg = {k: v for k, v in json.load(f).items() if not k.startswith("_")}
+        """``UNet2DConditionModel.from_pretrained(dir, subfolder="unet")`` (difashion.py:77-79, inf4eval.py:572): reads the
+        directory's ``config.json`` (so a 4-channel pretrained SD UNet and DiFashion's 8-channel checkpoints both load)
+        and ``diffusion_pytorch_model.safetensors`` or ``.bin``.  Config keys this path does not implement must hold their
+        SD values."""
+        from . import checkpoint as ck
+        d = ck.model_dir(path, subfolder)
+        cfg = ck.read_config(d)
         known = set(SD15_UNET_CONFIG.keys())
-        m = cls(**{k: (tuple(v) if isinstance(v, list) else v) for k, v in cfg.items() if k in known})
-        m.load_state_dict(torch.load(os.path.join(d, "diffusion_pytorch_model.bin"), map_location="cpu"))
+        for k, want in (("only_cross_attention", False), ("dual_cross_attention", False), ("class_embed_type", None),
+                        ("resnet_time_scale_shift", "default"), ("act_fn", "silu"), ("center_input_sample", False),
+                        ("mid_block_type", "UNetMidBlock2DCrossAttn")):
+            if k in cfg and cfg[k] != want:
+                raise NotImplementedError(f"UNet config {k}={cfg[k]!r} is not on the DiFashion path (expected {want!r})")
+        m = cls(**{k: v for k, v in cfg.items() if k in known})
+        m.load_state_dict(ck.read_state_dict(d), strict=True)
         return m
 
     @classmethod

@@ -190,6 +190,24 @@ class B200AutoencoderKL(nn.Module):
         self._op_dtype = torch.float32 if precision == "fp32" else torch.bfloat16
         return self
 
+    @classmethod
+    def from_pretrained(cls, path: str, subfolder: Optional[str] = None, **kw):
+        """``AutoencoderKL.from_pretrained(dir, subfolder="vae")`` (difashion.py:74): ``config.json`` +
+        ``diffusion_pytorch_model.(safetensors | bin)``; old attention key names are accepted."""
+        from . import checkpoint as ck
+        d = ck.model_dir(path, subfolder)
+        cfg = ck.read_config(d)
+        if cfg.get("act_fn", "silu") != "silu":
+            raise NotImplementedError(f"VAE act_fn={cfg['act_fn']!r}")
+        m = cls(**{k: v for k, v in cfg.items() if k in SD15_VAE_CONFIG})
+        m.load_diffusers_state_dict(ck.read_state_dict(d))
+        return m
+
+    def save_pretrained(self, save_directory: str, safe_serialization: bool = False, **kw):
+        from . import checkpoint as ck
+        ck.write_config(save_directory, dict(self._config), "AutoencoderKL")
+        ck.write_state_dict(save_directory, self.state_dict(), ck.DIFFUSERS_STEM, safe_serialization)
+
     def load_diffusers_state_dict(self, sd: Dict[str, torch.Tensor]):
         """Load a diffusers ``AutoencoderKL`` state dict (the pre-0.18 attention names query/key/value/proj_attn are
         mapped to to_q/to_k/to_v/to_out.0).  A decoder-only dict (no ``encoder.*`` keys) loads the decode half and
