@@ -89,8 +89,8 @@ class B200CLIPTextModel(nn.Module):
         super().__init__()
         cfg = dict(SD15_TEXT_ENCODER_CONFIG)
         cfg.update(config)
-        if cfg["hidden_act"] != "quick_gelu":
-            raise NotImplementedError("only hidden_act='quick_gelu' (the SD-1.5 text encoder) is implemented")
+        if cfg["hidden_act"] not in ("quick_gelu", "gelu"):
+            raise NotImplementedError("hidden_act must be 'quick_gelu' (SD-1.5's text encoder) or 'gelu' (SD-2's)")
         if cfg["hidden_size"] % cfg["num_attention_heads"] or (cfg["hidden_size"] // cfg["num_attention_heads"]) % 16:
             raise NotImplementedError("head dim must be a multiple of 16")
         self._config = FrozenConfig(cfg)
@@ -194,7 +194,7 @@ class B200CLIPTextModel(nn.Module):
                           causal=True)
             ops.gemm([att.view(M, D)], L["wo"], D, out=h, bias=L["bo"], residual=h)
             ops.layernorm(h, L["ln2"][0], L["ln2"][1], xn, eps=L["ln2"][2])
-            ops.gemm([xn], L["w1"], inner, out=mid, bias=L["b1"], act=ops.ACT_QUICK_GELU)
+            ops.gemm([xn], L["w1"], inner, out=mid, bias=L["b1"], act=ops.ACT_GELU if cfg.hidden_act == "gelu" else ops.ACT_QUICK_GELU)
             ops.gemm([mid], L["w2"], D, out=h, bias=L["b2"], residual=h)
         ops.layernorm(h, P["final"][0], P["final"][1], out.view(M, D), eps=P["final"][2])
         return out

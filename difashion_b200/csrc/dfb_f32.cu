@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(SG_THREADS) sgemm_kernel(const SgemmParams p) 
       else if (p.act == DFB_ACT_LEAKY_RELU) x = x > 0.f ? x : 0.01f * x;
       else if (p.act == DFB_ACT_TANH) x = tanhf(x);
       else if (p.act == DFB_ACT_QUICK_GELU) x = x / (1.0f + expf(-1.702f * x));
+      else if (p.act == DFB_ACT_GELU) x = gelu_erf_f(x);
       if (p.residual) x += p.residual[(size_t)m * p.res_ld + n];
       p.out[(size_t)m * p.out_ld + n] = x;
     }
@@ -224,6 +225,7 @@ int dfb_gemm_f32(const dfb_gemm_params* q, void* stream) {
     }
     kp_total += q->ntaps[s] * ((q->a_c[s] + 63) / 64 * 64);
   }
+  DFB_REQUIRE(q->act >= DFB_ACT_NONE && q->act <= DFB_ACT_GELU, "dfb_gemm_f32: unknown activation");
   DFB_REQUIRE(kp_total <= q->w_ld, "dfb_gemm_f32: packed weight K extent smaller than the A operand implies");
   if (q->conv) DFB_REQUIRE(q->B > 0 && q->H > 0 && q->W > 0 && (long long)q->B * q->H * q->W == q->M, "dfb_gemm_f32: conv geometry does not match M");
   p.nseg = q->nseg; p.conv = q->conv ? 1 : 0; p.B = q->B; p.H = q->H; p.W = q->W; p.M = q->M; p.N = q->N;

@@ -564,6 +564,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
               if (f_act == DFB_ACT_SILU) x[e] = silu_f(x[e]);
               else if (f_act == DFB_ACT_LEAKY_RELU) x[e] = x[e] > 0.f ? x[e] : 0.01f * x[e];
               else if (f_act == DFB_ACT_QUICK_GELU) x[e] = x[e] / (1.0f + __expf(-1.702f * x[e]));
+              else if (f_act == DFB_ACT_GELU) x[e] = gelu_fast_f(x[e]);
               else x[e] = tanhf(x[e]);
             }
           }
@@ -717,6 +718,7 @@ extern "C" int dfb_gemm(const dfb_gemm_params* q, void* stream_) {
   DFB_REQUIRE(q != nullptr, "dfb_gemm: null params");
   DFB_REQUIRE(q->nseg == 1 || q->nseg == 2, "dfb_gemm: nseg must be 1 or 2");
   DFB_REQUIRE(q->M > 0 && q->N > 0, "dfb_gemm: empty problem");
+  DFB_REQUIRE(q->act >= DFB_ACT_NONE && q->act <= DFB_ACT_GELU, "dfb_gemm: unknown activation");
   DFB_REQUIRE(q->w != nullptr && q->out != nullptr && q->a[0] != nullptr, "dfb_gemm: null buffer");
   DFB_REQUIRE((reinterpret_cast<uintptr_t>(q->w) & 15) == 0 && (q->w_ld % 8) == 0, "dfb_gemm: weights must be 16B aligned");
 

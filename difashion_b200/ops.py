@@ -183,7 +183,7 @@ def gemm(a: Sequence[torch.Tensor], w: torch.Tensor, n: int, *, out: torch.Tenso
     return out
 
 
-ACT_NONE, ACT_SILU, ACT_LEAKY_RELU, ACT_TANH, ACT_QUICK_GELU = 0, 1, 2, 3, 4
+ACT_NONE, ACT_SILU, ACT_LEAKY_RELU, ACT_TANH, ACT_QUICK_GELU, ACT_GELU = 0, 1, 2, 3, 4, 5
 
 
 # ----------------------------------------------------------------------------------------------

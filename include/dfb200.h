@@ -35,6 +35,7 @@ extern "C" {
 #define DFB_ACT_LEAKY_RELU 2 /* slope 0.01 (nn.LeakyReLU default, MutualEncoder) */
 #define DFB_ACT_TANH 3
 #define DFB_ACT_QUICK_GELU 4 /* x * sigmoid(1.702 x): CLIPTextModel mlp (hidden_act "quick_gelu") */
+#define DFB_ACT_GELU 5       /* exact erf GELU: CLIPTextModel mlp with hidden_act "gelu" (SD-2's OpenCLIP text encoder) */
 
 const char* dfb_strerror(int rc);
 const char* dfb_last_error(void);

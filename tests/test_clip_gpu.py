@@ -76,16 +76,20 @@ def test_embed_tokens_quick_gelu_and_uint8():
 def _mk(which, seed=0):
     from difashion_b200.clip import B200CLIPTextModel
     from oracle.clip_oracle import CLIPTextConfigLite, make_oracle_clip, tiny_clip_config
-    cfg = tiny_clip_config() if which == "tiny" else CLIPTextConfigLite()
+    # "*gelu": SD-2-base's text encoder activation (exact erf GELU; the reference's default base model, train.py:44)
+    cfg = {"tiny": tiny_clip_config, "full": CLIPTextConfigLite,
+           "tiny_gelu": lambda: tiny_clip_config(hidden_act="gelu", num_attention_heads=2)}[which]()
     o = make_oracle_clip(cfg, seed=seed)
     m = B200CLIPTextModel(vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size, intermediate_size=cfg.intermediate_size,
-                          num_hidden_layers=cfg.num_hidden_layers, num_attention_heads=cfg.num_attention_heads)
+                          num_hidden_layers=cfg.num_hidden_layers, num_attention_heads=cfg.num_attention_heads,
+                          hidden_act=cfg.hidden_act)
     m.load_transformers_state_dict(o.state_dict())
     return cfg, o, m.cuda()
 
 
 @pytest.mark.parametrize("which,B,precision,tol", [("tiny", 5, "bf16", 1e-2), ("tiny", 3, "fp32", 1e-4), ("full", 3, "bf16", 1e-2),
-                                                   ("full", 2, "fp32", 1e-4)])
+                                                   ("full", 2, "fp32", 1e-4), ("tiny_gelu", 4, "bf16", 1e-2),
+                                                   ("tiny_gelu", 3, "fp32", 1e-4)])
 def test_clip_text_model_matches_oracle(which, B, precision, tol):
     cfg, oracle, m = _mk(which)
     m.set_precision(precision)
@@ -108,10 +112,11 @@ def test_clip_text_model_matches_oracle(which, B, precision, tol):
     assert rel_l2(short.cpu(), oracle(ids[:, :20])[0]) <= tol
 
 
-def test_clip_against_transformers_golden_fixture():
-    """tests/golden/clip_tiny.pt: weights, ids and last_hidden_state produced by transformers.CLIPTextModel."""
+@pytest.mark.parametrize("fixture", ["clip_tiny.pt", "clip_tiny_gelu.pt"])
+def test_clip_against_transformers_golden_fixture(fixture):
+    """tests/golden/clip_tiny*.pt: weights, ids and last_hidden_state produced by transformers.CLIPTextModel."""
     from difashion_b200.clip import B200CLIPTextModel
-    gold = torch.load(os.path.join(GOLD, "clip_tiny.pt"))
+    gold = torch.load(os.path.join(GOLD, fixture))
     m = B200CLIPTextModel(**gold["config"])
     m.load_transformers_state_dict(gold["state_dict"])
     m.cuda()

@@ -322,7 +322,13 @@ def test_clip_and_vae_module_surfaces_without_gpu():
     with pytest.raises(NotImplementedError):
         m(torch.zeros(1, 77, dtype=torch.long), attention_mask=torch.ones(1, 77))
     with pytest.raises(NotImplementedError):
-        B200CLIPTextModel(hidden_act="gelu")
+        B200CLIPTextModel(hidden_act="relu")
+    from oracle.clip_oracle import sd2_clip_config
+    s2 = sd2_clip_config()
+    with torch.device("meta"):
+        big = B200CLIPTextModel(hidden_size=s2.hidden_size, intermediate_size=s2.intermediate_size, hidden_act=s2.hidden_act,
+                                num_hidden_layers=s2.num_hidden_layers, num_attention_heads=s2.num_attention_heads)
+    assert sum(p.numel() for p in big.parameters()) == 340_387_840 and big.config.hidden_act == "gelu"
     # VAE: full and decoder-only state dicts
     vcfg = tiny_vae_config(block_out_channels=(64, 64, 128, 128))
     kw = dict(block_out_channels=tuple(vcfg.block_out_channels), layers_per_block=vcfg.layers_per_block, norm_num_groups=vcfg.norm_num_groups)

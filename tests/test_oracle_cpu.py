@@ -38,6 +38,20 @@ def test_sd15_structure_param_and_tensor_counts():
     assert not any(k.startswith("down_blocks.3.downsamplers") or k.startswith("up_blocks.3.upsamplers") for k in keys8)
 
 
+def test_sd2_base_structure_param_count():
+    """The reference's default base model (stabilityai/stable-diffusion-2-base, train.py:44): published UNet size
+    865 910 724 parameters; linear proj_in / proj_out store [C, C] matrices instead of [C, C, 1, 1] kernels."""
+    cfg = dict(use_linear_projection=True, attention_head_dim=(5, 10, 20, 20), cross_attention_dim=1024)
+    n4, keys = _count(UNetConfig(in_channels=4, **cfg))
+    assert n4 == 865_910_724 and len(keys) == 686
+    with torch.device("meta"):
+        m = OracleUNet2DConditionModel(UNetConfig(**cfg))
+    sd = m.state_dict()
+    assert sd["down_blocks.0.attentions.0.proj_in.weight"].shape == (320, 320)
+    assert sd["down_blocks.2.attentions.0.transformer_blocks.0.attn2.to_k.weight"].shape == (1280, 1024)
+    assert [m.cfg.heads(i) for i in range(4)] == [5, 10, 20, 20] and all(c // h == 64 for c, h in zip((320, 640, 1280, 1280), (5, 10, 20, 20)))
+
+
 def test_layer_counts():
     with torch.device("meta"):
         m = OracleUNet2DConditionModel(UNetConfig())
@@ -194,11 +208,13 @@ def test_vae_decoder_oracle_structure_and_shapes():
 # ------------------------------------------------------------------------------------------------
 # stages around the loop: CLIP text encoder, VAE encoder, post-processing
 # ------------------------------------------------------------------------------------------------
-def test_clip_oracle_matches_transformers_golden():
-    """PINNED: tests/golden/clip_tiny.pt was produced by the real transformers.CLIPTextModel
-    (tools/make_golden_clip.py); the restatement must reproduce it from the same state dict."""
+@pytest.mark.parametrize("fixture", ["clip_tiny.pt", "clip_tiny_gelu.pt"])
+def test_clip_oracle_matches_transformers_golden(fixture):
+    """PINNED: tests/golden/clip_tiny*.pt were produced by the real transformers.CLIPTextModel
+    (tools/make_golden_clip.py; quick_gelu = SD-1.5's text encoder, gelu = SD-2-base's); the restatement must
+    reproduce them from the same state dict."""
     from oracle.clip_oracle import CLIPTextConfigLite, OracleCLIPTextModel
-    gold = torch.load(os.path.join(GOLD, "clip_tiny.pt"))
+    gold = torch.load(os.path.join(GOLD, fixture))
     m = OracleCLIPTextModel(CLIPTextConfigLite(**gold["config"])).eval()
     m.load_state_dict(gold["state_dict"], strict=True)
     y = m(gold["input_ids"])[0]
@@ -211,16 +227,17 @@ def test_clip_oracle_matches_transformers_golden():
     assert torch.allclose(y2[:, :40], y[:, :40], atol=1e-6) and not torch.allclose(y2[:, 40:], y[:, 40:], atol=1e-3)
 
 
-def test_clip_oracle_matches_transformers_live():
+@pytest.mark.parametrize("act", ["quick_gelu", "gelu"])
+def test_clip_oracle_matches_transformers_live(act):
     """Same check against transformers imported right here (skipped where the package is absent)."""
     tr = pytest.importorskip("transformers")
     from oracle.clip_oracle import make_oracle_clip, tiny_clip_config
-    cfg = tiny_clip_config()
+    cfg = tiny_clip_config(hidden_act=act)
     o = make_oracle_clip(cfg, seed=2)
     hf = tr.CLIPTextModel(tr.CLIPTextConfig(
         vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size, intermediate_size=cfg.intermediate_size,
         num_hidden_layers=cfg.num_hidden_layers, num_attention_heads=cfg.num_attention_heads,
-        max_position_embeddings=cfg.max_position_embeddings, hidden_act="quick_gelu", layer_norm_eps=cfg.layer_norm_eps,
+        max_position_embeddings=cfg.max_position_embeddings, hidden_act=act, layer_norm_eps=cfg.layer_norm_eps,
         projection_dim=cfg.hidden_size, pad_token_id=1, bos_token_id=0, eos_token_id=2)).eval()
     res = hf.load_state_dict(o.state_dict(), strict=False)
     assert not res.unexpected_keys and all(k.endswith("position_ids") for k in res.missing_keys)
@@ -242,6 +259,15 @@ def test_clip_sd15_structure():
         assert k in sd, k
     ids = null_input_ids()
     assert ids.shape == (1, 77) and ids[0, 0] == BOS_TOKEN_ID and bool((ids[0, 1:] == EOS_TOKEN_ID).all())
+
+
+def test_clip_sd2_base_structure():
+    """SD-2-base text encoder (OpenCLIP ViT-H text tower, 23 layers): 340 387 840 parameters, 372 tensors."""
+    from oracle.clip_oracle import OracleCLIPTextModel, sd2_clip_config
+    with torch.device("meta"):
+        m = OracleCLIPTextModel(sd2_clip_config())
+    assert sum(p.numel() for p in m.parameters()) == 340_387_840 and len(m.state_dict()) == 372
+    assert m.text_model.encoder.layers[22].mlp.exact
 
 
 def test_vae_encoder_oracle_structure_and_shapes():

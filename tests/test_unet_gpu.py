@@ -13,11 +13,16 @@ pytestmark = pytest.mark.gpu
 def _mk(cfg_kw, seed=0):
     from oracle.unet_oracle import UNetConfig, make_oracle_unet, tiny_config
     from difashion_b200.unet import B200UNet2DConditionModel
-    ocfg = tiny_config() if cfg_kw == "tiny" else UNetConfig()
+    # "sd2*": the reference's DEFAULT base model, stabilityai/stable-diffusion-2-base (train.py:44, inf4eval.py:65):
+    # linear proj_in / proj_out, per-level head counts (5, 10, 20, 20) -> head dim 64, cross-attention dim 1024
+    ocfg = {"tiny": tiny_config,
+            "tiny_sd2": lambda: tiny_config(use_linear_projection=True, attention_head_dim=(1, 2, 2, 2), cross_attention_dim=96),
+            "sd2": lambda: UNetConfig(use_linear_projection=True, attention_head_dim=(5, 10, 20, 20), cross_attention_dim=1024),
+            "full": UNetConfig}[cfg_kw]()
     oracle = make_oracle_unet(ocfg, seed=seed)
     kw = dict(sample_size=ocfg.sample_size, in_channels=ocfg.in_channels, out_channels=ocfg.out_channels,
               block_out_channels=tuple(ocfg.block_out_channels), cross_attention_dim=ocfg.cross_attention_dim,
-              attention_head_dim=ocfg.attention_head_dim)
+              attention_head_dim=ocfg.attention_head_dim, use_linear_projection=ocfg.use_linear_projection)
     unet = B200UNet2DConditionModel(**kw)
     missing = unet.load_state_dict(oracle.state_dict(), strict=True)
     return oracle, unet.cuda()
@@ -31,7 +36,7 @@ def _block_report(taps_o, taps_g):
     return " | ".join(out)
 
 
-@pytest.mark.parametrize("which,B,S", [("tiny", 4, 77), ("tiny", 3, 85), ("full", 2, 77)])
+@pytest.mark.parametrize("which,B,S", [("tiny", 4, 77), ("tiny", 3, 85), ("full", 2, 77), ("tiny_sd2", 3, 77), ("sd2", 1, 77)])
 def test_unet_forward_matches_oracle(which, B, S):
     oracle, unet = _mk(which)
     cfg = oracle.cfg

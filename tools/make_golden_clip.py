@@ -10,18 +10,29 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-OUT = os.path.join(ROOT, "tests", "golden", "clip_tiny.pt")
+GOLD = os.path.join(ROOT, "tests", "golden")
 
-CFG = dict(vocab_size=300, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
-           max_position_embeddings=77, layer_norm_eps=1e-5)
+# clip_tiny.pt: SD-1.5's activation (quick_gelu); clip_tiny_gelu.pt: SD-2-base's (exact erf "gelu", head dim 64 as in
+# OpenCLIP ViT-H's text tower) — the reference's default base model (train.py:44)
+VARIANTS = {
+    "clip_tiny.pt": dict(vocab_size=300, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+                         max_position_embeddings=77, layer_norm_eps=1e-5),
+    "clip_tiny_gelu.pt": dict(vocab_size=200, hidden_size=128, intermediate_size=256, num_hidden_layers=2,
+                              num_attention_heads=2, max_position_embeddings=77, layer_norm_eps=1e-5, hidden_act="gelu"),
+}
 
 
 def main():
+    for name, cfg in VARIANTS.items():
+        make(os.path.join(GOLD, name), cfg)
+
+
+def make(OUT, CFG):
     import transformers
     from transformers import CLIPTextConfig, CLIPTextModel
     torch.manual_seed(0)
-    hf = CLIPTextModel(CLIPTextConfig(hidden_act="quick_gelu", projection_dim=64, pad_token_id=1, bos_token_id=0,
-                                      eos_token_id=2, **CFG)).eval()
+    hf = CLIPTextModel(CLIPTextConfig(**dict(dict(hidden_act="quick_gelu", projection_dim=64, pad_token_id=1, bos_token_id=0,
+                                                  eos_token_id=2), **CFG))).eval()
     g = torch.Generator().manual_seed(5)
     with torch.no_grad():
         for p in hf.parameters():                       # non-trivial norms / biases (HF inits biases to zero)
