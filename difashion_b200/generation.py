@@ -93,16 +93,20 @@ class B200DiFashion:
                                    category_emb_size=getattr(args, "category_emb_size", 64),
                                    hid_dim=getattr(args, "hid_dim", 256), eta=getattr(args, "eta", 0.1), device=device, **kw)
 
-    def load_checkpoint(self, input_dir: str) -> "B200DiFashion":
+    def load_checkpoint(self, input_dir: str, use_ema: bool = False, use_ema_fashion: bool = False) -> "B200DiFashion":
         """``load_model_hook`` (inf4eval.py:556-581): ``<input_dir>/unet`` and ``<input_dir>/fashion_encoder`` (diffusers
-        ``save_pretrained`` directories) replace the weights AND the configs of the live modules, in place."""
-        loaded = B200UNet2DConditionModel.from_pretrained(input_dir, subfolder="unet")
+        ``save_pretrained`` directories) replace the weights AND the configs of the live modules, in place.
+        ``use_ema`` / ``use_ema_fashion`` (``--use_ema``, ``--use_ema_fashion``): inference runs on the EMA copies
+        (``ema_unet.copy_to(unet.parameters())``, inf4eval.py:691-697) — ``EMAModel.save_pretrained`` writes them as ordinary
+        model directories ``unet_ema`` / ``fashion_encoder_ema`` (shadow parameters + a few extra config keys), so they load
+        the same way."""
+        loaded = B200UNet2DConditionModel.from_pretrained(input_dir, subfolder="unet_ema" if use_ema else "unet")
         if loaded.conv_in.weight.shape[1] != self.unet.conv_in.weight.shape[1]:
             raise RuntimeError(f"checkpoint UNet has {loaded.conv_in.weight.shape[1]} input channels, the model "
                                f"{self.unet.conv_in.weight.shape[1]}")
-        self.unet.register_to_config(**loaded.config)
+        self.unet.register_to_config(**loaded.config)        # (EMA bookkeeping keys are not model config: from_pretrained dropped them)
         self.unet.load_state_dict(loaded.state_dict())
-        enc = MutualEncoder.from_pretrained(input_dir, subfolder="fashion_encoder")
+        enc = MutualEncoder.from_pretrained(input_dir, subfolder="fashion_encoder_ema" if use_ema_fashion else "fashion_encoder")
         self.fashion_encoder.register_to_config(**enc.config)
         self.fashion_encoder.load_state_dict(enc.state_dict())
         self._prompt_cache.clear()

@@ -76,6 +76,22 @@ def test_assemble_from_sd_directory_and_checkpoint(tmp_path, safe):
     m3 = B200DiFashion.from_pretrained(root, checkpoint=ckpt, cate_num=11, category_emb_size=8, hid_dim=32)
     assert all(torch.equal(v, want_u[k]) for k, v in m3.unet.state_dict().items())
 
+    # EMA copies (--use_ema / --use_ema_fashion): EMAModel.save_pretrained writes ordinary model directories + extra config keys
+    with torch.no_grad():
+        for q in list(m3.unet.parameters()) + list(m3.fashion_encoder.parameters()):
+            q.mul_(0.5)
+    m3.unet.save_pretrained(os.path.join(ckpt, "unet_ema"), safe_serialization=safe)
+    m3.fashion_encoder.save_pretrained(os.path.join(ckpt, "fashion_encoder_ema"), safe_serialization=safe)
+    with open(os.path.join(ckpt, "unet_ema", "config.json")) as f:
+        ecfg = json.load(f)
+    ecfg.update(decay=0.9999, min_decay=0.0, optimization_step=1234, update_after_step=0, use_ema_warmup=False, inv_gamma=1.0, power=0.75)
+    with open(os.path.join(ckpt, "unet_ema", "config.json"), "w") as f:
+        json.dump(ecfg, f)
+    m2.load_checkpoint(ckpt, use_ema=True, use_ema_fashion=True)
+    assert all(torch.equal(v, 0.5 * want_u[k]) for k, v in m2.unet.state_dict().items())
+    assert all(torch.equal(v, 0.5 * want_f[k]) for k, v in m2.fashion_encoder.state_dict().items())
+    assert "decay" not in m2.unet.config and m2.unet.config.in_channels == 8
+
     # the reference ctor's signature: DiFashion(args, logger, cate_num, device) (difashion.py:52-58)
     class Args:
         pretrained_model_name_or_path, category_emb_size, hid_dim, eta = root, 8, 32, 0.1
