@@ -36,6 +36,7 @@ def mutual_index_table(olists: torch.Tensor) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------------------------
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence
 
@@ -96,7 +97,8 @@ class B200DiFashionPipeline:
 
     def __init__(self, unet: B200UNet2DConditionModel, mutual_encoder: Optional[MutualEncoder], scheduler,
                  eta_mutual: float = 0.1, use_history: bool = True, use_mutual_guidance: bool = True,
-                 max_rows: int = 256, use_cuda_graph: bool = True, streams: int = 1):
+                 max_rows: int = 256, use_cuda_graph: bool = True, streams: int = 1,
+                 share_cfg_prefix: Optional[bool] = None):
         self.unet, self.mutual_encoder, self.scheduler = unet, mutual_encoder, scheduler
         self.eta_mutual = float(eta_mutual)
         self.use_history, self.use_mutual_guidance = use_history, use_mutual_guidance
@@ -107,6 +109,13 @@ class B200DiFashionPipeline:
         # kernels: no shared memory, they co-reside with a persistent GEMM CTA) overlap the tensor-bound kernels of
         # another.  Needs use_cuda_graph and >= 2 chunks (max_rows < rows of the batch).
         self.streams = max(1, int(streams))
+        # The last two CFG branches of every multi-branch plan that guides on the category get the SAME UNet input and
+        # differ only in the prompt (branches [.., (0m,0h,c), (0m,0h,0c)], difashion.py:388-431 / :494-512): the UNet part
+        # ahead of the first cross-attention is computed once for both (``forward_nhwc(shared_tail=...)``; bit-identical).
+        # DFB_SHARE_PREFIX=0 (or share_cfg_prefix=False) computes every branch in full.
+        if share_cfg_prefix is None:
+            share_cfg_prefix = os.environ.get("DFB_SHARE_PREFIX", "1") != "0"
+        self.share_cfg_prefix = bool(share_cfg_prefix)
         self._states = {}
         self.last_step_launches = 0          # kernels launched per denoising step (counted at capture / eager run)
 
@@ -120,7 +129,8 @@ class B200DiFashionPipeline:
         ws = ch.ws if ch.ws is not None else st.ws
         x_in = ws.get("pipe_x_in", (st.nb * n, st.size, st.size, 8), self.unet._op_dtype)
         ops.mutual_blend(x, m, hist, st.null, self.eta_mutual, st.use_m, st.use_h, x_in)
-        return self.unet.forward_nhwc(x_in, st.t_dev[: st.nb * n], ch.ctx_bf16, ch.kv_store, ws)
+        return self.unet.forward_nhwc(x_in, st.t_dev[: st.nb * n], ch.ctx_bf16, ch.kv_store, ws,
+                                      shared_tail=n if st.shared_tail else 0)
 
     def _mutual(self, st):
         if st.m is None:
@@ -130,7 +140,7 @@ class B200DiFashionPipeline:
 
     def _state(self, dev, n, n_given, olen, size, nb, S, D, plan) -> "_State":
         key = (str(dev), n, n_given, olen, size, nb, S, D, tuple(map(tuple, plan[:3])), self.use_history,
-               self.use_mutual_guidance, self.max_rows, str(self.unet._op_dtype), self.streams)
+               self.use_mutual_guidance, self.max_rows, str(self.unet._op_dtype), self.streams, self.share_cfg_prefix)
         st = self._states.get(key)
         if st is not None:
             return st
@@ -138,6 +148,10 @@ class B200DiFashionPipeline:
         hw = size * size
         st.n, st.size, st.hw, st.nb = n, size, hw, nb
         st.ctx_cat, st.use_m, st.use_h = plan[0], plan[1], plan[2]
+        # do the last two branches see the same (mutual, history) input?  (without a MutualEncoder / history the flag is moot)
+        same = lambda flags, active: (not active) or flags[-1] == flags[-2]
+        st.shared_tail = bool(self.share_cfg_prefix and nb >= 2 and same(plan[1], self.use_mutual_guidance)
+                              and same(plan[2], self.use_history))
         f = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
         st.latents = f(n, 4, size, size)
         st.null = f(4, size, size)

@@ -445,32 +445,41 @@ class B200UNet2DConditionModel(nn.Module):
             ops.gemm([ctx_bf16.view(b * skv, dctx)], a2.w_kv, 2 * a2.cp, out=kv.view(b * skv, 2 * a2.cp))
         return store
 
-    def _transformer(self, pk, name: str, x: torch.Tensor, ctx_bf16, kv_store, ws: Workspace, out_tag: str):
+    def _transformer(self, pk, name: str, x: torch.Tensor, ctx_bf16, kv_store, ws: Workspace, out_tag: str,
+                     shared_tail: int = 0):
+        """``shared_tail`` = k > 0: only the first B - k rows of ``x`` hold data and the last k rows are to equal the k rows
+        before them (CFG branches that differ in the text condition only — see ``forward_nhwc``): everything ahead of the
+        cross-attention runs on B - k rows, then the residual stream and ``x`` are widened to B rows by a device copy."""
         B, H, W, C = x.shape
         S, M = H * W, B * H * W
+        Bp = B - shared_tail
+        Mp = Bp * S
         g, b, eps, groups = pk["gn"]
         stats = ws.get("gn_stats", (ops.groupnorm_ws_floats(B, groups),), torch.float32)
         xn = ws.get("xn", (M, C), self._op_dtype)
-        ops.groupnorm(x, None, g, b, groups=groups, eps=eps, silu=False, stats_ws=stats, out=xn.view(B, H, W, C),
+        ops.groupnorm(x[:Bp], None, g, b, groups=groups, eps=eps, silu=False, stats_ws=stats, out=xn[:Mp].view(Bp, H, W, C),
                       partials=(self._gnp_of(x), None))
         h = ws.get("tr_h", (M, C), torch.float32)
-        ops.gemm([xn], pk["pin"][0], C, out=h, bias=pk["pin"][1])
+        ops.gemm([xn[:Mp]], pk["pin"][0], C, out=h[:Mp], bias=pk["pin"][1])
         ln = ws.get("ln", (M, C), self._op_dtype)
         a1, a2 = pk["a1"], pk["a2"]
         fast = isinstance(pk["attn1"].processor, B200AttnProcessor) and isinstance(pk["attn2"].processor, B200AttnProcessor)
 
         # --- self-attention
         g, b, eps = pk["ln1"]
-        ops.layernorm(h, g, b, ln, eps)
+        ops.layernorm(h[:Mp], g, b, ln[:Mp], eps)
         if fast:
             qkv = ws.get("qkv", (B, S, 3 * a1.cp), self._op_dtype)
-            ops.gemm([ln], a1.w_qkv, 3 * a1.cp, out=qkv.view(M, 3 * a1.cp))
+            ops.gemm([ln[:Mp]], a1.w_qkv, 3 * a1.cp, out=qkv.view(M, 3 * a1.cp)[:Mp])
             att = ws.get("att", (B, S, a1.cp), self._op_dtype)
-            ops.attention(qkv[..., :a1.cp], qkv[..., a1.cp:2 * a1.cp], qkv[..., 2 * a1.cp:], att, heads=a1.heads,
+            ops.attention(qkv[:Bp, :, :a1.cp], qkv[:Bp, :, a1.cp:2 * a1.cp], qkv[:Bp, :, 2 * a1.cp:], att[:Bp], heads=a1.heads,
                           dp=a1.dp, scale=a1.scale)
-            ops.gemm([att.view(M, a1.cp)], a1.w_o, C, out=h, bias=a1.b_o, residual=h)
+            ops.gemm([att.view(M, a1.cp)[:Mp]], a1.w_o, C, out=h[:Mp], bias=a1.b_o, residual=h[:Mp])
         else:
-            h.add_(pk["attn1"].processor(pk["attn1"], ln.view(B, S, C)).reshape(M, C).float())
+            h[:Mp].add_(pk["attn1"].processor(pk["attn1"], ln[:Mp].view(Bp, S, C)).reshape(Mp, C).float())
+        if shared_tail:
+            h[Mp:].copy_(h[Mp - shared_tail * S:Mp])
+            x[Bp:].copy_(x[Bp - shared_tail:Bp])
         # --- cross-attention over the (category prompt [+ history]) tokens
         g, b, eps = pk["ln2"]
         ops.layernorm(h, g, b, ln, eps)
@@ -511,23 +520,49 @@ class B200UNet2DConditionModel(nn.Module):
         return temb_all
 
     def forward_nhwc(self, x_in: torch.Tensor, t_dev: torch.Tensor, ctx_bf16: torch.Tensor, kv_store: Dict[str, torch.Tensor],
-                     ws: Workspace, taps: Optional[dict] = None) -> torch.Tensor:
+                     ws: Workspace, taps: Optional[dict] = None, shared_tail: int = 0) -> torch.Tensor:
         """x_in: bf16 NHWC [B,H,W,in_channels]; t_dev: fp32 [B]; ctx: bf16 [B,S_kv,D]; kv_store: the result of
-        ``project_context(ctx)``.  Returns the fp32 NHWC noise prediction [B,H,W,out_channels] (a workspace buffer)."""
+        ``project_context(ctx)``.  Returns the fp32 NHWC noise prediction [B,H,W,out_channels] (a workspace buffer).
+
+        ``shared_tail`` = k > 0 is the caller's promise that ``x_in[B-k:]`` equals ``x_in[B-2k:B-k]`` (and the timesteps
+        too) — the last two CFG branches of ``fashion_generation`` get the same latent / mutual / history input and differ
+        only in their prompt (difashion.py:388-431, :494-512).  The network is row-wise up to its first cross-attention, so
+        ``conv_in``, the first ResNet block and the first transformer's GroupNorm / proj_in / self-attention run on B - k
+        rows and their results are copied into the tail rows: bit-identical output (fixed reduction orders, no cross-row
+        arithmetic), 1.3 % fewer executed FLOPs per 4-branch step.  ``x_in[B-k:]`` is not read."""
         P = self.pack(x_in.device)
         B, H, W, cin = x_in.shape
+        k = int(shared_tail)
+        if k and not (0 < 2 * k <= B and P["down"][0]["attentions"] is not None):
+            k = 0
+        Bp = B - k
         self._gnp = {}
         temb_all = self._temb(P, t_dev, ws)
         c0 = self.config.block_out_channels[0]
         h = ws.get("skip0", (B, H, W, c0), torch.float32)
-        ops.gemm([x_in], P["conv_in"][0], c0, out=h, taps=[ops.TAPS_3X3], conv_geom=(B, H, W), bias=P["conv_in"][1],
-                 gn_partial=self._gnp_new(ws, "skip0", h))
+        part = self._gnp_new(ws, "skip0", h)
+        ops.gemm([x_in[:Bp]], P["conv_in"][0], c0, out=h[:Bp], taps=[ops.TAPS_3X3], conv_geom=(Bp, H, W), bias=P["conv_in"][1],
+                 gn_partial=part)
+        if k:                       # skip0 feeds the last up block for every row: widen it (and its GroupNorm partials) now
+            h[Bp:].copy_(h[Bp - k:Bp])
+            if part is not None:
+                blk = H * W // 32
+                part[Bp * blk:].copy_(part[(Bp - k) * blk:Bp * blk])
         if taps is not None:
             taps["conv_in"] = h.clone()
         skips, ns = [h], 1
         for i, bp in enumerate(P["down"]):
             for j, rp in enumerate(bp["resnets"]):
                 has_att = bp["attentions"] is not None
+                if k and i == 0 and j == 0:
+                    cr = rp["cout"]
+                    r_full = ws.get("rtmp", (B, H, W, cr), torch.float32)      # size the buffer for all rows first
+                    self._resnet(rp, [h[:Bp]], temb_all, ws, "rtmp")
+                    h = self._transformer(bp["attentions"][j], f"down{i}.{j}", r_full, ctx_bf16, kv_store, ws, f"skip{ns}",
+                                          shared_tail=k)
+                    skips.append(h)
+                    ns += 1
+                    continue
                 r = self._resnet(rp, [h], temb_all, ws, "rtmp" if has_att else f"skip{ns}")
                 h = self._transformer(bp["attentions"][j], f"down{i}.{j}", r, ctx_bf16, kv_store, ws, f"skip{ns}") if has_att else r
                 skips.append(h)

@@ -106,6 +106,21 @@ def test_timestep_embedding_is_cos_then_sin():
     assert abs(float(e[0, 1]) - math.cos(3.0 * f1)) < 1e-6
 
 
+def test_noise_schedule_published_constants():
+    """Known answers outside this repo: Stable Diffusion's scaled-linear schedule (beta 0.00085 -> 0.012, 1000 steps) has the
+    widely published noise range sigma_min = 0.0292, sigma_max = 14.6146 (sigma = sqrt((1 - a) / a); k-diffusion's SD wrapper
+    quotes exactly these), i.e. alphas_cumprod[0] = 0.99915, alphas_cumprod[999] = 0.00466.  Oracle and product tables agree
+    bit for bit (both fp32 cumprod of the same betas)."""
+    from difashion_b200.schedulers import B200DDIMScheduler, B200PNDMScheduler
+    for s in (OracleDDIMScheduler(), OraclePNDMScheduler(), B200DDIMScheduler(), B200PNDMScheduler()):
+        ac = s.alphas_cumprod.double()
+        sig = ((1 - ac) / ac).sqrt()
+        assert abs(float(sig[0]) - 0.0292) < 5e-5 and abs(float(sig[-1]) - 14.6146) < 5e-4
+        assert abs(float(ac[0]) - 0.99915) < 1e-5 and abs(float(ac[-1]) - 0.00466) < 1e-5
+        assert bool((ac[1:] < ac[:-1]).all())
+    assert torch.equal(OracleDDIMScheduler().alphas_cumprod, B200DDIMScheduler().alphas_cumprod)
+
+
 def test_ddim_closed_forms():
     s = OracleDDIMScheduler()
     s.set_timesteps(50)

@@ -243,3 +243,61 @@ def test_multi_stream_chunks_bitwise_equal_single_stream():
         outs.append(pipe.generate(**inp, num_inference_steps=50, max_steps=4, device="cuda").clone())
         assert (streams > 1) == bool(pipe._states[next(iter(pipe._states))].multi)
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+@pytest.mark.parametrize("scales,flags,shares", [((12.0, 4.0, 5.0), (True, True), True), ((12.0, 1.0, 5.0), (True, True), True),
+                                                 ((12.0, 4.0, 1.0), (True, True), True), ((12.0, 1.0, 1.0), (True, True), True),
+                                                 ((1.0, 4.0, 1.0), (True, True), False), ((1.0, 1.0, 5.0), (True, True), False),
+                                                 ((12.0, 4.0, 5.0), (False, True), True), ((12.0, 4.0, 5.0), (True, False), True)])
+def test_shared_cfg_prefix_is_bitwise_the_full_computation(scales, flags, shares):
+    """The last two CFG branches get the same UNet input and differ only in the prompt (difashion.py:388-431, :494-512):
+    computing the UNet ahead of its first cross-attention once for both (forward_nhwc(shared_tail=...)) must give the very
+    bits the full computation gives — per-branch eps of every step and the latents — for every branch layout, chunked or not,
+    eager or captured."""
+    from difashion_b200.mutual import MutualEncoder
+    from difashion_b200.pipeline import B200DiFashionPipeline
+    from difashion_b200.schedulers import B200DDIMScheduler
+    oracle, unet = _mk("tiny")
+    cfg = oracle.cfg
+    me = MutualEncoder(latent_size=cfg.sample_size, hid_dim=64).cuda()
+    olists = torch.tensor([[3, 0, 7, 9], [0, 5, 0, 2], [4, 4, 4, 0], [0, 0, 0, 0]])           # 8 blanks
+    inp = _gen_inputs(cfg, olists)
+    runs = {}
+    for share, max_rows, graph in ((False, 256, True), (True, 256, True), (True, 12, True), (True, 256, False)):
+        pipe = B200DiFashionPipeline(unet, me, B200DDIMScheduler(), use_history=flags[0], use_mutual_guidance=flags[1],
+                                     max_rows=max_rows, use_cuda_graph=graph, share_cfg_prefix=share)
+        rec = []
+        lat = pipe.generate(**inp, num_inference_steps=50, max_steps=3, device="cuda", category_guidance_scale=scales[0],
+                            hist_guidance_scale=scales[1], mutual_guidance_scale=scales[2], record=rec).clone()
+        st = pipe._states[next(iter(pipe._states))]
+        assert st.shared_tail == (share and shares)
+        runs[(share, max_rows, graph)] = (lat, [torch.cat([e.reshape(st.nb, -1, *e.shape[1:]) for e in r["eps_branches"]], 1) for r in rec])
+    base_lat, base_eps = runs[(False, 256, True)]
+    for key, (lat, eps) in runs.items():
+        assert torch.equal(lat, base_lat), key
+        for a, b in zip(eps, base_eps):
+            assert torch.equal(a, b), key
+
+
+def test_shared_tail_rows_are_not_read():
+    """forward_nhwc(shared_tail=k) promises not to read x_in[B-k:]: poison them and compare with the full computation."""
+    from difashion_b200 import ops
+    oracle, unet = _mk("tiny")
+    cfg = oracle.cfg
+    g = torch.Generator().manual_seed(11)
+    k = 3
+    x = torch.randn(2 * k, cfg.in_channels, cfg.sample_size, cfg.sample_size, generator=g)
+    x = torch.cat([x, x[k:]]).cuda()                                     # rows [2k, 3k) repeat rows [k, 2k)
+    ctx = torch.randn(3 * k, 77, cfg.cross_attention_dim, generator=g).cuda()
+    B = 3 * k
+    t = torch.full((B,), 421.0, device="cuda")
+    x_in = torch.empty(B, cfg.sample_size, cfg.sample_size, cfg.in_channels, dtype=torch.bfloat16, device="cuda")
+    ops.nchw_to_nhwc_bf16(x, x_in)
+    ws = unet.workspace(("tail", B), torch.device("cuda"))
+    c, kv = unet.set_context(ctx)
+    full = unet.forward_nhwc(x_in, t, c, kv, ws).clone()
+    x_in[2 * k:] = float("nan")
+    shared = unet.forward_nhwc(x_in, t, c, kv, ws, shared_tail=k).clone()
+    torch.cuda.synchronize()
+    assert torch.isfinite(shared).all() and torch.equal(shared, full)
+    assert not torch.equal(full[k:2 * k], full[2 * k:])                  # the two branches do differ (different prompts)

@@ -47,6 +47,12 @@ for rep in range(2):                           # launch 0 = warm-up, launch 1 = 
         out = torch.empty(R, 64, 64, 320, dtype=torch.float32, device=dev)
         for cg in (1, 2):
             ops.gemm([x], w, 320, out=out, taps=[ops.TAPS_3X3], conv_geom=(R, 64, 64), bias=rn(320).to(dev), cta_group=cg)
+    if "conv320wide" in which:                 # the same conv as two 160-column tiles vs ONE 320-column tile (two MMA sub-tiles sharing A)
+        x = rn(R, 64, 64, 320).bfloat16().to(dev)
+        w = ops.pack_conv3x3(rn(320, 320, 3, 3) * (9 * 320) ** -0.5).to(dev)
+        out = torch.empty(R, 64, 64, 320, dtype=torch.float32, device=dev)
+        for bn in (160, 0):                    # 0 = automatic: the wide tile (K = 2880 >= 2048)
+            ops.gemm([x], w, 320, out=out, taps=[ops.TAPS_3X3], conv_geom=(R, 64, 64), bias=rn(320).to(dev), cta_group=2, block_n=bn)
     if "conv640" in which:                     # ResNet conv 640->640 at 32x32 (N = 640: three 224-column tiles), 1-CTA and CTA pair
         x = rn(R, 32, 32, 640).bfloat16().to(dev)
         w = ops.pack_conv3x3(rn(640, 640, 3, 3) * (9 * 640) ** -0.5).to(dev)
