@@ -51,6 +51,7 @@ class GemmParams(C.Structure):
         ("block_n", C.c_int32),
         ("gn_partial", C.c_void_p),
         ("cta_group", C.c_int32),
+        ("up2x", C.c_int32),
     ]
 
 

@@ -226,6 +226,7 @@ int dfb_gemm_f32(const dfb_gemm_params* q, void* stream) {
     kp_total += q->ntaps[s] * ((q->a_c[s] + 63) / 64 * 64);
   }
   DFB_REQUIRE(q->act >= DFB_ACT_NONE && q->act <= DFB_ACT_GELU, "dfb_gemm_f32: unknown activation");
+  DFB_REQUIRE(q->up2x == 0, "dfb_gemm_f32: the fused upsample phases exist on the tcgen05 path only (upsample, then convolve)");
   DFB_REQUIRE(kp_total <= q->w_ld, "dfb_gemm_f32: packed weight K extent smaller than the A operand implies");
   if (q->conv) DFB_REQUIRE(q->B > 0 && q->H > 0 && q->W > 0 && (long long)q->B * q->H * q->W == q->M, "dfb_gemm_f32: conv geometry does not match M");
   p.nseg = q->nseg; p.conv = q->conv ? 1 : 0; p.B = q->B; p.H = q->H; p.W = q->W; p.M = q->M; p.N = q->N;

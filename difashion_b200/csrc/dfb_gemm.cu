@@ -55,6 +55,8 @@ struct GemmKernelParams {
   void* out;
   int out_ld, out_fp32, geglu, vec_ok, act;
   float* gn_partial;   // optional GroupNorm partial statistics of the fp32 output
+  int up_w, up_a, up_b, up_blk;   // up_w > 0: phase (up_a, up_b) of a fused nearest-2x upsample + 3x3 conv; rows are scattered into
+                                  // the [B, 2H, 2W, N] output (up_w = W of the input, up_blk = H*W/32 partial blocks per image)
 };
 
 // Epilogue specialisations (compile-time, so the hot epilogue loop carries no runtime flag tests and the
@@ -584,7 +586,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
             gs0 += x[0] + x[1]; gq0 += x[0] * x[0] + x[1] * x[1];
             gs1 += x[2] + x[3]; gq1 += x[2] * x[2] + x[3] * x[3];
           }
-          const size_t off = (size_t)m * p.out_ld + col;
+          // fused upsample phase: row (b*H + i)*W + j of the low-resolution grid -> pixel (2i + a, 2j + b) of the output
+          const size_t orow = p.up_w > 0 ? (size_t)(2 * (m / p.up_w) + p.up_a) * (size_t)(2 * p.up_w) + (size_t)(2 * (m % p.up_w) + p.up_b)
+                                         : (size_t)m;
+          const size_t off = orow * p.out_ld + col;
           if (f_out32) {
             float* dst = reinterpret_cast<float*>(p.out) + off;
             if (vec) *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
@@ -611,9 +616,13 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
             gs0 += __shfl_xor_sync(0xffffffffu, gs0, o); gq0 += __shfl_xor_sync(0xffffffffu, gq0, o);
             gs1 += __shfl_xor_sync(0xffffffffu, gs1, o); gq1 += __shfl_xor_sync(0xffffffffu, gq1, o);
           }
-          if (lane < 8 && nval >= 4 && row0 < p.M)
-            *reinterpret_cast<float4*>(p.gn_partial + ((size_t)(row0 >> 5) * (size_t)(p.N >> 1) + (size_t)(col >> 1)) * 2) =
+          if (lane < 8 && nval >= 4 && row0 < p.M) {
+            size_t blk = (size_t)(row0 >> 5);
+            if (p.up_w > 0)      // this phase's blocks of image `img` sit at [img * 4 * up_blk + phase * up_blk, ...)
+              blk = (blk / (size_t)p.up_blk) * (size_t)(4 * p.up_blk) + (size_t)((2 * p.up_a + p.up_b) * p.up_blk) + blk % (size_t)p.up_blk;
+            *reinterpret_cast<float4*>(p.gn_partial + (blk * (size_t)(p.N >> 1) + (size_t)(col >> 1)) * 2) =
                 make_float4(gs0, gq0, gs1, gq1);
+          }
         }
         __syncwarp();
       }
@@ -858,6 +867,17 @@ extern "C" int dfb_gemm(const dfb_gemm_params* q, void* stream_) {
   kp.geglu = q->geglu ? 1 : 0;
   kp.act = q->act;
   kp.gn_partial = q->gn_partial;
+  kp.up_w = 0; kp.up_a = 0; kp.up_b = 0; kp.up_blk = 1;
+  if (q->up2x != 0) {
+    DFB_REQUIRE(q->up2x >= 1 && q->up2x <= 4, "dfb_gemm: up2x must be 0 or 1 + 2a + b");
+    DFB_REQUIRE(q->conv && !q->geglu && q->residual == nullptr && q->rowbias == nullptr,
+                "dfb_gemm: up2x needs conv geometry and takes no residual / rowbias / GEGLU");
+    DFB_REQUIRE(!q->gn_partial || (q->H * q->W) % 32 == 0, "dfb_gemm: up2x with gn_partial needs H*W % 32 == 0");
+    kp.up_w = q->W;
+    kp.up_a = (q->up2x - 1) >> 1;
+    kp.up_b = (q->up2x - 1) & 1;
+    kp.up_blk = (q->H * q->W) / 32 > 0 ? (q->H * q->W) / 32 : 1;
+  }
   if (q->gn_partial)
     DFB_REQUIRE(q->out_dtype == DFB_DTYPE_F32 && !q->geglu && q->M % 32 == 0 && q->N % 4 == 0 &&
                     (reinterpret_cast<uintptr_t>(q->gn_partial) & 15) == 0,
@@ -873,7 +893,7 @@ extern "C" int dfb_gemm(const dfb_gemm_params* q, void* stream_) {
 
   // epilogue specialisation
   int mode = EPI_GENERIC;
-  const bool simple = kp.vec_ok && (q->N % 4) == 0 && kp.act == 0 && (q->residual == nullptr || kp.res_fp32) &&
+  const bool simple = kp.vec_ok && (q->N % 4) == 0 && kp.act == 0 && q->up2x == 0 && (q->residual == nullptr || kp.res_fp32) &&
                       (q->bias == nullptr || (reinterpret_cast<uintptr_t>(q->bias) & 15) == 0) &&
                       (q->rowbias == nullptr || (kp.rows_per_batch % 32 == 0 && (q->rowbias_ld % 4) == 0 &&
                                                  (reinterpret_cast<uintptr_t>(q->rowbias) & 15) == 0));

@@ -80,6 +80,40 @@ def pack_linear(weight: torch.Tensor, dtype: torch.dtype = torch.bfloat16) -> to
     return out.contiguous()
 
 
+def upsample_phase_taps(a: int, b: int):
+    """Tap table ``(dh, dw, channel_offset)`` of phase (a, b) of a fused nearest-2x upsample + 3x3 conv, pad 1: output pixel
+    ``(2i + a, 2j + b)`` reads the upsampled rows ``2i + a + {-1, 0, 1}``, i.e. input rows ``{i - 1, i, i}`` (a = 0) or
+    ``{i, i, i + 1}`` (a = 1) — two distinct rows; same for columns.  Out-of-range rows / columns are the conv's zero padding
+    in both formulations (the upsampled image's border maps to the input's border)."""
+    dhs = (-1, 0) if a == 0 else (0, 1)
+    dws = (-1, 0) if b == 0 else (0, 1)
+    return [(dh, dw, 0) for dh in dhs for dw in dws]
+
+
+def pack_upsample_phases(weight: torch.Tensor, dtype: torch.dtype = torch.bfloat16):
+    """OIHW 3x3 weight of ``Upsample2D.conv`` -> four packed ``[O, 4 * ceil64(I)]`` matrices, one per output phase
+    (a, b) in the order (0,0), (0,1), (1,0), (1,1), for the taps of ``upsample_phase_taps(a, b)``: the 3x3 kernel rows that
+    land on the same input row are summed (in fp32, before the operand rounding): phase a = 0 -> rows [w0, w1 + w2],
+    a = 1 -> [w0 + w1, w2]; same for columns.  16 tap-GEMMs on the low-resolution grid replace 9 on the 4x larger one."""
+    o, i, kh, kw = weight.shape
+    assert kh == 3 and kw == 3
+    w = weight.detach().float()
+    ip = ceil64(i)
+    rows = {0: [w[:, :, 0:1].sum(2), w[:, :, 1:3].sum(2)], 1: [w[:, :, 0:2].sum(2), w[:, :, 2:3].sum(2)]}    # [O, I, 3] each
+    out = []
+    for a in (0, 1):
+        for b in (0, 1):
+            pk = torch.zeros(o, 4, ip, dtype=torch.float32, device=w.device)
+            t = 0
+            for r in rows[a]:
+                cols = [r[:, :, 0:1].sum(2), r[:, :, 1:3].sum(2)] if b == 0 else [r[:, :, 0:2].sum(2), r[:, :, 2:3].sum(2)]
+                for c in cols:
+                    pk[:, t, :i] = c
+                    t += 1
+            out.append(pk.reshape(o, 4 * ip).to(dtype).contiguous())
+    return out
+
+
 def pack_conv3x3(weight: torch.Tensor, dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
     """OIHW 3x3 weight -> ``[O, 9 * ceil64(I)]`` with k = (kh*3+kw) * ceil64(I) + i."""
     o, i, kh, kw = weight.shape
@@ -113,13 +147,17 @@ def gemm(a: Sequence[torch.Tensor], w: torch.Tensor, n: int, *, out: torch.Tenso
          a_c: Optional[Sequence[int]] = None, conv_geom: Optional[Tuple[int, int, int]] = None,
          bias: Optional[torch.Tensor] = None, rowbias: Optional[torch.Tensor] = None,
          rows_per_batch: int = 1, residual: Optional[torch.Tensor] = None, geglu: bool = False,
-         block_n: int = 0, act: int = 0, gn_partial: Optional[torch.Tensor] = None, cta_group: int = 0) -> torch.Tensor:
+         block_n: int = 0, act: int = 0, gn_partial: Optional[torch.Tensor] = None, cta_group: int = 0,
+         up_phase: Optional[Tuple[int, int]] = None) -> torch.Tensor:
     """``out = epilogue(A @ w.T)`` on tcgen05 tensor cores (see ``dfb_gemm`` in include/dfb200.h).
 
     a:    1 or 2 bf16 operands; each ``[M, C]`` (plain) or ``[B, H, W, C]`` (conv), last dim
           contiguous; the row pitch is taken from ``stride(-2)``.
     taps: per segment a list of ``(dh, dw, channel_offset)``; default one centre tap.
     a_c:  per segment channel extent read per tap (default: the tensor's last dim).
+    up_phase: ``(a, b)``: this conv is phase (a, b) of a fused nearest-2x upsample + 3x3 conv (``pack_upsample_phases``):
+          ``a`` is the LOW-resolution ``[B, H, W, C]`` input, ``out`` the whole ``[B, 2H, 2W, N]`` output of which this call
+          writes the pixels ``(2i + a, 2j + b)``; ``gn_partial`` is the partial-statistics buffer of the whole output.
     """
     f32 = a[0].dtype == torch.float32          # fp32 verification path (CUDA cores): fp32 operands throughout
     if f32 and geglu:
@@ -137,6 +175,10 @@ def gemm(a: Sequence[torch.Tensor], w: torch.Tensor, n: int, *, out: torch.Tenso
     m_rows = 1
     for d in out.shape[:-1]:
         m_rows *= d
+    if up_phase is not None:
+        assert conv_geom is not None and m_rows == 4 * conv_geom[0] * conv_geom[1] * conv_geom[2] and out.is_contiguous()
+        m_rows //= 4
+        p.up2x = 1 + 2 * int(up_phase[0]) + int(up_phase[1])
     op_dtype = torch.float32 if f32 else torch.bfloat16
     for s, t in enumerate(a):
         assert t.dtype == op_dtype and t.is_cuda and t.stride(-1) == 1
@@ -169,7 +211,7 @@ def gemm(a: Sequence[torch.Tensor], w: torch.Tensor, n: int, *, out: torch.Tenso
     p.block_n = block_n
     p.cta_group = cta_group
     if gn_partial is not None:
-        assert gn_partial.dtype == torch.float32 and gn_partial.numel() >= (m_rows // 32) * (n // 2) * 2
+        assert gn_partial.dtype == torch.float32 and gn_partial.numel() >= ((4 if up_phase is not None else 1) * m_rows // 32) * (n // 2) * 2
         p.gn_partial = gn_partial.data_ptr()
     e0 = _prof_begin()
     if f32:

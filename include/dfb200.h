@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define DFB200_ABI_VERSION 4
+#define DFB200_ABI_VERSION 5
 
 #define DFB_OK 0
 #define DFB_ERR_INVALID (-1)
@@ -94,6 +94,14 @@ typedef struct dfb_gemm_params {
                             (dfb_groupnorm_fused); needs fp32 output, M % 32 == 0, N % 4 == 0            */
   int32_t cta_group;     /* 0 = automatic; 1 = one CTA per 128-row tile; 2 = CTA pair (cluster of 2 on one TPC,
                             tcgen05.mma.cta_group::2 over 256 rows, each CTA feeding half of the B tile)  */
+  int32_t up2x;          /* 0 = off.  1 + 2a + b (a, b in {0, 1}): this conv computes phase (a, b) of a nearest-2x upsample
+                            followed by a 3x3 convolution (diffusers Upsample2D) on the LOW-resolution input: output
+                            pixel (2i + a, 2j + b) depends on a 2x2 input window only, with the 3x3 weights summed per
+                            window tap (4 phase GEMMs of 4 taps instead of one 9-tap GEMM on 4x the pixels: 16/36 of the
+                            MACs).  Needs conv == 1; row m = (b*H + i)*W + j is stored at row
+                            (2*(m / W) + a) * 2W + 2*(m % W) + b of `out` ([B, 2H, 2W, N]); gn_partial (if given) is the
+                            buffer of the whole [B*2H*2W, N] output and receives this phase's blocks at
+                            [img * 4*HW/32 + phase * HW/32 + block].  tcgen05 path only.                      */
 } dfb_gemm_params;
 
 int dfb_gemm(const dfb_gemm_params* p, void* stream);

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_library_loads_and_exports_every_declared_symbol():
     from difashion_b200 import _lib
     lib = _lib.load()
-    assert lib.dfb_abi_version() == 4
+    assert lib.dfb_abi_version() == 5
     header = open(os.path.join(ROOT, "include", "dfb200.h")).read()
     declared = set(re.findall(r"\b(dfb_[a-z0-9_]+)\s*\(", header))
     assert declared, "no declarations parsed"
@@ -105,6 +105,36 @@ def test_space_to_depth_tap_table_is_a_stride2_conv():
     got = _emulate_gemm([(s2d.bfloat16(), ops.s2d_taps(C), C)], None, ops.pack_conv3x3(w), 3, (B, H // 2, W // 2))
     ref = F.conv2d(x.bfloat16().double().permute(0, 3, 1, 2), w.bfloat16().double(), stride=2, padding=1).permute(0, 2, 3, 1)
     assert torch.allclose(got, ref, atol=1e-9)
+
+
+def test_upsample_phase_tables_are_the_upsample_conv():
+    """Upsample2D = nearest-2x + conv3x3(pad 1) == four 2x2 phase convolutions on the low-resolution input with summed
+    weights, scattered to pixels (2i + a, 2j + b) by the row map dfb_gemm(up2x) uses — exact in real arithmetic."""
+    from difashion_b200 import ops
+    torch.manual_seed(4)
+    B, H, W, C, N = 2, 4, 8, 16, 5
+    x = torch.randn(B, H, W, C).bfloat16()
+    w = torch.randn(N, C, 3, 3)
+    packs = ops.pack_upsample_phases(w, torch.float32)
+    assert len(packs) == 4 and packs[0].shape == (N, 4 * 64)
+    out = torch.zeros(B * 2 * H * 2 * W, N, dtype=torch.float64)
+    m = torch.arange(B * H * W)
+    for a in (0, 1):
+        for b in (0, 1):
+            ph = _emulate_gemm([(x, ops.upsample_phase_taps(a, b), C)], None, packs[2 * a + b], N, (B, H, W)).reshape(B * H * W, N)
+            rows = (2 * (m // W) + a) * (2 * W) + 2 * (m % W) + b           # the kernel's scatter: row m -> pixel (2i+a, 2j+b)
+            out[rows] = ph
+    up = F.interpolate(x.double().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest")
+    ref = F.conv2d(up, w.double(), padding=1).permute(0, 2, 3, 1).reshape(-1, N)
+    assert torch.allclose(out, ref, atol=1e-5)          # fp32-summed weights vs fp64 reference
+    assert ops.upsample_phase_taps(0, 1) == [(-1, 0, 0), (-1, 1, 0), (0, 0, 0), (0, 1, 0)]
+    # partial-statistics block map: image-major, then phase, then the phase's own 32-row blocks
+    blk_per_img = H * W // 32
+    q = torch.arange(B * blk_per_img)
+    seen = set()
+    for phase in range(4):
+        seen |= set(((q // blk_per_img) * 4 * blk_per_img + phase * blk_per_img + q % blk_per_img).tolist())
+    assert seen == set(range(B * 4 * blk_per_img))
 
 
 def test_geglu_and_head_padding_layouts():
