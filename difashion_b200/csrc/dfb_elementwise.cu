@@ -220,6 +220,18 @@ __global__ void __launch_bounds__(256) pad_cast_rows_kernel(const TIn* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
+// fp32 -> MMA operand (bf16, or fp32 on the verification path), 4 elements per thread: the low-resolution input of the
+// fused upsample-phase convolutions (dfb_gemm up2x)
+// ---------------------------------------------------------------------------------------------
+template <typename TOut>
+__global__ void __launch_bounds__(256) cast_rows_kernel(const float* __restrict__ in, TOut* __restrict__ out, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(in) + i);
+    store4(out + 4 * i, v.x, v.y, v.z, v.w);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // nearest-2x upsample (Upsample2D, App. A.2 item 7): fp32 NHWC [B,H,W,C] -> bf16 NHWC [B,2H,2W,C]
 // ---------------------------------------------------------------------------------------------
 template <typename TOut>
@@ -415,6 +427,17 @@ int dfb_pad_cast_rows(const void* in, int in_dtype, void* out, int out_dtype, in
     pad_cast_rows_kernel<__nv_bfloat16, float><<<g, 256, 0, st>>>((const __nv_bfloat16*)in, (float*)out, B, S, S_pad, D);
   else
     pad_cast_rows_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, B, S, S_pad, D);
+  DFB_CHECK_CUDA(cudaGetLastError());
+  return DFB_OK;
+}
+
+int dfb_cast_f32(const float* in, void* out, int out_dtype, long long n, void* stream) {
+  DFB_REQUIRE(in && out && n > 0 && n % 4 == 0, "dfb_cast_f32: bad args (n must be a positive multiple of 4)");
+  DFB_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+              "dfb_cast_f32: buffers must be 16-byte aligned");
+  const int g = grid_for(n / 4, 256);
+  if (out_dtype == DFB_DTYPE_F32) cast_rows_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>(in, (float*)out, n / 4);
+  else cast_rows_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream>>>(in, (__nv_bfloat16*)out, n / 4);
   DFB_CHECK_CUDA(cudaGetLastError());
   return DFB_OK;
 }

@@ -439,6 +439,15 @@ def pad_cast_rows(x: torch.Tensor, out: torch.Tensor):
     return out
 
 
+@_profiled("cast")
+def cast_f32(x: torch.Tensor, out: torch.Tensor):
+    """fp32 -> ``out.dtype`` (the MMA operand type), same shape, both contiguous."""
+    assert x.dtype == torch.float32 and x.is_contiguous() and out.is_contiguous() and x.numel() == out.numel()
+    check(_lib.load().dfb_cast_f32(x.data_ptr(), out.data_ptr(), _dt(out), x.numel(), _stream()), "dfb_cast_f32")
+    _count(1)
+    return out
+
+
 @_profiled("upsample2x")
 def upsample2x(x: torch.Tensor, out: torch.Tensor):
     b, h, w, c = x.shape

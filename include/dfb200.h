@@ -204,6 +204,8 @@ int dfb_mutual_blend(const float* x, const float* m, const float* hist, const fl
 int dfb_nchw_to_nhwc(const void* in, int in_dtype, void* out, int out_dtype, int B, int C, int HW, void* stream);
 int dfb_nhwc_to_nchw(const float* in, void* out, int out_dtype, int B, int C, int HW, void* stream);
 int dfb_pad_cast_rows(const void* in, int in_dtype, void* out, int out_dtype, int B, int S, int S_pad, int D, void* stream);
+/* fp32 [n] -> MMA operand dtype (n % 4 == 0, 16-byte aligned): the low-resolution input of the fused upsample phases. */
+int dfb_cast_f32(const float* in, void* out, int out_dtype, long long n, void* stream);
 /* Upsample2D nearest-2x (fp32 NHWC -> NHWC operand) and the space-to-depth feeding Downsample2D's
  * stride-2 conv (fp32 NHWC [B,H,W,C] -> [B,H/2,W/2,4C]). */
 int dfb_upsample2x(const float* in, void* out, int out_dtype, int B, int H, int W, int C, void* stream);

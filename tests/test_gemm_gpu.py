@@ -309,3 +309,82 @@ def test_wide_tile_is_the_automatic_choice_for_deep_n320_convs():
     assert torch.equal(o1, o2) and torch.equal(p1, p2)
     ref = F.conv2d(x[:2].cpu().permute(0, 3, 1, 2).double(), _rand((C, C, 3, 3), 26, (9 * C) ** -0.5).bfloat16().double(), bias.cpu().double(), padding=1)
     assert rel_l2(o1[:2].permute(0, 3, 1, 2).cpu(), ref) < 1e-5
+
+
+@pytest.mark.parametrize("B,H,W,C,N", [(3, 8, 8, 1280, 1280), (2, 16, 16, 1280, 1280), (2, 32, 32, 640, 640), (2, 8, 8, 64, 128),
+                                       (150, 32, 32, 64, 64)])
+def test_upsample_as_four_phase_convs(B, H, W, C, N):
+    """Upsample2D (nearest-2x + conv3x3 pad 1) as four 4-tap phase convolutions on the low-resolution input
+    (dfb_gemm up2x: rows scattered to pixels (2i + a, 2j + b); GroupNorm partials of the WHOLE output, image-major).
+    Reference: fp64 upsample + conv of the same bf16 input with the bf16-rounded ORIGINAL weights — the phases round the
+    summed weights instead, so the bar is operand-rounding level (1e-2 of it), and exact vs the phases' own packed weights."""
+    ops = _ops()
+    x = _rand((B, H, W, C), 11)
+    w = _rand((N, C, 3, 3), 12, (9 * C) ** -0.5)
+    bias = _rand((N,), 13).cuda()
+    lo = torch.empty(B, H, W, C, dtype=torch.bfloat16, device="cuda")
+    ops.cast_f32(x.cuda(), lo)
+    assert torch.equal(lo.cpu(), x.bfloat16())
+    packs = [p.cuda() for p in ops.pack_upsample_phases(w)]
+    out = torch.full((B, 2 * H, 2 * W, N), float("nan"), dtype=torch.float32, device="cuda")
+    hw_ok = (4 * H * W) % 32 == 0 and (H * W) % 32 == 0
+    part = torch.zeros(ops.gn_partial_shape(B * 4 * H * W, N), dtype=torch.float32, device="cuda") if hw_ok else None
+    for a in (0, 1):
+        for b in (0, 1):
+            ops.gemm([lo], packs[2 * a + b], N, out=out, taps=[ops.upsample_phase_taps(a, b)], conv_geom=(B, H, W), bias=bias,
+                     gn_partial=part, up_phase=(a, b))
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()                       # every output pixel was written by exactly one phase
+    nb = min(B, 3)                                          # fp64 reference on a few images (first, and the last ones)
+    sel = [0] + list(range(B - nb + 1, B))
+    up = F.interpolate(lo[sel].cpu().double().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest")
+    # exact reference for the phases' own arithmetic: per phase a 2x2 conv with the packed (summed, bf16) weights
+    ref_exact = torch.zeros(len(sel), 2 * H, 2 * W, N, dtype=torch.float64)
+    cp = (C + 63) // 64 * 64
+    xl = lo[sel].cpu().double()
+    for a in (0, 1):
+        for b in (0, 1):
+            acc = torch.zeros(len(sel), H, W, N, dtype=torch.float64)
+            for t, (dh, dw, _) in enumerate(ops.upsample_phase_taps(a, b)):
+                sh = torch.zeros_like(xl)
+                hs, he = max(0, -dh), min(H, H - dh)
+                ws_, we = max(0, -dw), min(W, W - dw)
+                sh[:, hs:he, ws_:we] = xl[:, hs + dh:he + dh, ws_ + dw:we + dw]
+                acc += sh @ packs[2 * a + b][:, t * cp:t * cp + C].cpu().double().t()
+            ref_exact[:, a::2, b::2] = acc + bias.cpu().double()
+    got = out[sel].cpu().double()
+    assert rel_l2(got, ref_exact) < 1e-5, err_report(got.reshape(-1, N), ref_exact.reshape(-1, N), "phase conv (exact)")
+    ref = F.conv2d(up, w.bfloat16().double(), bias.cpu().double(), padding=1).permute(0, 2, 3, 1)
+    assert rel_l2(got, ref) < 5e-3
+    if part is not None:
+        # per image the partial blocks sum to the image's channel-pair sums, whatever their order
+        blk = 4 * H * W // 32
+        s = part.view(B, blk, N // 2, 2).double().sum(1).cpu()
+        o = out.view(B, 4 * H * W, N // 2, 2).double().cpu()
+        assert rel_l2(s[..., 0], o.sum(dim=(1, 3))) < 1e-5 and rel_l2(s[..., 1], (o ** 2).sum(dim=(1, 3))) < 1e-5
+
+
+def test_unet_upsample_phases_match_upsample_then_conv():
+    """The UNet with the fused upsample phases vs the literal upsample-then-convolve sequence: same network, the three
+    Upsample2D convs round summed instead of individual weights -> agreement far inside the parity budget."""
+    from oracle.unet_oracle import make_oracle_unet, tiny_config
+    from difashion_b200.unet import B200UNet2DConditionModel
+    cfg = tiny_config()
+    o = make_oracle_unet(cfg, seed=0)
+    unet = B200UNet2DConditionModel(sample_size=cfg.sample_size, in_channels=cfg.in_channels, block_out_channels=tuple(cfg.block_out_channels),
+                                    cross_attention_dim=cfg.cross_attention_dim, attention_head_dim=cfg.attention_head_dim)
+    unet.load_state_dict(o.state_dict())
+    unet.cuda()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(4, cfg.in_channels, cfg.sample_size, cfg.sample_size, generator=g)
+    ctx = torch.randn(4, 77, cfg.cross_attention_dim, generator=g)
+    ref = o(x, torch.tensor(500), ctx)
+    outs = {}
+    try:
+        for flag in (True, False):
+            B200UNet2DConditionModel.upsample_phases = flag
+            outs[flag] = unet(x.cuda(), 500, ctx.cuda()).sample.cpu()
+    finally:
+        B200UNet2DConditionModel.upsample_phases = True
+    assert rel_l2(outs[True], ref) <= 1e-2 and rel_l2(outs[False], ref) <= 1e-2
+    assert 0 < rel_l2(outs[True], outs[False]) < 3e-3

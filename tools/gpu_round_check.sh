@@ -14,7 +14,7 @@ timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_ref
 timeout 600 ncu --profile-from-start off --clock-control none --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
   --csv --log-file $O/ncu_launches_step_$V.csv python tools/step_traffic.py > $O/step_traffic_$V.log 2>&1
 python tools/step_traffic.py --summarise $O/ncu_launches_step_$V.csv $O/step_traffic_$V.json >> $O/step_traffic_$V.log 2>&1
-for n in 1 4 64; do
+for n in ${SWEEP:-1 4 64}; do
   timeout 300 python bench.py --outfits $n --steps 10 --no-e2e --no-cpu-baseline > $O/bench_${V}_sweep_${n}outfits.json 2>> $O/sweep_$V.err
 done
 ls -la $O
