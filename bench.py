@@ -137,7 +137,7 @@ def workload_config(args, world):
             "parallelism": f"outfit-sharded replicas x{world}, no in-loop collective"}
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, guard):
     """--impl reference: the reference path's CPU implementation (oracle port) on the host cores."""
     if rank != 0:
         return
@@ -190,10 +190,26 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "outfits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    guard.emit(json.dumps(line))
+
+
+class _StdoutGuard:
+    """The contract is ONE JSON line on rank 0's stdout.  Libraries write there too (NCCL prints its version banner to
+    stdout when NCCL_DEBUG is set in the environment, as on the pool's multi-GPU boxes), so for the duration of the run
+    file descriptor 1 points at stderr and the JSON line goes to the saved descriptor."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line: str):
+        sys.stdout.flush()
+        os.write(self.saved, (line + "\n").encode())
 
 
 def main():
+    guard = _StdoutGuard()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=DDIM_STEPS)
@@ -217,7 +233,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, guard)
         return
 
     import torch.distributed as dist
@@ -392,7 +408,7 @@ def main():
         line["e2e"] = e2e
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line), flush=True)
+    guard.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
