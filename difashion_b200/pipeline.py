@@ -210,6 +210,15 @@ class B200DiFashionPipeline:
         sched = self.scheduler
         sched.set_timesteps(num_inference_steps)
         st.timesteps = [int(t) for t in sched.timesteps]
+        # PLMS keeps the last four noise predictions of its sample (difashion.py:569 -> PNDMScheduler.step_plms): with more
+        # than one row chunk every chunk gets its own scheduler state (same config and timesteps)
+        st.chunk_scheds = None
+        if not isinstance(sched, B200DDIMScheduler) and len(st.chunks) > 1:
+            st.chunk_scheds = []
+            for _ in st.chunks:
+                c = type(sched)(**dict(sched.config))
+                c.set_timesteps(num_inference_steps)
+                st.chunk_scheds.append(c)
 
         st.latents.copy_(init_latents, non_blocking=True)
         if float(sched.init_noise_sigma) != 1.0:
@@ -266,7 +275,7 @@ class B200DiFashionPipeline:
                         cur.wait_stream(s_)
                 st.step_graph = g
             st.step_graph.replay()
-        for ch in st.chunks:
+        for ci, ch in enumerate(st.chunks):
             if st.multi:
                 eps = ch.eps
                 step_launches += ch.launches
@@ -295,9 +304,7 @@ class B200DiFashionPipeline:
             if isinstance(sched, B200DDIMScheduler):
                 sched.cfg_step(eps, st.weights, t, x, eta=ddim_eta, generator=generator, out=x)
             else:
-                if len(st.chunks) != 1:
-                    raise NotImplementedError("PLMS keeps per-call history: run it with a single row chunk")
-                sched.cfg_step(eps, st.weights, t, x, out=x)
+                (sched if st.chunk_scheds is None else st.chunk_scheds[ci]).cfg_step(eps, st.weights, t, x, out=x)
             step_launches += 1
         self.last_step_launches = step_launches
         if record is not None:

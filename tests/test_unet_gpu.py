@@ -301,3 +301,22 @@ def test_shared_tail_rows_are_not_read():
     torch.cuda.synchronize()
     assert torch.isfinite(shared).all() and torch.equal(shared, full)
     assert not torch.equal(full[k:2 * k], full[2 * k:])                  # the two branches do differ (different prompts)
+
+
+def test_plms_row_chunks_keep_their_own_history():
+    """PNDM/PLMS (the reference's scheduler, difashion.py:64) carries four past noise predictions per sample: a batch split
+    into row chunks must give the bits of the unsplit batch (7 model calls: warm-up, the repeated second timestep, 4th order)."""
+    from difashion_b200.mutual import MutualEncoder
+    from difashion_b200.pipeline import B200DiFashionPipeline
+    from difashion_b200.schedulers import B200PNDMScheduler
+    oracle, unet = _mk("tiny")
+    cfg = oracle.cfg
+    me = MutualEncoder(latent_size=cfg.sample_size, hid_dim=64).cuda()
+    olists = torch.zeros(3, 4, dtype=torch.long)                       # 12 items -> 48 rows
+    inp = _gen_inputs(cfg, olists)
+    outs = []
+    for max_rows in (256, 16, 20):                                     # 1 chunk / 3 chunks of 4 items / chunks of 5, 5, 2
+        pipe = B200DiFashionPipeline(unet, me, B200PNDMScheduler(), max_rows=max_rows)
+        outs.append(pipe.generate(**inp, num_inference_steps=50, max_steps=7, device="cuda").clone())
+        assert len(pipe._states[next(iter(pipe._states))].chunks) == {256: 1, 16: 3, 20: 3}[max_rows]
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
