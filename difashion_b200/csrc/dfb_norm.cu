@@ -359,13 +359,14 @@ int dfb_groupnorm(const float* src0, int c0, int ld0, const float* src1, int c1,
   DFB_REQUIRE((Cch / groups) % 2 == 0 && c0 % 4 == 0 && c1 % 4 == 0, "dfb_groupnorm: channels/group must be even, sources multiple of 4");
   DFB_REQUIRE(Cch / 4 <= GN_THREADS * GN_MAX_VEC_PER_THREAD, "dfb_groupnorm: too many channels");
   DFB_REQUIRE(ld0 % 4 == 0 && ld1 % 4 == 0 && ld_out % 4 == 0 && ld_raw % 4 == 0, "dfb_groupnorm: pitches must be multiples of 4");
-  // enough blocks to fill the machine: ~4 waves of CTAs over (B x pixel chunks), <= GN_MAX_CHUNKS per image
-  int chunks = (num_sms() * 4 + B - 1) / B;
-  if (chunks > hw) chunks = hw;
-  if (chunks > GN_MAX_CHUNKS) chunks = GN_MAX_CHUNKS;
-  if (chunks < 1) chunks = 1;
-  const int ppb = (hw + chunks - 1) / chunks;
-  chunks = (hw + ppb - 1) / ppb;
+  // Pixels per block are a function of the IMAGE size only (32 .. hw / GN_MAX_CHUNKS): the order in which an image's
+  // statistics are summed — hence every bit of its output — must not depend on how many images share the launch, or the
+  // row chunks of a batch would not reproduce the unsplit batch.  (It used to be sized to fill the machine from B: measured
+  // on B200, a 48-row batch of 4x4 images then differed from the same rows run 16 at a time in the last bits of the
+  // statistics, which flips bf16 roundings downstream.)
+  int ppb = (hw + GN_MAX_CHUNKS - 1) / GN_MAX_CHUNKS;
+  if (ppb < 32) ppb = 32;
+  const int chunks = (hw + ppb - 1) / ppb;
   float* stats = stats_ws;                                   // [B, groups, 2] (mean, rstd)
   float* partial = stats_ws + (size_t)B * groups * 2;        // [B, chunks, groups, 2]
   groupnorm_stats_kernel<<<dim3(chunks, B), GN_THREADS, 0, stream>>>(src0, c0, ld0, src1, c1, ld1, hw, groups, ppb, partial);
