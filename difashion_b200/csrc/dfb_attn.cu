@@ -709,6 +709,302 @@ attn_fwd_db_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant_
 
 
 // =================================================================================================
+// Ping-pong variant (EXPERIMENT, opt-in through dbg_flags bit12; not yet run on hardware — written at the end of round 1
+// from the reading of the stamps in profiles/r01_attention_experiments.md, session 5).
+//
+// The shipped kernel keeps two CTAs per SM so that one CTA's bookkeeping (wait for S, P store, fence, arrive) can hide under
+// the other's exponentials.  The stamps say it does not happen: two streams that contend for the one MUFU progress at equal
+// speed, reach their bookkeeping together and idle together (1029 + ~380 cycles per tile instead of ~1024).  Here the
+// alternation is explicit: ONE CTA per SM owns two query tiles (256 rows) of one (batch, head); softmax warpgroup A
+// (warps 0..3) works on tile 0, warpgroup B (warps 4..7) on tile 1, and two named barriers pass the "exponential turn"
+// back and forth (FlashAttention-3's ping-pong, applied to the MUFU): while A computes the exponentials of its KV tile j,
+// B stores P_j, arrives, and waits for its next S; then they swap.  K/V tiles are loaded ONCE for both query tiles.
+// TMEM: S_A[2] | S_B[2] | O_A | O_B = 4 x 64 + 2 x dp <= 512 columns (dp <= 64: the S = 4096, d = 40 -> 48 layers).
+// KV tile 64, P through tensor memory (TS-form PV).  Same numerics as attn_fwd_db_kernel<64, true>.
+// =================================================================================================
+constexpr int ATT_PP_THREADS = 320;     // 8 softmax warps + TMA producer + MMA issuer
+
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+__global__ void __launch_bounds__(ATT_PP_THREADS, 1)
+attn_fwd_pp_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnKernelParams p) {
+  constexpr int KV = 64;
+  constexpr int NST_MAX = 4;
+  const int NST = p.kv_stages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int dchunks = p.dp >> 4;
+  const uint32_t q_tile_bytes = (uint32_t)dchunks * ATT_BLOCK_Q * 32u;
+  constexpr uint32_t kv_chunk_bytes = KV * 32u;
+  const uint32_t kv_tile_bytes = (uint32_t)dchunks * kv_chunk_bytes;
+  const uint32_t sQ = smem_base;                                            // Q tile 0, Q tile 1
+  const uint32_t sKV = sQ + 2 * q_tile_bytes;                               // stage s: K then V
+  const uint32_t bar_base = sKV + NST * 2 * kv_tile_bytes;
+  const uint32_t q_full = bar_base;
+  auto s_full = [&](int g, int i) { return bar_base + 8u + 8u * (2 * g + i); };          // 4
+  auto p_full = [&](int g, int i) { return bar_base + 40u + 8u * (2 * g + i); };         // 4
+  auto o_done = [&](int g, int i) { return bar_base + 72u + 8u * (2 * g + i); };         // 4
+  auto kv_full = [&](int st) { return bar_base + 104u + 8u * st; };
+  auto kv_empty = [&](int st) { return bar_base + 104u + 8u * (NST_MAX + st); };
+  const uint32_t tmem_ptr_smem = bar_base + 104u + 8u * (2 * NST_MAX);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qt2 = blockIdx.x, head = blockIdx.y, b = blockIdx.z;            // qt2: pair of query tiles
+  const int n_tiles = p.n_kv_tiles;
+  constexpr int W_TMA = 8, W_MMA = 9;                                        // control warps above the softmax warps
+
+  if (warp == W_TMA && lane == 0) {
+    tma_prefetch_desc(&maps.q);
+    tma_prefetch_desc(&maps.k);
+    tma_prefetch_desc(&maps.v);
+    mbar_init(q_full, 1);
+    for (int g = 0; g < 2; ++g)
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(s_full(g, i), 1);
+        mbar_init(p_full(g, i), 128);
+        mbar_init(o_done(g, i), 1);
+      }
+    for (int st = 0; st < NST; ++st) {
+      mbar_init(kv_full(st), 1);
+      mbar_init(kv_empty(st), 1);
+    }
+    fence_mbar_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == W_MMA) tmem_alloc(tmem_ptr_smem, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+  auto tmem_S = [&](int g, int i) { return tmem_base + (uint32_t)((2 * g + i) * KV); };
+  auto tmem_Og = [&](int g) { return tmem_base + (uint32_t)(4 * KV) + (uint32_t)(g * p.dp); };
+
+  if (warp == W_TMA) {
+    // ---------------- TMA producer: both Q tiles once, K/V tiles through the ring (shared by both query tiles) ----------------
+    if (elect_one()) {
+      mbar_expect_tx(q_full, 2 * q_tile_bytes);
+      for (int g = 0; g < 2; ++g)
+        for (int c = 0; c < dchunks; ++c)
+          tma_load_3d(&maps.q, sQ + (uint32_t)g * q_tile_bytes + (uint32_t)c * ATT_BLOCK_Q * 32u, q_full,
+                      p.q_col0 + head * p.dp + c * 16, (2 * qt2 + g) * ATT_BLOCK_Q, b);
+    }
+    __syncwarp();
+    int st = 0;
+    uint32_t ph = 0;
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(kv_empty(st), ph ^ 1u);
+      if (elect_one()) {
+        const uint32_t sK = sKV + (uint32_t)st * 2 * kv_tile_bytes;
+        const uint32_t sV = sK + kv_tile_bytes;
+        mbar_expect_tx(kv_full(st), 2 * kv_tile_bytes);
+        for (int c = 0; c < dchunks; ++c)
+          tma_load_3d(&maps.k, sK + (uint32_t)c * kv_chunk_bytes, kv_full(st), p.k_col0 + head * p.dp + c * 16, j * KV, b);
+        for (int c = 0; c < dchunks; ++c)
+          tma_load_3d(&maps.v, sV + (uint32_t)c * kv_chunk_bytes, kv_full(st), p.v_col0 + head * p.dp + c * 16, j * KV, b);
+      }
+      __syncwarp();
+      if (++st == NST) { st = 0; ph ^= 1u; }
+    }
+  } else if (warp == W_MMA) {
+    // ---------------- MMA issuer: QK for both query tiles per K/V stage, PV as each group's P arrives ----------------
+    const uint32_t idesc_qk = make_idesc_f16(ATT_BLOCK_Q, (uint32_t)KV, true, 0, 0);
+    const uint32_t idesc_pv = make_idesc_f16(ATT_BLOCK_Q, (uint32_t)p.dp, true, 0, 1);
+    const uint64_t desc_q0 = make_smem_desc(sQ, 16, 256, SWZ_32B);
+    const uint64_t desc_k0 = make_smem_desc(sKV, 16, 256, SWZ_32B);
+    const uint64_t desc_v0 = make_smem_desc(sKV + kv_tile_bytes, KV * 32u, 256, SWZ_32B);
+    const uint32_t stage_step = (2 * kv_tile_bytes) >> 4;
+    const uint32_t q_step = q_tile_bytes >> 4;
+    auto issue_qk = [&](int g, int jj) {          // S[g][jj & 1] = Q_g K_jj^T   (K/V stage jj % NST must be full)
+      if (elect_one()) {
+        const uint64_t dk = desc_k0 + (uint64_t)((uint32_t)(jj % NST) * stage_step);
+        const uint64_t dq = desc_q0 + (uint64_t)((uint32_t)g * q_step);
+        for (int c = 0; c < dchunks; ++c)
+          umma_f16_ss(tmem_S(g, jj & 1), dq + (uint64_t)(c * (ATT_BLOCK_Q * 32 / 16)), dk + (uint64_t)(c * (int)(kv_chunk_bytes >> 4)),
+                      idesc_qk, c != 0);
+        umma_commit(s_full(g, jj & 1));
+      }
+      __syncwarp();
+    };
+    auto wait_kv = [&](int jj) {
+      mbar_wait(kv_full(jj % NST), (uint32_t)(jj / NST) & 1u);
+      tc_fence_after();
+    };
+    mbar_wait(q_full, 0);
+    wait_kv(0);
+    issue_qk(0, 0);
+    issue_qk(1, 0);
+    if (n_tiles > 1) {
+      wait_kv(1);
+      issue_qk(0, 1);
+      issue_qk(1, 1);
+    }
+    for (int j = 0; j < n_tiles; ++j) {
+      const int bi = j & 1;
+      const int st = j % NST;
+      if (j + 2 < n_tiles) wait_kv(j + 2);
+      for (int g = 0; g < 2; ++g) {
+        mbar_wait(p_full(g, bi), (uint32_t)(j >> 1) & 1u);      // P_g[bi] written, S_g[bi] consumed
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t dv = desc_v0 + (uint64_t)((uint32_t)st * stage_step);
+#pragma unroll
+          for (int k = 0; k < KV / 16; ++k)
+            umma_f16_ts(tmem_Og(g), tmem_S(g, bi) + (uint32_t)(8 * k), dv + (uint64_t)(k * (512 / 16)), idesc_pv, (j | k) != 0);
+          umma_commit(o_done(g, bi));
+          if (g == 1) umma_commit(kv_empty(st));                 // both groups' MMAs on this K/V stage are issued
+        }
+        __syncwarp();
+        if (j + 2 < n_tiles) issue_qk(g, j + 2);                 // overwrites S_g[bi] after PV_g(j) (in-order tensor pipe)
+      }
+    }
+  } else {
+    // ---------------- softmax warpgroups A (warps 0..3, query tile 0) and B (warps 4..7, query tile 1) ----------------
+    const int g = warp >> 2;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const int q_row = (2 * qt2 + g) * ATT_BLOCK_Q + row;
+    float m_ref = -INFINITY, l = 0.f;
+    // named barriers 1 + g: "group g may use the MUFU".  B hands the first turn to A.
+    const int my_turn = 1 + g, other_turn = 2 - g;
+    if (g == 1) named_bar_arrive(other_turn, 256);
+    for (int j = 0; j < n_tiles; ++j) {
+      const int bi = j & 1;
+      const uint32_t tS = tmem_S(g, bi) + lane_addr;
+      mbar_wait(s_full(g, bi), (uint32_t)(j >> 1) & 1u);
+      tc_fence_after();
+      named_bar_sync(my_turn, 256);                               // ---- my exponential turn starts ----
+      const int kv_valid = min(KV, p.Skv - j * KV);
+      uint32_t sreg[KV];
+      uint32_t pw[KV / 2];
+      bool careful = (kv_valid != KV) || (j == 0);
+      float mx = -INFINITY;
+      if (!careful) {
+        float m8[8], l8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { m8[i] = -INFINITY; l8[i] = 0.f; }
+        tmem_ld_32x32b_x32(tS, *reinterpret_cast<uint32_t(*)[32]>(&sreg[0]));
+#pragma unroll
+        for (int c = 0; c < KV / 32; ++c) {
+          tmem_ld_wait();
+          if (c + 1 < KV / 32)
+            tmem_ld_32x32b_x32(tS + (uint32_t)((c + 1) * 32), *reinterpret_cast<uint32_t(*)[32]>(&sreg[(c + 1) * 32]));
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float pv[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float sv = __uint_as_float(sreg[c * 32 + h * 16 + i]);
+              m8[i & 7] = fmaxf(m8[i & 7], sv);
+              pv[i] = ex2f(fmaf(sv, p.scale_log2, -m_ref));
+              l8[i & 7] += pv[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pw[(c * 2 + h) * 8 + i] = pack_bf16x2(pv[2 * i], pv[2 * i + 1]);
+          }
+        }
+        const float tsum = ((l8[0] + l8[1]) + (l8[2] + l8[3])) + ((l8[4] + l8[5]) + (l8[6] + l8[7]));
+        mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7]))) * p.scale_log2;
+        careful = __any_sync(0xffffffffu, mx > m_ref + 8.0f);
+        if (!careful) l += tsum;
+      } else {
+#pragma unroll
+        for (int c = 0; c < KV / 32; ++c)
+          tmem_ld_32x32b_x32(tS + (uint32_t)(c * 32), *reinterpret_cast<uint32_t(*)[32]>(&sreg[c * 32]));
+        tmem_ld_wait();
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int i = 0; i < KV; ++i)
+          if (i < kv_valid) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(sreg[i]));
+        mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * p.scale_log2;
+      }
+      if (careful) {
+        const bool need = mx > m_ref + 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          const float m_new = need ? mx : m_ref;
+          const float alpha = ex2f(m_ref - m_new);
+          if (j > 0) {
+            mbar_wait(o_done(g, (j - 1) & 1), (uint32_t)((j - 1) >> 1) & 1u);
+            tc_fence_after();
+            for (int c = 0; c < dchunks; ++c) {
+              uint32_t r[16];
+              tmem_ld_32x32b_x16(tmem_Og(g) + lane_addr + (uint32_t)(c * 16), r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+              tmem_st_32x32b_x16(tmem_Og(g) + lane_addr + (uint32_t)(c * 16), r);
+            }
+            tmem_st_wait();
+          }
+          l *= alpha;
+          m_ref = m_new;
+        }
+        float l4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < KV / 16; ++c) {
+          float pv[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float e = ex2f(fmaf(__uint_as_float(sreg[c * 16 + i]), p.scale_log2, -m_ref));
+            pv[i] = (c * 16 + i < kv_valid) ? e : 0.f;
+            l4[i & 3] += pv[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pw[c * 8 + i] = pack_bf16x2(pv[2 * i], pv[2 * i + 1]);
+        }
+        l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+      }
+      // ---- my turn ends: the other group computes while I store P and wait for my next S ----
+      if (!(g == 1 && j == n_tiles - 1)) named_bar_arrive(other_turn, 256);
+#pragma unroll
+      for (int c = 0; c < KV / 64; ++c)
+        tmem_st_32x32b_x32(tS + (uint32_t)(c * 32), *reinterpret_cast<uint32_t(*)[32]>(&pw[c * 32]));
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(p_full(g, bi));
+    }
+    // ---- epilogue: O / l -> bf16 ----
+    mbar_wait(o_done(g, (n_tiles - 1) & 1), (uint32_t)((n_tiles - 1) >> 1) & 1u);
+    tc_fence_after();
+    const float inv_l = 1.0f / l;
+    __nv_bfloat16* orow = p.out + (size_t)b * p.out_batch_stride + (size_t)q_row * p.out_ld + p.out_col0 + head * p.dp;
+    for (int c = 0; c < dchunks; ++c) {
+      uint32_t r[16];
+      tmem_ld_32x32b_x16(tmem_Og(g) + lane_addr + (uint32_t)(c * 16), r);
+      tmem_ld_wait();
+      if (q_row < p.Sq) {
+        uint4 a, bq;
+        a.x = pack_bf16x2(__uint_as_float(r[0]) * inv_l, __uint_as_float(r[1]) * inv_l);
+        a.y = pack_bf16x2(__uint_as_float(r[2]) * inv_l, __uint_as_float(r[3]) * inv_l);
+        a.z = pack_bf16x2(__uint_as_float(r[4]) * inv_l, __uint_as_float(r[5]) * inv_l);
+        a.w = pack_bf16x2(__uint_as_float(r[6]) * inv_l, __uint_as_float(r[7]) * inv_l);
+        bq.x = pack_bf16x2(__uint_as_float(r[8]) * inv_l, __uint_as_float(r[9]) * inv_l);
+        bq.y = pack_bf16x2(__uint_as_float(r[10]) * inv_l, __uint_as_float(r[11]) * inv_l);
+        bq.z = pack_bf16x2(__uint_as_float(r[12]) * inv_l, __uint_as_float(r[13]) * inv_l);
+        bq.w = pack_bf16x2(__uint_as_float(r[14]) * inv_l, __uint_as_float(r[15]) * inv_l);
+        *reinterpret_cast<uint4*>(orow + c * 16) = a;
+        *reinterpret_cast<uint4*>(orow + c * 16 + 8) = bq;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+
+// =================================================================================================
 // Split-KV variant of the double-buffered kernel (block_kv == 64, dp <= 64) — an EXPERIMENT, not the default (see
 // dfb_attention below).  ncu of attn_fwd_db_kernel showed neither the MUFU (63 %) nor the issue slots (57 %)
 // saturated, which suggested latency-bound exponential chains with two softmax warps per scheduler.
@@ -1259,7 +1555,12 @@ extern "C" int dfb_attention(const dfb_attn_params* a, void* stream_) {
   const bool use_split = use_db && bkv == 64 && a->dp <= 64 && (a->dbg_flags & 16) == 0 && (a->dbg_flags & 32) != 0;
   // short-KV kernel (one key tile, K/V resident, query tiles streamed): cross-attention.  dbg_flags bit6 disables it.
   const bool use_short = !causal && !use_db && a->Skv <= bkv && 2 * (bkv + a->dp) <= 512 && a->Sq > ATT_BLOCK_Q && (a->dbg_flags & (8 | 64)) == 0;
+  // ping-pong kernel (one CTA per SM, two query tiles, two softmax warpgroups alternating on the MUFU): opt-in experiment,
+  // dbg_flags bit12; see attn_fwd_pp_kernel.
+  const bool use_pp = use_db && !use_split && bkv == 64 && a->dp <= 64 && a->Sq > ATT_BLOCK_Q && (a->dbg_flags & 16) == 0 &&
+                      (a->dbg_flags & 4096) != 0;
   uint32_t need_cols = use_short ? (uint32_t)(2 * (bkv + a->dp))
+                       : use_pp  ? (uint32_t)(4 * bkv + 2 * a->dp)
                                  : (uint32_t)((use_db ? 2 : 1) * bkv + (use_split ? 2 : 1) * a->dp), cols = 32;
   while (cols < need_cols) cols <<= 1;
   DFB_REQUIRE(cols <= 512, "dfb_attention: block_kv + dp exceeds TMEM");
@@ -1307,6 +1608,10 @@ extern "C" int dfb_attention(const dfb_attn_params* a, void* stream_) {
     smem = 1024 + (size_t)dch * ATT_BLOCK_Q * 32 + (size_t)(bkv / 16) * ATT_BLOCK_Q * 32 + (size_t)ATT_STAGES * 2 * dch * bkv * 32 + 128;
   }
   const int n_qtiles = (a->Sq + ATT_BLOCK_Q - 1) / ATT_BLOCK_Q;
+  if (use_pp) {
+    kp.kv_stages = 4;       // >= 3 required: QK(j + 2) is issued before the stage of tile j is released
+    smem = 1024 + 2 * (size_t)dch * ATT_BLOCK_Q * 32 + (size_t)kp.kv_stages * 2 * dch * bkv * 32 + 256;
+  }
   if (use_short) {
     smem = 1024 + 2 * (size_t)dch * ATT_BLOCK_Q * 32 + (size_t)2 * dch * bkv * 32 + 256;
     // query tiles per CTA: amortise the per-CTA set-up, but keep >= ~4 CTAs per SM slot for load balance
@@ -1332,12 +1637,16 @@ extern "C" int dfb_attention(const dfb_attn_params* a, void* stream_) {
     DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_db_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_short_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     attr_set[dev] = true;
   }
   dim3 grid((a->Sq + ATT_BLOCK_Q - 1) / ATT_BLOCK_Q, a->heads, a->B);
   if (use_short) {
     dim3 gshort((n_qtiles + kp.q_tiles - 1) / kp.q_tiles, a->heads, a->B);
     attn_short_kv_kernel<<<gshort, ATT_THREADS, smem, stream>>>(maps, kp);
+  } else if (use_pp) {
+    dim3 gpp((n_qtiles + 1) / 2, a->heads, a->B);
+    attn_fwd_pp_kernel<<<gpp, ATT_PP_THREADS, smem, stream>>>(maps, kp);
   } else if (use_split)
     attn_fwd_split_kernel<<<grid, ATT_SPLIT_THREADS, smem, stream>>>(maps, kp);
   else if (use_db && bkv == 64 && p_tmem && (a->dbg_flags & 128))

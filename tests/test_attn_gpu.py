@@ -143,3 +143,28 @@ def test_attention_no_max_fast_path_variant():
     # the two variants round P (and the output) to bf16 against different reference maxima, so with these sharply peaked
     # rows they differ at the bf16-rounding level (measured 2.0e-3 on B200, the size of either one's error vs fp64)
     assert rel_l2(outs[1], outs[0]) < 4e-3
+
+
+@pytest.mark.skipif(__import__("os").environ.get("DFB_TEST_PP") != "1",
+                    reason="attn_fwd_pp_kernel (ping-pong softmax warpgroups, dbg bit12) was written after round 1's GPU budget "
+                           "was spent and has never run: opt in with DFB_TEST_PP=1 (a faulty kernel can poison the CUDA context)")
+@pytest.mark.parametrize("B,H,Sq,Skv,d", [(2, 8, 4096, 4096, 40), (1, 2, 512, 320, 64), (2, 3, 300, 1000, 48), (1, 1, 256, 128, 16)])
+def test_attention_ping_pong_variant(B, H, Sq, Skv, d):
+    """dbg bit12: one CTA per SM, two query tiles, two softmax warpgroups taking turns on the MUFU (named barriers), K/V
+    tiles shared — must agree with the shipped double-buffered kernel to bf16-rounding level and with fp64 to 1e-2."""
+    from difashion_b200 import ops
+    g = torch.Generator().manual_seed(Sq + Skv + d)
+    q = torch.randn(B, Sq, H * d, generator=g).bfloat16().cuda()
+    k = torch.randn(B, Skv, H * d, generator=g).bfloat16().cuda()
+    v = torch.randn(B, Skv, H * d, generator=g).bfloat16().cuda()
+    dp = ops.pad16(d)
+    qp, kp, vp = (_pad_heads(t, H, d, dp).contiguous() for t in (q, k, v))
+    outs = []
+    for flags in (0, 4096):
+        out = torch.full((B, Sq, H * dp), float("nan"), dtype=torch.bfloat16, device="cuda")
+        ops.attention(qp, kp, vp, out, heads=H, dp=dp, scale=d ** -0.5, block_kv=64, dbg_flags=flags)
+        torch.cuda.synchronize()
+        outs.append(out.reshape(B, Sq, H, dp)[..., :d].reshape(B, Sq, H * d))
+    ref = _ref(q, k, v, H, d, d ** -0.5)
+    assert rel_l2(outs[1], ref) < 1e-2 and rel_l2(outs[0], ref) < 1e-2
+    assert rel_l2(outs[1], outs[0]) < 4e-3
