@@ -10,3 +10,6 @@ timeout 300 python -m pytest tests/test_zz_batch_invariance_gpu.py tests/test_un
 timeout 120 python tools/batch_invariance_diag.py > $O/batch_invariance_$V.log 2>&1
 timeout 120 python tools/plms_chunk_diag.py > $O/plms_chunk_$V.log 2>&1
 bash tools/gpu_round_check.sh $V
+# last, because a faulty kernel traps and poisons its process: the ping-pong attention experiment (dbg bit12, never run)
+DFB_TEST_PP=1 timeout 200 python -m pytest tests/test_attn_gpu.py -q -k ping_pong > $O/pytest_pp_$V.log 2>&1; echo "rc=$?" >> $O/pytest_pp_$V.log
+timeout 200 python tools/attn_pp_experiment.py > $O/attn_pp_$V.log 2>&1; echo "rc=$?" >> $O/attn_pp_$V.log
