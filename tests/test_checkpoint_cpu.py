@@ -160,3 +160,23 @@ def test_scheduler_config_file(tmp_path):
             json.dump(dict(cfg, **bad), f)
         with pytest.raises(NotImplementedError):
             B200PNDMScheduler.from_pretrained(d)
+
+
+def test_history_latent_format(tmp_path):
+    """data_utils.py:114-147: all_item_latents.npy cache + hist_latents[uid][cate] = mean of the interacted items' latents,
+    hist_latents["null"] = the white image's latent; what fashion_generation's `history` argument holds."""
+    import numpy as np
+    from difashion_b200 import B200AutoencoderKL, build_history_latents, encode_all_item_latents
+    g = torch.Generator().manual_seed(0)
+    all_latents = torch.randn(6, 4, 8, 8, generator=g)
+    np.save(str(tmp_path / "all_item_latents.npy"), np.array(all_latents))           # the reference's own cache file
+    vae = B200AutoencoderKL(**TINY_VAE)                                               # on the host: the cache must make it unnecessary
+    got = encode_all_item_latents(vae, img_dataset=None, data_path=str(tmp_path))
+    assert torch.equal(got, all_latents)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        encode_all_item_latents(vae, img_dataset=[torch.zeros(3, 64, 64)], data_path=None)
+    history = {7: {3: [1, 2, 5], 9: [4]}, 8: {3: [0]}}
+    hist = build_history_latents(history, all_latents)
+    assert set(hist) == {7, 8, "null"} and torch.equal(hist["null"], all_latents[0])
+    assert torch.allclose(hist[7][3], (all_latents[1] + all_latents[2] + all_latents[5]) / 3) and torch.equal(hist[7][9], all_latents[4])
+    assert hist[8][3].shape == (4, 8, 8)
