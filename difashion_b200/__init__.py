@@ -17,8 +17,9 @@ from .generation import B200DiFashion  # noqa: F401
 from .outputs import merge_and_save_images, save_batch_outputs, save_outputs_npy  # noqa: F401
 from . import checkpoint  # noqa: F401  (the reference's on-disk model / checkpoint layout)
 from .history import build_history_latents, encode_all_item_latents  # noqa: F401
+from .prompts import category_prompt, tokenize_categories  # noqa: F401
 
 __all__ = ["B200UNet2DConditionModel", "UNet2DConditionOutput", "B200AttnProcessor", "Attention", "B200DDIMScheduler",
            "B200PNDMScheduler", "MutualEncoder", "B200DiFashionPipeline", "guidance_plan", "mutual_index_table",
            "shard_outfits", "B200AutoencoderKL", "DecoderOutput", "B200CLIPTextModel", "B200DiFashion",
-           "save_batch_outputs", "merge_and_save_images", "save_outputs_npy", "build_history_latents", "encode_all_item_latents"]
+           "save_batch_outputs", "merge_and_save_images", "save_outputs_npy", "build_history_latents", "encode_all_item_latents", "category_prompt", "tokenize_categories"]

@@ -180,3 +180,29 @@ def test_history_latent_format(tmp_path):
     assert set(hist) == {7, 8, "null"} and torch.equal(hist["null"], all_latents[0])
     assert torch.allclose(hist[7][3], (all_latents[1] + all_latents[2] + all_latents[5]) / 3) and torch.equal(hist[7][9], all_latents[4])
     assert hist[8][3].shape == (4, 8, 8)
+
+
+def test_category_prompts_and_tokenisation():
+    """data_utils.py:88-111: prompt template ("a pair of" for pants / earrings) and the [outfits, olen, 77] id tensor."""
+    from types import SimpleNamespace
+    from difashion_b200 import category_prompt, tokenize_categories
+    assert category_prompt("dress") == "A photo of a dress, on white background, high quality"
+    assert category_prompt("skinny pants") == "A photo of a pair of skinny pants, on white background, high quality"
+    assert category_prompt("hoop earrings").startswith("A photo of a pair of hoop earrings")
+
+    class Tok:                                   # stands in for CLIPTokenizer: one id per character, padded to model_max_length
+        model_max_length = 77
+
+        def __call__(self, prompts, max_length, padding, truncation, return_tensors):
+            assert padding == "max_length" and truncation and return_tensors == "pt" and max_length == 77
+            ids = torch.zeros(len(prompts), max_length, dtype=torch.long)
+            for i, p in enumerate(prompts):
+                t = torch.tensor([ord(c) for c in p][:max_length])
+                ids[i, :len(t)] = t
+            return SimpleNamespace(input_ids=ids)
+    ids = tokenize_categories(Tok(), [[1, 2, 3, 4], [4, 4, 1, 2]], {1: "dress", 2: "pants", 3: "bag", 4: "earrings"})
+    assert ids.shape == (2, 4, 77) and ids.dtype == torch.long
+    assert torch.equal(ids[0, 0], ids[1, 2]) and torch.equal(ids[0, 3], ids[1, 0]) and not torch.equal(ids[0, 0], ids[0, 1])
+    assert "".join(chr(int(c)) for c in ids[0, 1] if c) == category_prompt("pants")[:77]
+    tr = pytest.importorskip("transformers")     # the real tokenizer class accepts the same call (no vocabulary files offline)
+    assert hasattr(tr, "CLIPTokenizer")
