@@ -1,7 +1,16 @@
 #!/usr/bin/env python
 """Benchmark of the DiFashion conditional denoising step on B200 (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--outfits O]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C2|C3|C4|C5] [--outfits O]
+                  [--ddim-steps S]
+
+configs (BASELINE.json `configs`; the driver's default is C2 = configs[1], the one the metric is quoted on):
+  C2  GOR, 16 outfits x 4 items per GPU (256 UNet rows / step), S_kv 77, weak scaling.
+  C3  PFITB: 64 fill-in-the-blank outfits per GPU (1 blank + 3 given items: mutual condition over the given items, history
+      condition), 64 items x 4 branches = 256 rows / step; `value` counts FITB outfits (1 generated item each).
+  C4  history-conditioned GOR, S_kv 85 (77 prompt + 8 history CLIP tokens), ONE job of 128 outfits sharded over the N GPUs
+      (strong scaling; the e2e leg includes the NCCL gather of the finished latents).
+  C5  sweep point: ONE job of --outfits O outfits (1..512) x --ddim-steps S (20 | 50), sharded over the N GPUs (strong).
 
 metric : outfits/sec for GOR generation = 4 items x 512 px (4x64x64 latents) x 50-step DDIM x 4-branch CFG.
 step   : one denoising step (mutual gather + MutualEncoder MLP + blend + SD-1.5-shaped UNet over
@@ -13,9 +22,13 @@ e2e    : the same metric through B200DiFashionPipeline.generate() with PINNED HO
          finished latents,) D2H — one full generation per rank.
 roofline: tensor-bound.  `achieved` = algorithmic FLOPs of the tcgen05 GEMM/conv kernel launches of one step
          (rows x 677.31 GFLOP: F_row 803.37 minus the attention core 126.06) / their summed
-         CUDA-event durations, vs the measured sustained bf16 peak of MEASURED_PEAKS.json.
+         CUDA-event durations, vs the measured sustained bf16 peak of MEASURED_PEAKS.json; `achieved_executed` counts the
+         FLOPs those launches really execute (the upsample phases and the shared CFG prefix skip work the algorithmic
+         figure still contains).  `attention` = the same for the flash-attention launches against the burst peak.
 cpu_baseline / --impl reference: the CPU oracle (PyTorch fp32 restatement of the reference path; the
-         reference itself needs diffusers, absent here) timed on the box's host cores on a bounded sample.
+         reference itself needs diffusers, absent here) timed on the box's host cores on a bounded sample: one FITB
+         outfit-step with the real guidance scales (4 UNet rows per step) when K + W <= 31, one full GOR outfit-step
+         (16 rows) when K + W <= 7, else 1 row per step.
 """
 from __future__ import annotations
 
@@ -95,14 +108,20 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
-def synthetic_inputs(n_outfits: int, s_kv: int = 77, seed: int = 123, pin: bool = True):
-    """GOR inputs per SURVEY §8d: every slot is generated; CPU-generated from fixed seeds."""
+def synthetic_inputs(n_outfits: int, s_kv: int = 77, seed: int = 123, pin: bool = True, task: str = "GOR"):
+    """GOR inputs per SURVEY §8d: every slot is generated.  FITB (configs[2]): one blank per outfit at a seeded position, the
+    other three slots are given items whose VAE latents feed the mutual condition.  CPU-generated from fixed seeds."""
     g = torch.Generator().manual_seed(seed)
-    n = n_outfits * 4
     mk = lambda *shape, scale=1.0: (torch.randn(*shape, generator=g) * scale)
+    if task == "FITB":
+        olists = torch.randint(1, 1000, (n_outfits, 4), generator=g)
+        olists[torch.arange(n_outfits), torch.randint(0, 4, (n_outfits,), generator=g)] = 0
+        n, given = n_outfits, mk(n_outfits * 4, 4, 64, 64, scale=0.9)
+    else:
+        olists, n, given = torch.zeros(n_outfits, 4, dtype=torch.long), n_outfits * 4, None
     d = dict(
-        olists=torch.zeros(n_outfits, 4, dtype=torch.long),
-        all_latents=None,
+        olists=olists,
+        all_latents=given,
         init_latents=mk(n, 4, 64, 64),
         category_prompts=mk(n, s_kv, 768),
         null_prompt=mk(1, s_kv, 768),
@@ -129,12 +148,36 @@ def cpu_oracle_sample(rows: int, threads: int):
     return dt
 
 
+CONFIGS = {   # BASELINE.json `configs`[1..4]
+    "C2": dict(task="GOR", outfits=16, skv=77, scaling="weak"),
+    "C3": dict(task="FITB", outfits=64, skv=77, scaling="weak"),
+    "C4": dict(task="GOR", outfits=128, skv=85, scaling="strong"),
+    "C5": dict(task="GOR", outfits=None, skv=77, scaling="strong"),
+}
+
+
+def resolve_config(args):
+    c = CONFIGS[args.config]
+    args.task, args.scaling = c["task"], c["scaling"]
+    if args.outfits is None:
+        args.outfits = c["outfits"] if c["outfits"] is not None else 16
+    if args.skv is None:
+        args.skv = c["skv"]
+    args.rows_per_outfit = ROWS_PER_OUTFIT if args.task == "GOR" else 4          # items per outfit x 4 CFG branches
+    return args
+
+
 def workload_config(args, world):
-    rows = args.outfits * ROWS_PER_OUTFIT
-    return {"workload": f"GOR generation: 50-step DDIM + 4-branch CFG, {args.outfits} outfits x 4 items per GPU "
-                        f"({rows} UNet rows/step), SD-1.5-shaped UNet (in_channels 8, S_kv {args.skv}), random-init weights",
-            "outfits_per_gpu": args.outfits, "unet_rows_per_step": rows, "ddim_steps": DDIM_STEPS,
-            "parallelism": f"outfit-sharded replicas x{world}, no in-loop collective"}
+    per = "per GPU" if args.scaling == "weak" else f"in ONE job sharded over {world} GPU(s)"
+    rows = args.outfits * args.rows_per_outfit
+    what = ("GOR generation" if args.task == "GOR" else
+            "PFITB generation (1 blank + 3 given items per outfit: mutual condition over the given items + history condition)")
+    items = "4 items" if args.task == "GOR" else "1 generated item"
+    return {"workload": f"{args.config}: {what}: {args.ddim_steps}-step DDIM + 4-branch CFG, {args.outfits} outfits x {items} {per} "
+                        f"({rows} UNet rows/step{'' if args.scaling == 'weak' else ' in total'}), SD-1.5-shaped UNet (in_channels 8, "
+                        f"S_kv {args.skv}), random-init weights",
+            ("outfits_per_gpu" if args.scaling == "weak" else "outfits_total"): args.outfits, "unet_rows_per_step": rows,
+            "ddim_steps": args.ddim_steps, "parallelism": f"outfit-sharded replicas x{world}, no in-loop collective"}
 
 
 def run_reference(args, rank, world, guard):
@@ -149,19 +192,24 @@ def run_reference(args, rank, world, guard):
     unet = make_oracle_unet(seed=0)
     me = make_oracle_mutual_encoder(seed=1)
     total_steps = args.steps + args.warmup
-    # bounded sample: one FITB outfit with one blank (4 CFG rows per step) when few steps are asked,
-    # else a single-branch row (guidance scales 1.0 -> 1 UNet row per step)
-    few = total_steps <= 8
+    # Bounded sample of the workload, sized to end within a few minutes at ~1.2 s per fp32 UNet row on 16 host cores: one full
+    # GOR outfit-step (4 items x 4 branches = 16 rows) when K + W <= 7; one FITB outfit-step with the real guidance scales
+    # (1 blank x 4 branches = 4 rows: all of the step's arithmetic, a quarter of an outfit's rows) when K + W <= 31; else a single
+    # row per step (guidance scales 1.0).
     g = torch.Generator().manual_seed(123)
-    olists = torch.tensor([[11, 0, 7, 9]])
+    real_scales = dict(category_guidance_scale=12.0, hist_guidance_scale=4.0, mutual_guidance_scale=5.0)
+    if total_steps <= 7 and args.task == "GOR":
+        rows_per_step, n_items, olists, scales, what = 16, 4, torch.zeros(1, 4, dtype=torch.long), real_scales, "one GOR outfit (4 items x 4 CFG branches)"
+    elif total_steps <= 31:
+        rows_per_step, n_items, olists, scales, what = 4, 1, torch.tensor([[11, 0, 7, 9]]), real_scales, "one FITB outfit (1 blank x 4 CFG branches, guidance 12 / 5 / 4)"
+    else:
+        rows_per_step, n_items, olists, what = 1, 1, torch.tensor([[11, 0, 7, 9]]), "one item, guidance scales 1.0 (single branch)"
+        scales = dict(category_guidance_scale=1.0, hist_guidance_scale=1.0, mutual_guidance_scale=1.0)
+    skv = args.skv
     inp = dict(olists=olists, all_latents=0.9 * torch.randn(4, 4, 64, 64, generator=g),
-               category_prompts=torch.randn(1, 77, 768, generator=g), null_prompt=torch.randn(1, 77, 768, generator=g),
-               hist_latents=0.9 * torch.randn(1, 4, 64, 64, generator=g), null_latent=0.9 * torch.randn(4, 64, 64, generator=g),
-               init_latents=torch.randn(1, 4, 64, 64, generator=g))
-    scales = dict(category_guidance_scale=12.0, hist_guidance_scale=4.0, mutual_guidance_scale=5.0) if few else \
-        dict(category_guidance_scale=1.0, hist_guidance_scale=1.0, mutual_guidance_scale=1.0)
-    rows_per_step = 4 if few else 1
-    rec = []
+               category_prompts=torch.randn(n_items, skv, 768, generator=g), null_prompt=torch.randn(1, skv, 768, generator=g),
+               hist_latents=0.9 * torch.randn(n_items, 4, 64, 64, generator=g), null_latent=0.9 * torch.randn(4, 64, 64, generator=g),
+               init_latents=torch.randn(n_items, 4, 64, 64, generator=g))
     sched = OracleDDIMScheduler()
     t_marks = []
 
@@ -172,21 +220,23 @@ def run_reference(args, rank, world, guard):
             return out
 
     t_start = time.perf_counter()
-    oracle_generation(_Timed(), me, sched, **inp, num_inference_steps=max(DDIM_STEPS, total_steps), max_steps=total_steps, **scales)
+    oracle_generation(_Timed(), me, sched, **inp, num_inference_steps=max(args.ddim_steps, total_steps), max_steps=total_steps, **scales)
     marks = [t_start] + t_marks
     dt = marks[-1] - marks[args.warmup]
     ms_per_step = dt / args.steps * 1e3
-    # a GOR outfit costs 16 rows x 50 steps
-    value = (rows_per_step / ROWS_PER_OUTFIT) * args.steps / DDIM_STEPS / dt
+    # an outfit of this config costs rows_per_outfit rows x ddim_steps steps
+    value = (rows_per_step / args.rows_per_outfit) * args.steps / args.ddim_steps / dt
     line = {
         "impl": "reference", "metric": "outfits/sec (4x512px, 50-step DDIM+CFG)", "value": value, "unit": "outfits/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(workload_config(args, world), reference_note="CPU arm runs a bounded per-row sample of this workload"),
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, world),
+        "reference_note": f"CPU arm: {rows_per_step} UNet row(s) per step — {what} — of the {args.outfits * args.rows_per_outfit} rows "
+                          f"the GPU arm's step has; outfits/s = rows / {args.rows_per_outfit} per step over {args.ddim_steps} steps",
         "cpu_baseline": {"value": value, "unit": "outfits/s", "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} denoising steps x {rows_per_step} UNet row(s) of one FITB outfit "
+                         "sample": f"{args.steps} denoising steps x {rows_per_step} UNet row(s) per step: {what} "
                                    f"(oracle fp32 port of the diffusers path; the reference itself needs diffusers, "
-                                   f"not installable here); outfits/s = rows/16 per step over 50 steps"},
+                                   f"not installable here); outfits/s = rows/{args.rows_per_outfit} per step over {args.ddim_steps} steps"},
         "e2e": {"value": value, "unit": "outfits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -215,8 +265,11 @@ def main():
     ap.add_argument("--steps", type=int, default=DDIM_STEPS)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--outfits", type=int, default=16, help="outfits per GPU (16 -> 256 UNet rows: BASELINE configs[1])")
-    ap.add_argument("--skv", type=int, default=77, help="text tokens (85 = 77 + 8 history tokens, configs[3])")
+    ap.add_argument("--config", default="C2", choices=sorted(CONFIGS), help="BASELINE.json configs[1..4] (default C2 = configs[1])")
+    ap.add_argument("--outfits", type=int, default=None, help="outfits per GPU (weak-scaling configs C2 / C3) or in the whole job "
+                                                              "(strong-scaling configs C4 / C5); default: the config's")
+    ap.add_argument("--skv", type=int, default=None, help="text tokens (85 = 77 + 8 history tokens, configs[3]); default: the config's")
+    ap.add_argument("--ddim-steps", type=int, default=DDIM_STEPS, help="DDIM steps of one generation (C5 sweeps 20 | 50)")
     ap.add_argument("--max-rows", type=int, default=256, help="UNet rows per micro-batch")
     ap.add_argument("--streams", type=int, default=1, help="CUDA streams the row chunks of a step are spread over (needs max-rows < rows)")
     ap.add_argument("--no-share-prefix", action="store_true",
@@ -227,6 +280,9 @@ def main():
     ap.add_argument("--profile-step", action="store_true", help="print per-kernel-kind time of one eager step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    resolve_config(args)
+    if args.steps == DDIM_STEPS and args.ddim_steps != DDIM_STEPS:
+        args.steps = args.ddim_steps
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -257,17 +313,26 @@ def main():
     share = False if args.no_share_prefix else None            # None: the pipeline's default (on; DFB_SHARE_PREFIX=0 disables)
     pipe = B200DiFashionPipeline(unet, me, B200DDIMScheduler(), eta_mutual=0.1, max_rows=args.max_rows, streams=args.streams,
                                  share_cfg_prefix=share)
-    # weak scaling: every rank owns `outfits` whole outfits (distinct seeds = distinct outfits)
-    inp = synthetic_inputs(args.outfits, args.skv, seed=123 + rank)
-    rows = args.outfits * ROWS_PER_OUTFIT
+    # ONE job of `total` outfits, identical on every rank (same seed), dealt out in whole outfits by the product's own sharding
+    # (B200DiFashionPipeline.generate_sharded / shard_generation_inputs): weak scaling = `outfits` per GPU, strong = `outfits` in all
+    from difashion_b200.pipeline import shard_generation_inputs
+    total = args.outfits * world if args.scaling == "weak" else args.outfits
+    glob = synthetic_inputs(total, args.skv, seed=123, task=args.task)
+    inp, (i0, i1), item_counts = shard_generation_inputs(glob, rank, world)
+    my_outfits = inp["olists"].shape[0]
+    rows = my_outfits * args.rows_per_outfit               # UNet rows of this rank's step
+    rows_job = total * args.rows_per_outfit
+    f_row = F_ROW if args.skv == 77 else 804.04e9
 
     # ---------------- device-resident throughput (value) ----------------
-    st = pipe.begin(**inp, num_inference_steps=DDIM_STEPS, device=dev)
-    ts = st.timesteps
-    for w in range(args.warmup):
-        pipe.step(st, ts[w % len(ts)])
-    torch.cuda.synchronize()
-    launches_per_step = pipe.last_step_launches
+    st, ts, launches_per_step = None, list(range(args.ddim_steps)), 0
+    if my_outfits:
+        st = pipe.begin(**inp, num_inference_steps=args.ddim_steps, device=dev)
+        ts = st.timesteps
+        for w in range(args.warmup):
+            pipe.step(st, ts[w % len(ts)])
+        torch.cuda.synchronize()
+        launches_per_step = pipe.last_step_launches
     sampler = ClockSampler(local_rank)
     sampler.start()
     if world > 1:
@@ -275,7 +340,7 @@ def main():
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for k in range(args.steps):
+    for k in range(args.steps if my_outfits else 0):
         pipe.step(st, ts[(args.warmup + k) % len(ts)])
     e1.record()
     torch.cuda.synchronize()
@@ -288,42 +353,62 @@ def main():
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     t_ms = float(t_ms.item())
     ms_per_step = t_ms / args.steps
-    value = world * args.outfits * (args.steps / DDIM_STEPS) / (t_ms / 1e3)
-    step_tflops = rows * (F_ROW if args.skv == 77 else 804.04e9) / (ms_per_step / 1e3) / 1e12
+    value = total * (args.steps / args.ddim_steps) / (t_ms / 1e3)
+    step_tflops = (rows_job / world) * f_row / (ms_per_step / 1e3) / 1e12      # per GPU (the slowest rank sets ms_per_step)
 
     # ---------------- dominant-kernel roofline: per-launch CUDA events over one eager step ----------------
     peaks = _peaks()
     pipe_eager = B200DiFashionPipeline(unet, me, B200DDIMScheduler(), eta_mutual=0.1, max_rows=args.max_rows,
                                        use_cuda_graph=False, share_cfg_prefix=share)
-    st2 = pipe_eager.begin(**inp, num_inference_steps=DDIM_STEPS, device=dev)
-    pipe_eager.step(st2, ts[0])
-    torch.cuda.synchronize()
-    ops.PROFILE = []
-    es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    es0.record()
-    pipe_eager.step(st2, ts[1])
-    es1.record()
-    torch.cuda.synchronize()
-    prof, ops.PROFILE = ops.PROFILE, None
+    prof, eager_ms, alg_by_kind = [], 0.0, {}
+    if rank == 0 and my_outfits:
+        st2 = pipe_eager.begin(**inp, num_inference_steps=args.ddim_steps, device=dev)
+        pipe_eager.step(st2, ts[0])
+        torch.cuda.synchronize()
+        ops.PROFILE, ops.ALG_BYTES = [], {}
+        es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        es0.record()
+        pipe_eager.step(st2, ts[1])
+        es1.record()
+        torch.cuda.synchronize()
+        prof, ops.PROFILE = ops.PROFILE, None
+        alg_by_kind, ops.ALG_BYTES = ops.ALG_BYTES, None
+        eager_ms = es0.elapsed_time(es1)
+        del st2
     kinds = {}
     for kind, flops, shape, a, b in prof:
         d = kinds.setdefault(kind, [0.0, 0.0, 0])
         d[0] += a.elapsed_time(b)
         d[1] += flops
         d[2] += 1
-    eager_ms = es0.elapsed_time(es1)
     mma_ms = kinds.get("gemm", [0, 0, 0])[0] + kinds.get("conv", [0, 0, 0])[0]
     mma_launches = kinds.get("gemm", [0, 0, 0])[2] + kinds.get("conv", [0, 0, 0])[2]
-    gemm_alg_flops = rows * (F_ROW - F_ROW_ATTN_CORE)
+    mma_exec_flops = kinds.get("gemm", [0, 0, 0])[1] + kinds.get("conv", [0, 0, 0])[1]       # what the launches really multiply
+    f_attn = F_ROW_ATTN_CORE + (f_row - F_ROW)                                             # (S_kv 85 adds cross-attention work)
+    gemm_alg_flops = rows * (f_row - f_attn)
     achieved = gemm_alg_flops / (mma_ms / 1e3) / 1e12 if mma_ms > 0 else 0.0
+    achieved_exec = mma_exec_flops / (mma_ms / 1e3) / 1e12 if mma_ms > 0 else 0.0
+    att_ms, att_exec_flops, att_launches = kinds.get("attention", [0, 0, 0])
+    att_alg = rows * f_attn
     traffic, traffic_src = _ncu_traffic()
+    alg_bytes = ((alg_by_kind.get("gemm", 0.0) + alg_by_kind.get("conv", 0.0)) / mma_launches) if mma_launches else None
     roofline = {
         "bound": "tensor", "kernel": "gemm_tcgen05_kernel (all conv3x3 / 1x1 / linear launches of one step)",
         "achieved": achieved, "peak": peaks["sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["sustained"],
+        "achieved_executed": achieved_exec, "frac_executed": achieved_exec / peaks["sustained"],
+        "frac_of_burst": achieved / peaks["burst"], "frac_executed_of_burst": achieved_exec / peaks["burst"],
         "traffic": traffic, "traffic_unit": "bytes per launch (DRAM read+write, ncu)", "traffic_source": traffic_src,
+        "algorithmic_bytes_per_launch": alg_bytes,
+        "algorithmic_bytes_note": "operand + result tensors of each launch counted once (A activations, packed weights, bias / "
+                                  "row bias, fp32 residual in, output, GroupNorm partials), averaged over the step's launches",
         "algorithmic_flop_per_launch": gemm_alg_flops / mma_launches if mma_launches else None, "peak_source": f"{peaks['src']} (bf16_tflops_sustained; burst {peaks['burst']})",
         "launches_per_step": mma_launches, "kernel_ms_per_step": mma_ms, "kernel_share_of_step": mma_ms / eager_ms if eager_ms else None,
-        "attention_ms_per_step": kinds.get("attention", [0, 0, 0])[0],
+        "attention_ms_per_step": att_ms,
+        "attention": {"kernel": "attn_fwd_* (self-attention S=4096/1024/256/64 + short-KV cross-attention)", "launches_per_step": att_launches,
+                      "ms_per_step": att_ms, "achieved": att_alg / (att_ms / 1e3) / 1e12 if att_ms else None,
+                      "achieved_executed_padded_d": att_exec_flops / (att_ms / 1e3) / 1e12 if att_ms else None, "unit": "TFLOP/s",
+                      "frac_of_burst": att_alg / (att_ms / 1e3) / 1e12 / peaks["burst"] if att_ms else None,
+                      "bound": "MUFU (16 ex2/clk/SM) for S=4096, d=40: 1024 cycles per 128x128 score tile pair"},
         "step_achieved": step_tflops, "step_frac": step_tflops / peaks["sustained"], "step_frac_of_burst": step_tflops / peaks["burst"],
     }
     if args.profile_step and rank == 0:
@@ -339,24 +424,23 @@ def main():
             d[2] += 1
         for (kind, shape), (ms, fl, cnt) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:40]:
             print(f"#   {kind:9s} {str(shape):34s} x{cnt:<3d} {ms:8.3f} ms {fl / (ms / 1e3) / 1e12:8.1f} TFLOP/s", file=sys.stderr)
-    del pipe_eager, st2
+    del pipe_eager
 
     # ---------------- end-to-end through the public API with host buffers ----------------
     e2e = None
     if not args.no_e2e:
-        n_items = args.outfits * 4
+        n_items = sum(item_counts)
         out_host = torch.empty(n_items, 4, 64, 64, dtype=torch.float32).pin_memory()
-        gathered = torch.empty(world * n_items, 4, 64, 64, dtype=torch.float32, device=dev) if world > 1 else None
-        h2d = sum(v.numel() * v.element_size() for k, v in inp.items() if torch.is_tensor(v) and k != "olists")
+        h2d = sum(v.numel() * v.element_size() for k, v in inp.items() if torch.is_tensor(v) and k != "olists")   # this rank's shard
         d2h = out_host.numel() * 4
 
         def one_generation():
+            # the public call: N = 1 generate(); N > 1 generate_sharded() = shard by whole outfits, generate, ONE NCCL all-gather
+            # of the finished latents (padded when the shards are uneven), every rank gets the global tensor
             if world > 1:
-                lat = pipe.generate(**inp, num_inference_steps=DDIM_STEPS, device=dev)
-                dist.all_gather_into_tensor(gathered, lat)       # NCCL over NVLink: finished latents only
-                out_host.copy_(gathered[rank * n_items:(rank + 1) * n_items], non_blocking=True)
+                pipe.generate_sharded(**glob, num_inference_steps=args.ddim_steps, device=dev, out=out_host)
             else:
-                pipe.generate(**inp, num_inference_steps=DDIM_STEPS, device=dev, out=out_host)
+                pipe.generate(**inp, num_inference_steps=args.ddim_steps, device=dev, out=out_host)
             torch.cuda.synchronize()
 
         one_generation()                                          # warm (graphs already captured above)
@@ -369,9 +453,10 @@ def main():
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         dt = float(dt.item())
-        e2e = {"value": world * args.outfits / dt, "unit": "outfits/s", "h2d_bytes_per_step": h2d // DDIM_STEPS,
-               "d2h_bytes_per_step": d2h // DDIM_STEPS, "h2d_bytes_per_generation": h2d, "d2h_bytes_per_generation": d2h,
-               "seconds_per_generation": dt, "finite": bool(torch.isfinite(out_host).all())}
+        e2e = {"value": total / dt, "unit": "outfits/s", "h2d_bytes_per_step": h2d // args.ddim_steps,
+               "d2h_bytes_per_step": d2h // args.ddim_steps, "h2d_bytes_per_generation": h2d, "d2h_bytes_per_generation": d2h,
+               "seconds_per_generation": dt, "finite": bool(torch.isfinite(out_host).all()),
+               "api": "B200DiFashionPipeline.generate_sharded" if world > 1 else "B200DiFashionPipeline.generate"}
 
     if rank != 0:
         if world > 1:
@@ -384,16 +469,16 @@ def main():
         threads = os.cpu_count() or 1
         sample_rows = 2
         dt = cpu_oracle_sample(sample_rows, threads)
-        cpu = {"value": sample_rows / ROWS_PER_OUTFIT / DDIM_STEPS / dt, "unit": "outfits/s", "cores": threads, "kind": "port",
-               "sample": f"one fp32 UNet forward over {sample_rows} of the 256 rows of one denoising step ({dt:.2f} s); "
-                         f"outfits/s extrapolated as rows/16/50 (oracle = PyTorch restatement of the diffusers path)"}
+        cpu = {"value": sample_rows / args.rows_per_outfit / args.ddim_steps / dt, "unit": "outfits/s", "cores": threads, "kind": "port",
+               "sample": f"one fp32 UNet forward over {sample_rows} of the {rows} rows of one denoising step ({dt:.2f} s); "
+                         f"outfits/s extrapolated as rows/{args.rows_per_outfit}/{args.ddim_steps} (oracle = PyTorch restatement of the diffusers path)"}
 
     line = {
         "metric": "outfits/sec (4x512px, 50-step DDIM+CFG)", "value": value, "unit": "outfits/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": dict(workload_config(args, world),
-                       l2="inputs larger than L2: each step streams 1.7 GB of weights + multi-GB activations (126 MB L2)",
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": workload_config(args, world),
+        "notes": dict(l2="inputs larger than L2: each step streams 1.7 GB of weights + multi-GB activations (126 MB L2)",
                        unet_step_ms=ms_per_step,
                        cfg_shared_prefix=("on: CFG branches 2/3 get identical UNet inputs (null mutual, null history) and differ only in the "
                                           "prompt, so conv_in .. first self-attention run once for both (bit-identical; 1.3 % of the "

@@ -8,7 +8,8 @@ C ABI in ``include/dfb200.h``); importing this package never imports the test or
 """
 from .attention import Attention, B200AttnProcessor  # noqa: F401
 from .mutual import MutualEncoder  # noqa: F401
-from .pipeline import B200DiFashionPipeline, guidance_plan, mutual_index_table, shard_outfits  # noqa: F401
+from .pipeline import (B200DiFashionPipeline, gather_item_rows, guidance_plan, mutual_index_table,  # noqa: F401
+                       shard_generation_inputs, shard_outfits)
 from .schedulers import B200DDIMScheduler, B200PNDMScheduler  # noqa: F401
 from .unet import B200UNet2DConditionModel, UNet2DConditionOutput  # noqa: F401
 from .vae import B200AutoencoderKL, DecoderOutput  # noqa: F401
@@ -21,5 +22,5 @@ from .prompts import category_prompt, tokenize_categories  # noqa: F401
 
 __all__ = ["B200UNet2DConditionModel", "UNet2DConditionOutput", "B200AttnProcessor", "Attention", "B200DDIMScheduler",
            "B200PNDMScheduler", "MutualEncoder", "B200DiFashionPipeline", "guidance_plan", "mutual_index_table",
-           "shard_outfits", "B200AutoencoderKL", "DecoderOutput", "B200CLIPTextModel", "B200DiFashion",
+           "shard_outfits", "shard_generation_inputs", "gather_item_rows", "B200AutoencoderKL", "DecoderOutput", "B200CLIPTextModel", "B200DiFashion",
            "save_batch_outputs", "merge_and_save_images", "save_outputs_npy", "build_history_latents", "encode_all_item_latents", "category_prompt", "tokenize_categories"]

@@ -234,15 +234,20 @@ class B200CLIPTextModel(nn.Module):
             return (out,)
         return CLIPTextOutput(last_hidden_state=out)
 
-    def null_input_ids(self, max_length: Optional[int] = None) -> torch.Tensor:
-        """``tokenizer([""], padding="max_length", max_length=...)`` of the SD-1.5 CLIPTokenizer
-        (difashion.py:343-350): BOS followed by EOS (= pad token)."""
+    def null_input_ids(self, max_length: Optional[int] = None, pad_token_id: Optional[int] = None) -> torch.Tensor:
+        """``tokenizer([""], padding="max_length", max_length=...)`` of the CLIPTokenizer (difashion.py:343-350): BOS, EOS, then
+        padding.  The ids are the CLIP vocabulary's last two entries (``<|startoftext|>`` = vocab_size - 2 = 49406,
+        ``<|endoftext|>`` = vocab_size - 1 = 49407), NOT ``config.bos_token_id / eos_token_id``: the ``text_encoder/config.json``
+        Stable Diffusion ships carries transformers' generic defaults (bos 0, eos 2, pad 1), which are not CLIP tokens.
+        ``pad_token_id``: SD-1.5's tokenizer pads with EOS (the default here); SD-2's pads with id 0 — pass it, or give
+        ``B200DiFashion`` the tokenizer directory, which is what the reference does."""
         cfg = self.config
         n = max_length or cfg.max_position_embeddings
-        ids = torch.full((1, n), cfg.eos_token_id if cfg.pad_token_id is None else cfg.pad_token_id, dtype=torch.long)
-        ids[0, 0] = cfg.bos_token_id
+        bos, eos = cfg.vocab_size - 2, cfg.vocab_size - 1
+        ids = torch.full((1, n), eos if pad_token_id is None else int(pad_token_id), dtype=torch.long)
+        ids[0, 0] = bos
         if n > 1:
-            ids[0, 1] = cfg.eos_token_id
+            ids[0, 1] = eos
         return ids
 
     @torch.no_grad()

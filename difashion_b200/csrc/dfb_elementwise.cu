@@ -159,11 +159,26 @@ __global__ void __launch_bounds__(256) mutual_blend_kernel(const BlendParams p) 
       m[c] = p.m ? __ldg(p.m + o) : z[c];
       h[c] = p.hist ? __ldg(p.hist + o) : z[c];
     }
+    // Both candidates of the blended latent are computed ONCE per pixel, with explicitly rounded operations, and the
+    // branch loop only selects: branches with equal flags then hold equal bits by construction.  (Written inside the loop
+    // as `(1 - eta) * x + eta * m`, nvcc unrolled the loop by two and contracted the expression into an FMA differently
+    // in the unrolled body and in the remainder iteration — FFMA(m, eta, x * (1 - eta)) against FFMA(x, 1 - eta, m * eta) —
+    // so with an ODD branch count the last branch differed from an identical earlier one in the last fp32 bit, which now
+    // and then flips a bf16 rounding: the shared-CFG-prefix mismatch of round 1's driver run.)  The reference computes
+    // two products and a sum (difashion.py:513), which is what the intrinsics spell out.
+    const float w_x = 1.f - p.eta;
+    float vm[4], vz[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float xs = __fmul_rn(w_x, x[c]);
+      vm[c] = __fadd_rn(xs, __fmul_rn(p.eta, m[c]));
+      vz[c] = __fadd_rn(xs, __fmul_rn(p.eta, z[c]));
+    }
     for (int b = 0; b < p.nb; ++b) {
       float v[8];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        v[c] = (1.f - p.eta) * x[c] + p.eta * (p.use_m[b] ? m[c] : z[c]);
+        v[c] = p.use_m[b] ? vm[c] : vz[c];
         v[4 + c] = p.use_h[b] ? h[c] : z[c];
       }
       const size_t o = (((size_t)b * p.n_items + n) * p.hw + px) * 8;

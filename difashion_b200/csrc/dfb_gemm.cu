@@ -527,7 +527,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
             const float* rb = p.rowbias + (size_t)(row0 / p.rows_per_batch) * p.rowbias_ld + col;
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-              if (e < nval) b4[e] += __ldg(rb + e);       // folded into the per-column bias
+              if (e < nval) rb4[e] = __ldg(rb + e);       // one load per chunk; ADDED AFTER the bias, like the per-row path below
           }
         }
         const bool f_gn = (kGeneric || (MODE & EPI_OUT_F32)) && p.gn_partial != nullptr;
@@ -554,6 +554,13 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
           if ((!full_rows && m >= p.M) || nval <= 0) continue;
 #pragma unroll
           for (int e = 0; e < 4; ++e) x[e] += b4[e];
+          // (acc + bias) + rowbias in BOTH paths: folding the row bias into the column bias first rounds differently, and
+          // whether a 32-row chunk lies in one batch row depends on the row's position in the batch (images of 16 or 4
+          // pixels: the last chunk of an odd batch) — found with tools/shared_prefix_diag2.py on B200, round 2
+          if (f_rowbias && rb_uniform) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[e] += rb4[e];
+          }
           if (f_rowbias && !rb_uniform) {
             const float* rb = p.rowbias + (size_t)(m / p.rows_per_batch) * p.rowbias_ld + col;
 #pragma unroll

@@ -34,14 +34,15 @@ class B200DiFashion:
     def __init__(self, unet: B200UNet2DConditionModel, vae: B200AutoencoderKL, text_encoder: B200CLIPTextModel,
                  fashion_encoder: Optional[MutualEncoder], noise_scheduler, *, eta: float = 0.1, use_history: bool = True,
                  use_mutual_guidance: bool = True, max_rows: int = 256, use_cuda_graph: bool = True,
-                 reference_history_lookup: bool = False):
+                 reference_history_lookup: bool = True):
         self.unet, self.vae, self.text_encoder = unet, vae, text_encoder
         self.fashion_encoder, self.noise_scheduler = fashion_encoder, noise_scheduler
         self.vae_scale_factor = 2 ** (len(vae.config.block_out_channels) - 1)
         self.use_history, self.use_mutual_guidance = use_history, use_mutual_guidance
         # The reference tests `cate in history[uid]` with `cate` a 0-d TENSOR (difashion.py:380-382): tensors hash by
-        # identity, so that membership test is always False and every item gets the null latent.  False (default)
-        # implements the evident intent (integer category keys); True reproduces the reference's behaviour.
+        # identity, so that membership test is always False and every item gets the null latent.  True (default)
+        # reproduces the reference — same outputs for the same checkpoint and seed; False implements the evident intent
+        # (integer category keys), an explicit opt-in because it feeds the UNet an input the reference never produces.
         self.reference_history_lookup = reference_history_lookup
         self.pipe = B200DiFashionPipeline(unet, fashion_encoder, noise_scheduler, eta_mutual=eta, use_history=use_history,
                                           use_mutual_guidance=use_mutual_guidance, max_rows=max_rows,
@@ -89,6 +90,9 @@ class B200DiFashion:
         the same ``args`` fields (``pretrained_model_name_or_path``, ``category_emb_size``, ``hid_dim``, ``eta``)."""
         if logger is not None:
             logger.info("load scheduler / CLIPTextModel / VAE / UNet for the B200 path...")
+        for flag in ("use_history", "use_mutual_guidance"):          # the reference's ablation switches (inf4eval.py:148-160)
+            if hasattr(args, flag):
+                kw.setdefault(flag, bool(getattr(args, flag)))
         return cls.from_pretrained(args.pretrained_model_name_or_path, cate_num=cate_num,
                                    category_emb_size=getattr(args, "category_emb_size", 64),
                                    hid_dim=getattr(args, "hid_dim", 256), eta=getattr(args, "eta", 0.1), device=device, **kw)
@@ -110,6 +114,7 @@ class B200DiFashion:
         self.fashion_encoder.register_to_config(**enc.config)
         self.fashion_encoder.load_state_dict(enc.state_dict())
         self._prompt_cache.clear()
+        self.pipe._states.clear()            # captured graphs point into the packed weights of the previous checkpoint
         return self
 
     def save_checkpoint(self, output_dir: str, safe_serialization: bool = False) -> None:

@@ -26,7 +26,7 @@ def encode_all_item_latents(vae, img_dataset, data_path: Optional[str] = None, b
     ``vae.encode_latents`` (mode of the posterior times the scaling factor) and saved there."""
     path = os.path.join(data_path, ALL_LATENTS_FILE) if data_path else None
     if path and os.path.exists(path):
-        return torch.tensor(np.load(path, allow_pickle=True))
+        return torch.tensor(np.load(path, allow_pickle=False))
     device = torch.device(device) if device is not None else vae.device
     if device.type != "cuda":
         raise RuntimeError("encode_all_item_latents needs the VAE on a CUDA device: there is no CPU fallback")

@@ -29,12 +29,17 @@ def _prof_begin():
     return e0
 
 
-def _prof_end(e0, kind: str, flops: float, shape):
+ALG_BYTES = None    # with PROFILE: algorithmic HBM bytes per kind (operand + result tensors of each launch counted once)
+
+
+def _prof_end(e0, kind: str, flops: float, shape, nbytes: float = 0.0):
     if e0 is None:
         return
     e1 = torch.cuda.Event(enable_timing=True)
     e1.record(torch.cuda.current_stream())
     PROFILE.append((kind, flops, shape, e0, e1))
+    if ALG_BYTES is not None:
+        ALG_BYTES[kind] = ALG_BYTES.get(kind, 0.0) + nbytes
 
 
 def launch_count() -> int:
@@ -220,7 +225,15 @@ def gemm(a: Sequence[torch.Tensor], w: torch.Tensor, n: int, *, out: torch.Tenso
         check(_lib.load().dfb_gemm(C.byref(p), _stream()), "dfb_gemm")
     if e0 is not None:
         k_exec = sum(int(p.ntaps[s]) * ceil64(int(p.a_c[s])) for s in range(nseg))
-        _prof_end(e0, "conv" if conv_geom is not None else "gemm", 2.0 * m_rows * n * k_exec, (m_rows, n, k_exec))
+        # algorithmic bytes: every operand / result tensor once (a conv reads its input once, not once per tap)
+        esz = 4 if f32 else 2
+        nb = sum(m_rows * max(int(p.a_c[s]) + max(co for _, _, co in (taps[s] if taps is not None else TAP_CENTER)), 1) * esz
+                 for s in range(nseg))
+        nb += n * k_exec * esz + (n * 4 if bias is not None else 0)
+        nb += (rowbias.shape[0] * n * 4 if rowbias is not None else 0) + (m_rows * n * residual.element_size() if residual is not None else 0)
+        out_rows = m_rows * (4 if up_phase is not None else 1)
+        nb += m_rows * (n // 2 if geglu else n) * out.element_size() + (gn_partial.numel() * 4 // (4 if up_phase is not None else 1) if gn_partial is not None else 0)
+        _prof_end(e0, "conv" if conv_geom is not None else "gemm", 2.0 * m_rows * n * k_exec, (m_rows, n, k_exec), float(nb))
     _count(1)
     return out
 

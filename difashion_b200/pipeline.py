@@ -63,7 +63,9 @@ def guidance_plan(use_history: bool, use_mutual: bool, s_cate: float, s_hist: fl
             return [1, 1, 0], [1, 0, 0], [1, 1, 1], [s_mutual, s_cate - s_mutual, 1.0 - s_cate]
         return [1, 0], [1, 1], [1, 1], [s_cate, 1.0 - s_cate]
     if do_h:
-        return [1, 1], [1, 1], [1, 0], [s_hist, 1.0 - s_hist]
+        # (the mutual section checks do_m first, difashion.py:506-508: with both history and mutual guidance on and no
+        # category guidance the second branch drops the mutual condition too, and the hist scale combines them, :555-560)
+        return [1, 1], ([1, 0] if do_m else [1, 1]), [1, 0], [s_hist, 1.0 - s_hist]
     if do_m:
         return [1, 1], [1, 0], [1, 1], [s_mutual, 1.0 - s_mutual]
     return [1], [1], [1], [1.0]
@@ -140,7 +142,8 @@ class B200DiFashionPipeline:
 
     def _state(self, dev, n, n_given, olen, size, nb, S, D, plan) -> "_State":
         key = (str(dev), n, n_given, olen, size, nb, S, D, tuple(map(tuple, plan[:3])), self.use_history,
-               self.use_mutual_guidance, self.max_rows, str(self.unet._op_dtype), self.streams, self.share_cfg_prefix)
+               self.use_mutual_guidance, self.max_rows, str(self.unet._op_dtype), self.streams, self.share_cfg_prefix,
+               self.eta_mutual)                 # (eta is a kernel scalar inside the captured graph)
         st = self._states.get(key)
         if st is not None:
             return st
@@ -181,6 +184,7 @@ class B200DiFashionPipeline:
                 ch.ws = self.unet.workspace(("pipe", nb, min(n, per), size, str(self.unet._op_dtype), "stream", i % self.streams), dev)
         st.step_graph = None
         st.warm = False
+        st.graph_sig = None
         self._states[key] = st
         return st
 
@@ -206,6 +210,14 @@ class B200DiFashionPipeline:
         S, D = category_prompts.shape[1], category_prompts.shape[2]
         n_given = 0 if all_latents is None else all_latents.shape[0]
         st = self._state(dev, n, n_given, olen, size, nb, S, D, plan)
+        # A captured graph holds raw pointers into the UNet's packed weights: when the weights were replaced since the
+        # capture (load_checkpoint between two generations — inf4eval.py's loop over checkpoints), the pack is re-made
+        # here and the graphs of this state are dropped, to be captured again on the first step.
+        sig = self.unet.graph_signature(dev)
+        if st.graph_sig != sig:
+            st.graph_sig, st.step_graph = sig, None
+            for ch in st.chunks:
+                ch.graph = None
         st.weights = weights
         sched = self.scheduler
         sched.set_timesteps(num_inference_steps)
@@ -329,6 +341,85 @@ class B200DiFashionPipeline:
             out.copy_(st.latents, non_blocking=True)
             return out
         return st.latents
+
+
+    # ---------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def generate_sharded(self, *, olists: torch.Tensor, all_latents: Optional[torch.Tensor], category_prompts: torch.Tensor,
+                         null_prompt: torch.Tensor, hist_latents: Optional[torch.Tensor], null_latent: torch.Tensor,
+                         init_latents: torch.Tensor, group=None, out: Optional[torch.Tensor] = None, device=None,
+                         **kw) -> torch.Tensor:
+        """``generate`` for one job spread over the ranks of a ``torch.distributed`` group (one process per GPU).
+
+        Every rank passes the SAME global inputs (host tensors are fine: only the rank's shard is copied to its GPU).  Whole
+        outfits are dealt out in contiguous blocks (``shard_outfits``; the mutual condition couples only the items of one
+        outfit, so the denoising loop needs no collective), every rank runs ``generate`` on its block, and ONE padded
+        ``all_gather`` of the finished latents (NCCL over NVLink; uneven blocks are padded to the largest) returns the
+        global ``[N, 4, h, w]`` tensor, in ``torch.nonzero(olists == 0)`` order, on every rank — bit-identical to what a
+        single rank computes for the same inputs.  Ranks left without an outfit (fewer outfits than ranks) only take part
+        in the gather.  Replaces the single-process loop body of ``inf4eval.py:688-760`` for a multi-GPU box."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("generate_sharded needs an initialised torch.distributed process group (torchrun); "
+                               "use generate() in a single process")
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        local, (i0, i1), counts = shard_generation_inputs(
+            dict(olists=olists, all_latents=all_latents, category_prompts=category_prompts, null_prompt=null_prompt,
+                 hist_latents=hist_latents, null_latent=null_latent, init_latents=init_latents), rank, world)
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        lat = self.generate(**local, device=dev, **kw) if i1 > i0 else None
+        full = gather_item_rows(lat, counts, tuple(init_latents.shape[1:]), dev, group)
+        if out is not None:
+            out.copy_(full, non_blocking=True)
+            return out
+        return full
+
+
+def shard_generation_inputs(inputs: dict, rank: int, world_size: int):
+    """The slice of ``generate``'s inputs that rank ``rank`` of ``world_size`` owns: whole outfits ``shard_outfits`` deals it,
+    the rows of ``all_latents`` of those outfits, and the item rows (blank slots, ``nonzero(olists == 0)`` order — outfit-major,
+    hence contiguous per block) of the per-item tensors.  Returns ``(local_inputs, (item_start, item_stop), items_per_rank)``.
+    Pure host logic (CPU-tested with gloo, world_size 2)."""
+    olists = inputs["olists"].cpu()
+    bsz, olen = olists.shape
+    blanks = (olists == 0).sum(1)
+    cum = [0]
+    for b in blanks.tolist():
+        cum.append(cum[-1] + int(b))
+    counts = []
+    for r in range(world_size):
+        sh = shard_outfits(bsz, r, world_size)
+        counts.append(cum[sh.stop] - cum[sh.start])
+    mine = shard_outfits(bsz, rank, world_size)
+    i0, i1 = cum[mine.start], cum[mine.stop]
+    local = dict(inputs)
+    local["olists"] = olists[mine.start:mine.stop]
+    if inputs.get("all_latents") is not None:
+        local["all_latents"] = inputs["all_latents"][mine.start * olen:mine.stop * olen]
+    for k in ("category_prompts", "hist_latents", "init_latents"):
+        if inputs.get(k) is not None:
+            local[k] = inputs[k][i0:i1]
+    return local, (i0, i1), counts
+
+
+def gather_item_rows(local: Optional[torch.Tensor], counts: Sequence[int], row_shape, device, group=None) -> torch.Tensor:
+    """One padded all-gather of per-item rows (finished latents): rank r contributes ``counts[r]`` rows; every rank gets the
+    ``[sum(counts), *row_shape]`` tensor in rank order.  The only collective of a sharded generation."""
+    import torch.distributed as dist
+    world = len(counts)
+    rank = dist.get_rank(group)
+    pad = max(max(counts), 1)
+    buf = torch.zeros(pad, *row_shape, dtype=torch.float32, device=device)
+    if counts[rank]:
+        buf[:counts[rank]].copy_(local)
+    gathered = torch.empty(world * pad, *row_shape, dtype=torch.float32, device=device)
+    if dist.get_backend(group) == "nccl":
+        dist.all_gather_into_tensor(gathered, buf, group=group)
+    else:                                   # gloo (CPU tests)
+        dist.all_gather(list(gathered.view(world, pad, *row_shape).unbind(0)), buf, group=group)
+    if all(c == pad for c in counts):
+        return gathered
+    return torch.cat([gathered[r * pad:r * pad + c] for r, c in enumerate(counts)], 0)
 
 
 def shard_outfits(n_outfits: int, rank: int, world_size: int):

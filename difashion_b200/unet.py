@@ -198,6 +198,7 @@ class B200UNet2DConditionModel(nn.Module):
             p.requires_grad_(False)
         self._pack: Optional[Dict[str, Any]] = None
         self._pack_key = None
+        self._pack_gen = 0                  # bumped on every (re)pack: captured graphs hold pointers into the packed buffers
         self._op_dtype = torch.bfloat16
         self._ws: Dict[Any, Workspace] = {}
 
@@ -377,6 +378,7 @@ class B200UNet2DConditionModel(nn.Module):
         P["tproj"] = (ops.pack_linear(torch.cat(tp_w, 0), dt), torch.cat(tp_b, 0).contiguous(), off)
         P["device"] = device
         self._pack, self._pack_key = P, key
+        self._pack_gen += 1
         self.clear_context_cache()
         return P
 
@@ -395,6 +397,13 @@ class B200UNet2DConditionModel(nn.Module):
     def _gnp_of(self, t: Optional[torch.Tensor]):
         return None if t is None else self._gnp.get(t.data_ptr())
 
+    def _tap(self, name: str, t: torch.Tensor):
+        """Diagnostic capture of an intermediate (``forward_nhwc(taps=..., fine_taps=True)``): used by the parity tests'
+        failure reports and tools/shared_prefix_diag.py; never active inside a captured graph."""
+        d = self.__dict__.get("_fine_taps")
+        if d is not None:
+            d[f"{len(d):03d}:{name}"] = t.detach().clone()
+
     def _resnet(self, pk, srcs: List[torch.Tensor], temb_all, ws: Workspace, out_tag: str):
         x0 = srcs[0]
         x1 = srcs[1] if len(srcs) > 1 else None
@@ -406,13 +415,16 @@ class B200UNet2DConditionModel(nn.Module):
         xraw = ws.get("xraw", (B, H, W, cin), self._op_dtype) if pk["shortcut"] else None
         ops.groupnorm(x0, x1, g, b, groups=groups, eps=eps, silu=True, stats_ws=stats, out=xn, raw_out=xraw,
                       partials=(self._gnp_of(x0), self._gnp_of(x1)))
+        self._tap(out_tag + ".gn1", xn)
         h1 = ws.get("h1", (B, H, W, cout), torch.float32)
         h1p = self._gnp_new(ws, "h1", h1)
         ops.gemm([xn], pk["w1"], cout, out=h1, taps=[ops.TAPS_3X3], conv_geom=(B, H, W), bias=pk["b1"],
                  rowbias=temb_all[:, pk["temb_off"]:pk["temb_off"] + cout], rows_per_batch=H * W, gn_partial=h1p)
+        self._tap(out_tag + ".conv1", h1)
         g, b, eps, groups = pk["n2"]
         hn = ws.get("hn", (B, H, W, cout), self._op_dtype)
         ops.groupnorm(h1, None, g, b, groups=groups, eps=eps, silu=True, stats_ws=stats, out=hn, partials=(h1p, None))
+        self._tap(out_tag + ".gn2", hn)
         out = ws.get(out_tag, (B, H, W, cout), torch.float32)
         outp = self._gnp_new(ws, out_tag, out)
         if pk["shortcut"]:
@@ -421,6 +433,7 @@ class B200UNet2DConditionModel(nn.Module):
         else:
             ops.gemm([hn], pk["w2"], cout, out=out, taps=[ops.TAPS_3X3], conv_geom=(B, H, W), bias=pk["b2"], residual=x0,
                      gn_partial=outp)
+        self._tap(out_tag + ".out", out)
         return out
 
     # Upsample2D (nearest-2x, then conv3x3): an output pixel (2i + a, 2j + b) sees only a 2x2 window of the INPUT, so the
@@ -491,8 +504,10 @@ class B200UNet2DConditionModel(nn.Module):
         xn = ws.get("xn", (M, C), self._op_dtype)
         ops.groupnorm(x[:Bp], None, g, b, groups=groups, eps=eps, silu=False, stats_ws=stats, out=xn[:Mp].view(Bp, H, W, C),
                       partials=(self._gnp_of(x), None))
+        self._tap(name + ".gn", xn[:Mp])
         h = ws.get("tr_h", (M, C), torch.float32)
         ops.gemm([xn[:Mp]], pk["pin"][0], C, out=h[:Mp], bias=pk["pin"][1])
+        self._tap(name + ".pin", h[:Mp])
         ln = ws.get("ln", (M, C), self._op_dtype)
         a1, a2 = pk["a1"], pk["a2"]
         fast = isinstance(pk["attn1"].processor, B200AttnProcessor) and isinstance(pk["attn2"].processor, B200AttnProcessor)
@@ -500,40 +515,52 @@ class B200UNet2DConditionModel(nn.Module):
         # --- self-attention
         g, b, eps = pk["ln1"]
         ops.layernorm(h[:Mp], g, b, ln[:Mp], eps)
+        self._tap(name + ".ln1", ln[:Mp])
         if fast:
             qkv = ws.get("qkv", (B, S, 3 * a1.cp), self._op_dtype)
             ops.gemm([ln[:Mp]], a1.w_qkv, 3 * a1.cp, out=qkv.view(M, 3 * a1.cp)[:Mp])
+            self._tap(name + ".qkv", qkv[:Bp])
             att = ws.get("att", (B, S, a1.cp), self._op_dtype)
             ops.attention(qkv[:Bp, :, :a1.cp], qkv[:Bp, :, a1.cp:2 * a1.cp], qkv[:Bp, :, 2 * a1.cp:], att[:Bp], heads=a1.heads,
                           dp=a1.dp, scale=a1.scale)
+            self._tap(name + ".att1", att[:Bp])
             ops.gemm([att.view(M, a1.cp)[:Mp]], a1.w_o, C, out=h[:Mp], bias=a1.b_o, residual=h[:Mp])
         else:
             h[:Mp].add_(pk["attn1"].processor(pk["attn1"], ln[:Mp].view(Bp, S, C)).reshape(Mp, C).float())
         if shared_tail:
             h[Mp:].copy_(h[Mp - shared_tail * S:Mp])
             x[Bp:].copy_(x[Bp - shared_tail:Bp])
+        self._tap(name + ".h1", h)
         # --- cross-attention over the (category prompt [+ history]) tokens
         g, b, eps = pk["ln2"]
         ops.layernorm(h, g, b, ln, eps)
+        self._tap(name + ".ln2", ln)
         if fast:
             q = ws.get("q", (B, S, a2.cp), self._op_dtype)
             ops.gemm([ln], a2.w_q, a2.cp, out=q.view(M, a2.cp))
+            self._tap(name + ".q", q)
             kv = kv_store[name]
             att = ws.get("att", (B, S, a2.cp), self._op_dtype)
             ops.attention(q, kv[..., :a2.cp], kv[..., a2.cp:], att, heads=a2.heads, dp=a2.dp, scale=a2.scale)
+            self._tap(name + ".att2", att)
             ops.gemm([att.view(M, a2.cp)], a2.w_o, C, out=h, bias=a2.b_o, residual=h)
         else:
             h.add_(pk["attn2"].processor(pk["attn2"], ln.view(B, S, C), encoder_hidden_states=ctx_bf16).reshape(M, C).float())
+        self._tap(name + ".h2", h)
         # --- GEGLU feed-forward
         g, b, eps = pk["ln3"]
         ops.layernorm(h, g, b, ln, eps)
+        self._tap(name + ".ln3", ln)
         ff = ws.get("ff", (M, 4 * C), self._op_dtype)
         ops.gemm([ln], pk["geglu"][0], 8 * C, out=ff, bias=pk["geglu"][1], geglu=True)
+        self._tap(name + ".ff", ff)
         hb = ws.get("tr_hb", (M, C), self._op_dtype)
         ops.gemm([ff], pk["ffo"][0], C, out=hb, bias=pk["ffo"][1], residual=h)
+        self._tap(name + ".ffo", hb)
         out = ws.get(out_tag, (B, H, W, C), torch.float32)
         ops.gemm([hb], pk["pout"][0], C, out=out.view(M, C), bias=pk["pout"][1], residual=x.view(M, C),
                  gn_partial=self._gnp_new(ws, out_tag, out))
+        self._tap(name + ".out", out)
         return out
 
     def _temb(self, P, t_dev: torch.Tensor, ws: Workspace):
@@ -552,7 +579,7 @@ class B200UNet2DConditionModel(nn.Module):
         return temb_all
 
     def forward_nhwc(self, x_in: torch.Tensor, t_dev: torch.Tensor, ctx_bf16: torch.Tensor, kv_store: Dict[str, torch.Tensor],
-                     ws: Workspace, taps: Optional[dict] = None, shared_tail: int = 0) -> torch.Tensor:
+                     ws: Workspace, taps: Optional[dict] = None, shared_tail: int = 0, fine_taps: bool = False) -> torch.Tensor:
         """x_in: bf16 NHWC [B,H,W,in_channels]; t_dev: fp32 [B]; ctx: bf16 [B,S_kv,D]; kv_store: the result of
         ``project_context(ctx)``.  Returns the fp32 NHWC noise prediction [B,H,W,out_channels] (a workspace buffer).
 
@@ -569,7 +596,10 @@ class B200UNet2DConditionModel(nn.Module):
             k = 0
         Bp = B - k
         self._gnp = {}
+        # fine_taps: every intermediate of every ResNet / transformer block goes into ``taps`` too (diagnostics only)
+        self.__dict__["_fine_taps"] = taps if (fine_taps and taps is not None) else None
         temb_all = self._temb(P, t_dev, ws)
+        self._tap("temb_all", temb_all)
         c0 = self.config.block_out_channels[0]
         h = ws.get("skip0", (B, H, W, c0), torch.float32)
         part = self._gnp_new(ws, "skip0", h)
@@ -582,6 +612,8 @@ class B200UNet2DConditionModel(nn.Module):
                 part[Bp * blk:].copy_(part[(Bp - k) * blk:Bp * blk])
         if taps is not None:
             taps["conv_in"] = h.clone()
+            if part is not None:
+                self._tap("conv_in.gnp", part)
         skips, ns = [h], 1
         for i, bp in enumerate(P["down"]):
             for j, rp in enumerate(bp["resnets"]):
@@ -636,7 +668,16 @@ class B200UNet2DConditionModel(nn.Module):
         cout = self.config.out_channels
         eps_out = ws.get("eps_out", (B, H, W, cout), torch.float32)
         ops.gemm([xn], P["conv_out"][0], cout, out=eps_out, taps=[ops.TAPS_3X3], conv_geom=(B, H, W), bias=P["conv_out"][1])
+        self.__dict__["_fine_taps"] = None
         return eps_out
+
+    def graph_signature(self, device=None):
+        """Everything a captured graph of ``forward_nhwc`` bakes in besides its shapes: the packed-weight buffers (re-made
+        whenever a parameter changes — ``load_state_dict``, ``conv_in`` surgery, ``set_precision``), the attention
+        processors and the upsample variant.  ``B200DiFashionPipeline`` re-captures when this changes."""
+        self.pack(device)
+        procs = tuple(type(m.processor).__name__ for m in self.modules() if isinstance(m, Attention))
+        return (self._pack_gen, str(self._op_dtype), procs, bool(self.upsample_phases))
 
     def workspace(self, key, device) -> Workspace:
         ws = self._ws.get(key)

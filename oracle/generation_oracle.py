@@ -223,6 +223,7 @@ def oracle_fashion_generation(unet, mutual_encoder, scheduler, text_encoder, vae
                               outfit_images, category, history, null_img, init_latents, num_inference_steps=50,
                               category_guidance_scale=7.5, hist_guidance_scale=7.5, mutual_guidance_scale=7.5,
                               eta_mutual=0.1, use_history=True, use_mutual_guidance=True, ddim_eta=0.0, generator=None,
+                              history_int_keys=False,
                               max_steps: Optional[int] = None, record: Optional[dict] = None):
     """``DiFashion.fashion_generation(..., return_dict=False)`` (difashion.py:277-616) on the CPU oracles.
 
@@ -239,8 +240,14 @@ def oracle_fashion_generation(unet, mutual_encoder, scheduler, text_encoder, vae
     null_prompt = text_encoder(null_input_ids(category_prompts.shape[1]))[0]      # :343-352
     null_latent = vae.encode_mode_scaled(null_img.unsqueeze(0))[0]          # :375-376
     hist = []                                                               # :378-386
-    for i, cate in enumerate(fill_cate.tolist()):
+    # difashion.py:380-382 iterates the TENSOR ``fill_cate`` and tests ``cate in history[uid]`` with the 0-d tensor: tensors
+    # hash by identity, so the membership test never matches an integer key and every item gets the null latent.  Restated
+    # literally (default); ``history_int_keys=True`` is the evident intent (integer category keys), kept for the product's
+    # ``reference_history_lookup=False`` option.
+    for i, cate in enumerate(fill_cate):
         uid = int(uids[fill_idx[i][0]])
+        if history_int_keys:
+            cate = int(cate)
         if use_history and cate in history.get(uid, {}):
             hist.append(history[uid][cate])
         else:

@@ -89,11 +89,13 @@ def _oracle_run(o, inp, steps, scales, **kw):
 @pytest.mark.parametrize("precision,task,sched", [("fp32", "FITB", "ddim"), ("bf16", "FITB", "ddim"), ("bf16", "GOR", "pndm"), ("fp32", "GOR", "ddim")])
 def test_fashion_generation_matches_oracle(precision, task, sched, tmp_path):
     from difashion_b200 import save_batch_outputs, save_outputs_npy
-    o, model, ucfg, ccfg = _build(precision, sched)
+    # GOR runs the reference's history lookup (never matches: null latents), FITB the integer-key intent (history rows active)
+    int_keys = task == "FITB"
+    o, model, ucfg, ccfg = _build(precision, sched, reference_history_lookup=not int_keys)
     olists = torch.tensor([[3, 0, 7, 9], [0, 5, 0, 2], [4, 4, 4, 0]]) if task == "FITB" else torch.zeros(2, 4, dtype=torch.long)
     inp = _inputs(ucfg, ccfg, olists)
     steps, scales = 6, (12.0, 4.0, 5.0)
-    ref, rec = _oracle_run(o, inp, steps, scales)
+    ref, rec = _oracle_run(o, inp, steps, scales, history_int_keys=int_keys)
     got, init = model.fashion_generation(**inp, num_inference_steps=steps, category_guidance_scale=scales[0],
                                          hist_guidance_scale=scales[1], mutual_guidance_scale=scales[2], output_type="uint8",
                                          return_dict=False)
@@ -130,9 +132,12 @@ def test_fashion_generation_matches_oracle(precision, task, sched, tmp_path):
 
 
 def test_fashion_generation_history_lookup_and_prompt_cache():
-    """History rows are used for (uid, category) pairs present in `history` (integer keys); `reference_history_lookup=True`
-    reproduces the reference's tensor-keyed membership test, which never matches; prompts are encoded once."""
+    """`reference_history_lookup=True` (default) reproduces the reference's tensor-keyed membership test, which never matches
+    (every item gets the null latent); False uses history rows for (uid, category) pairs present in `history` (integer keys);
+    prompts are encoded once."""
     o, model, ucfg, ccfg = _build("fp32")
+    assert model.reference_history_lookup is True
+    model.reference_history_lookup = False
     olists = torch.tensor([[0, 0, 7, 9], [0, 5, 0, 2]])
     inp = _inputs(ucfg, ccfg, olists)
     inp["category"] = torch.tensor([[1, 2, 5, 5], [4, 5, 5, 5]])              # (uid 40: 1, 2) and (uid 41: 4) are in `history`
@@ -141,9 +146,11 @@ def test_fashion_generation_history_lookup_and_prompt_cache():
     n_cached = len(model._prompt_cache)
     b = model.fashion_generation(**inp, **kw)[0].images.clone()
     assert torch.equal(a, b) and len(model._prompt_cache) == n_cached            # deterministic; no re-encoding
-    _, rec = _oracle_run(o, inp, 3, (12.0, 4.0, 5.0))
+    _, rec = _oracle_run(o, inp, 3, (12.0, 4.0, 5.0), history_int_keys=True)
     assert rel_l2(a.cpu(), rec["latents"]) <= 1e-4
     model.reference_history_lookup = True
     c = model.fashion_generation(**inp, **kw)[0].images
+    _, rec_ref = _oracle_run(o, inp, 3, (12.0, 4.0, 5.0))                       # the literal restatement: lookup never matches
     _, rec_nohist = _oracle_run(o, dict(inp, history={}), 3, (12.0, 4.0, 5.0))
-    assert rel_l2(c.cpu(), rec_nohist["latents"]) <= 1e-4 and rel_l2(c.cpu(), rec["latents"]) > 1e-3
+    assert torch.equal(rec_ref["latents"], rec_nohist["latents"])
+    assert rel_l2(c.cpu(), rec_ref["latents"]) <= 1e-4 and rel_l2(c.cpu(), rec["latents"]) > 1e-3

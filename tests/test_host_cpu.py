@@ -240,7 +240,13 @@ def test_guidance_plan_weights_equal_reference_formula():
     assert torch.allclose(sum(wi * e[i] for i, wi in enumerate(w)), e[2] + s_m * (e[0] - e[1]) + s_c * (e[1] - e[2]), atol=1e-5)
     assert guidance_plan(True, True, 1.0, 1.0, 1.0)[3] == [1.0]
     ctx, um, uh, w = guidance_plan(True, True, 1.0, s_h, 1.0)
-    assert ctx == [1, 1] and uh == [1, 0] and w == [s_h, 1 - s_h]
+    assert ctx == [1, 1] and um == [1, 1] and uh == [1, 0] and w == [s_h, 1 - s_h]
+    # history + mutual guidance without category guidance: difashion.py:506-508 nulls the mutual condition of branch 2
+    # (do_m is tested first there), :418-420 nulls its history, and :555-560 combines the two with the HISTORY scale
+    ctx, um, uh, w = guidance_plan(True, True, 1.0, s_h, s_m)
+    assert ctx == [1, 1] and um == [1, 0] and uh == [1, 0] and w == [s_h, 1 - s_h]
+    ctx, um, uh, w = guidance_plan(True, True, 1.0, 1.0, s_m)
+    assert ctx == [1, 1] and um == [1, 0] and uh == [1, 1] and w == [s_m, 1 - s_m]
 
 
 def test_mutual_index_table_matches_oracle_bookkeeping():

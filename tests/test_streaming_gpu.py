@@ -207,3 +207,34 @@ def test_groupnorm_fused_statistics_from_gemm_epilogue(B, H, W, c0, c1):
     x = srcs[0] if not c1 else torch.cat(srcs, -1)
     ref = F.silu(F.group_norm(x.double().permute(0, 3, 1, 2), 32, gamma.double(), beta.double(), 1e-5)).permute(0, 2, 3, 1)
     assert rel_l2(o, ref) < 4e-3, err_report(o.reshape(-1, C), ref.reshape(-1, C), "gn fused")
+
+
+def test_mutual_blend_branches_with_equal_flags_hold_equal_bits():
+    """CFG branches that get the same (mutual, history) flags must come out of the blend kernel bit-identical for EVERY branch
+    count — the shared CFG prefix relies on it.  (Round 1's kernel computed `(1 - eta) * x + eta * m` inside the branch
+    loop; nvcc unrolled the loop by two and contracted the expression into an FMA differently in the remainder iteration, so
+    with 3 branches the last one differed in the last fp32 bit, flipping a bf16 rounding about once per 65k elements —
+    hence 2M elements here.)  Also: the result is the two-products-and-a-sum the reference computes (difashion.py:513)."""
+    from difashion_b200 import ops
+    g = torch.Generator().manual_seed(17)
+    n, s = 128, 64
+    x, m, h = (torch.randn(n, 4, s, s, generator=g).cuda() for _ in range(3))
+    z = torch.randn(4, s, s, generator=g).cuda()
+    eta = 0.1
+    for use_m, use_h in (([1, 1, 1], [1, 0, 0]), ([1, 0, 0], [1, 1, 1]), ([1, 1, 0, 0], [1, 0, 0, 0]), ([1, 1], [1, 0]), ([1, 0, 0], [0, 0, 0])):
+        nb = len(use_m)
+        for dt in (torch.bfloat16, torch.float32):
+            out = torch.empty(nb * n, s, s, 8, dtype=dt, device="cuda")
+            ops.mutual_blend(x, m, h, z, eta, use_m, use_h, out)
+            o = out.view(nb, n, s, s, 8)
+            for a in range(nb):
+                for b in range(a + 1, nb):
+                    if use_m[a] == use_m[b]:
+                        assert torch.equal(o[a, ..., :4], o[b, ..., :4]), (use_m, a, b, dt)
+                    if use_h[a] == use_h[b]:
+                        assert torch.equal(o[a, ..., 4:], o[b, ..., 4:]), (use_h, a, b, dt)
+            if dt == torch.float32:
+                for b in range(nb):
+                    src = m if use_m[b] else z.expand_as(x)
+                    want = ((1 - eta) * x + eta * src).permute(0, 2, 3, 1)        # torch fp32: two products, one sum
+                    assert torch.equal(o[b, ..., :4], want), (use_m, b)

@@ -137,7 +137,7 @@ def test_generation_gor_tiny_50_steps(sched, use_graph):
                                           ((12.0, 4.0, 1.0), (True, True)), ((12.0, 1.0, 1.0), (True, True)),
                                           ((1.0, 4.0, 1.0), (True, True)), ((1.0, 1.0, 5.0), (True, True)),
                                           ((1.0, 1.0, 1.0), (True, True)), ((12.0, 4.0, 5.0), (False, True)),
-                                          ((12.0, 4.0, 5.0), (True, False))])
+                                          ((12.0, 4.0, 5.0), (True, False)), ((1.0, 4.0, 5.0), (True, True))])
 def test_generation_fitb_and_degenerate_cfg_variants(scales, flags):
     """FITB-style outfits (given items + blanks) through every CFG branch layout of difashion.py:533-566."""
     olists = torch.tensor([[3, 0, 7, 9], [0, 5, 0, 2], [4, 4, 4, 0]])
@@ -206,6 +206,34 @@ def test_bitwise_reproducible():
     a = unet(x, 500, ctx).sample.clone()
     b = unet(x, 500, ctx).sample
     assert torch.equal(a, b)
+
+
+def test_captured_graphs_follow_weight_changes():
+    """inf4eval.py's loop over checkpoints: generate, load other weights into the SAME model, generate again.  The captured
+    graphs hold pointers into the packed weights of the first checkpoint: the pipeline has to notice the re-pack and capture
+    again (it used to replay the stale graph).  Second generation == a fresh model built from the second weights, bit for bit."""
+    from difashion_b200.mutual import MutualEncoder
+    from difashion_b200.pipeline import B200DiFashionPipeline
+    from difashion_b200.schedulers import B200DDIMScheduler
+    oracle_a, unet = _mk("tiny", seed=0)
+    oracle_b, unet_b = _mk("tiny", seed=5)
+    cfg = oracle_a.cfg
+    torch.manual_seed(3)
+    me = MutualEncoder(latent_size=cfg.sample_size, hid_dim=64).cuda()
+    inp = _gen_inputs(cfg, torch.tensor([[3, 0, 7, 9], [0, 0, 0, 0]]))
+    pipe = B200DiFashionPipeline(unet, me, B200DDIMScheduler())
+    first = pipe.generate(**inp, num_inference_steps=50, max_steps=3, device="cuda").clone()
+    unet.load_state_dict(oracle_b.state_dict())
+    second = pipe.generate(**inp, num_inference_steps=50, max_steps=3, device="cuda").clone()
+    fresh = B200DiFashionPipeline(unet_b, me, B200DDIMScheduler()).generate(**inp, num_inference_steps=50, max_steps=3, device="cuda")
+    torch.cuda.synchronize()
+    assert not torch.equal(first, second)
+    assert torch.equal(second, fresh)
+    # eta is a kernel scalar inside the graph: a pipeline with another eta on the same UNet must not reuse anything stale
+    pipe.eta_mutual = 0.3
+    third = pipe.generate(**inp, num_inference_steps=50, max_steps=3, device="cuda").clone()
+    fresh3 = B200DiFashionPipeline(unet_b, me, B200DDIMScheduler(), eta_mutual=0.3).generate(**inp, num_inference_steps=50, max_steps=3, device="cuda")
+    assert torch.equal(third, fresh3) and not torch.equal(third, second)
 
 
 def test_attn_processor_on_foreign_attention_module():
