@@ -68,6 +68,8 @@ class AttnParams(C.Structure):
         ("dbg_flags", C.c_int32),
         ("dbg_timeline", C.c_void_p),
         ("causal", C.c_int32),
+        ("ones_col", C.c_int32),
+        ("workspace", C.c_void_p),
     ]
 
 
@@ -81,6 +83,7 @@ _PROTOTYPES = {
     "dfb_abi_version": (C.c_int, []),
     "dfb_num_sms": (C.c_int, []),
     "dfb_sizeof_gemm_params": (C.c_size_t, []),
+    "dfb_attention_ws_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "dfb_sizeof_attn_params": (C.c_size_t, []),
     "dfb_gemm": (C.c_int, [C.POINTER(GemmParams), C.c_void_p]),
     "dfb_gemm_f32": (C.c_int, [C.POINTER(GemmParams), C.c_void_p]),

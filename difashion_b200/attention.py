@@ -51,6 +51,17 @@ class AttnPack:
         self.w_q = ops.pack_linear(hp(wq), dtype)
         self.w_kv = ops.pack_linear(torch.cat([hp(wk), hp(wv)], 0), dtype)
         self.w_qkv = ops.pack_linear(torch.cat([hp(wq), hp(wk), hp(wv)], 0), dtype) if wk.shape[1] == wq.shape[1] else None
+        # Self-attention with head padding (d = 40 -> 48): the fused q|k|v projection gets a bias that is 1.0 in the first
+        # padding column of every head of V and 0 elsewhere (to_q / to_k / to_v have no bias of their own), so V carries a
+        # ones column and the P V MMA of the long-sequence kernel accumulates the softmax denominator (ops.attention
+        # ``ones_col``).  The padding columns of Q / K stay zero (scores unchanged) and to_out's packed weight has zero
+        # columns there (the 1.0 the attention writes into that output column is multiplied by zero).
+        self.ones_col = d if (self.w_qkv is not None and self.dp > d and dtype == torch.bfloat16) else None
+        self.b_qkv = None
+        if self.ones_col is not None:
+            bq = torch.zeros(3, heads, self.dp, dtype=torch.float32, device=device)
+            bq[2, :, d] = 1.0
+            self.b_qkv = bq.reshape(-1).contiguous()
         self.w_o = ops.pack_linear(pack_head_cols(f(attn.to_out[0].weight), heads, self.dp), dtype)
         b = attn.to_out[0].bias
         self.b_o = f(b).contiguous() if b is not None else None
@@ -88,8 +99,9 @@ class B200AttnProcessor:
         dev = x.device
         if encoder_hidden_states is None:
             qkv = torch.empty(b, s, 3 * pk.cp, dtype=torch.bfloat16, device=dev)
-            ops.gemm([x.view(b * s, c)], pk.w_qkv, 3 * pk.cp, out=qkv.view(b * s, 3 * pk.cp))
+            ops.gemm([x.view(b * s, c)], pk.w_qkv, 3 * pk.cp, out=qkv.view(b * s, 3 * pk.cp), bias=pk.b_qkv)
             q, k, v = qkv[..., :pk.cp], qkv[..., pk.cp:2 * pk.cp], qkv[..., 2 * pk.cp:]
+            ones_col = pk.ones_col
         else:
             ctx = encoder_hidden_states.to(torch.bfloat16).contiguous()
             skv = ctx.shape[1]
@@ -98,8 +110,9 @@ class B200AttnProcessor:
             kv = torch.empty(b, skv, 2 * pk.cp, dtype=torch.bfloat16, device=dev)
             ops.gemm([ctx.view(b * skv, ctx.shape[2])], pk.w_kv, 2 * pk.cp, out=kv.view(b * skv, 2 * pk.cp))
             k, v = kv[..., :pk.cp], kv[..., pk.cp:]
+            ones_col = None
         o = torch.empty(b, s, pk.cp, dtype=torch.bfloat16, device=dev)
-        ops.attention(q, k, v, o, heads=pk.heads, dp=pk.dp, scale=pk.scale)
+        ops.attention(q, k, v, o, heads=pk.heads, dp=pk.dp, scale=pk.scale, ones_col=ones_col)
         out = torch.empty(b, s, pk.c_out, dtype=torch.float32, device=dev)
         ops.gemm([o.view(b * s, pk.cp)], pk.w_o, pk.c_out, out=out.view(b * s, pk.c_out), bias=pk.b_o)
         return out.to(hidden_states.dtype)        # to_out[1] is Dropout(0.0): identity

@@ -23,6 +23,12 @@
 namespace dfb {
 
 constexpr int ATT_BLOCK_Q = 128;
+#ifndef DFB_ATTN_POLY_ONES_DEFAULT
+#define DFB_ATTN_POLY_ONES_DEFAULT 0      // until measured: every exponential on the MUFU
+#endif
+#ifndef DFB_ATTN_POLY_DEFAULT
+#define DFB_ATTN_POLY_DEFAULT 0
+#endif
 constexpr int ATT_THREADS = 192;
 constexpr int ATT_STAGES = 2;
 
@@ -43,6 +49,10 @@ struct AttnKernelParams {
   int kv_stages;                  // K/V ring depth of the double-buffered kernel (2 or 3)
   int q_tiles;                    // query tiles per CTA of the short-KV kernel
   int causal;                     // key j visible to query i only when j <= i (generic single-buffer kernel only)
+  int l_col;                      // attn_fwd_sa_kernel<ONES>: column of O that accumulates the softmax denominator (V holds 1.0 there)
+  int s_ring;                     // attn_fwd_sa_kernel: score / probability buffers in tensor memory (2 or 3)
+  int tl_second;                  // attn_fwd_sa_kernel tuning hook: linear index of the second CTA that writes stamps
+  int* redo_flags;                // attn_fwd_sa8_kernel -> attn_fwd_sa_kernel<.., REDO>: one flag per CTA (caller's workspace)
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -397,12 +407,7 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ A
 // PT: the probabilities go back into tensor memory (over the score buffer they came from) and O += P V reads
 // its A operand from TMEM (tcgen05.mma TS form): no P round trip through shared memory, no proxy fence, and the
 // PV MMA no longer pays the 4 KB-per-instruction shared-memory A fetch.
-// NM ("no max"): the fast path does not track the tile maximum (one FMNMX per score less: 3.5 instead of 4.5 issue slots
-// per element).  Every exponential is >= 0, so the tile's row sum bounds its largest term: a sum <= 2^12 over 64 columns
-// means no term above 2^12, and a sum > 2^12 implies a term above 2^6, i.e. a score more than 6 (log2 units) above the
-// reference max -> the careful path finds the true maximum in the registers and rescales (its threshold is 6 instead
-// of 8 here, so a trigger always rescales and cannot repeat on the next tile).
-template <int KV, bool PT, bool NM = false>
+template <int KV, bool PT>
 __global__ void __launch_bounds__(ATT_THREADS, KV == 64 ? 2 : 1)
 attn_fwd_db_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnKernelParams p) {
   constexpr int NST_MAX = 3;
@@ -574,7 +579,7 @@ attn_fwd_db_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const float sv = __uint_as_float(sreg[c * 32 + h * 16 + i]);
-              if constexpr (!NM) m8[i & 7] = fmaxf(m8[i & 7], sv);
+              m8[i & 7] = fmaxf(m8[i & 7], sv);
               pv[i] = ex2f(fmaf(sv, p.scale_log2, -m_ref));
               l8[i & 7] += pv[i];
             }
@@ -591,18 +596,8 @@ attn_fwd_db_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant_
           }
         }
         const float tsum = ((l8[0] + l8[1]) + (l8[2] + l8[3])) + ((l8[4] + l8[5]) + (l8[6] + l8[7]));
-        if constexpr (NM) {
-          careful = __any_sync(0xffffffffu, !(tsum <= 4096.0f));        // also catches inf / nan
-          if (careful) {                                                   // rare: true maximum from the registers
-            float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-            for (int i = 0; i < KV; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(sreg[i]));
-            mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * p.scale_log2;
-          }
-        } else {
-          mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7]))) * p.scale_log2;
-          careful = __any_sync(0xffffffffu, mx > m_ref + 8.0f);
-        }
+        mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7]))) * p.scale_log2;
+        careful = __any_sync(0xffffffffu, mx > m_ref + 8.0f);
         if (!careful) l += tsum;
       } else {
 #pragma unroll
@@ -617,7 +612,7 @@ attn_fwd_db_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant_
       }
       if (careful) {
         // new reference max: rescale O (needs every earlier PV retired) and l, redo the tile from registers
-        const bool need = mx > m_ref + (NM ? 6.0f : 8.0f);
+        const bool need = mx > m_ref + 8.0f;
         if (__any_sync(0xffffffffu, need)) {
           const float m_new = need ? mx : m_ref;
           const float alpha = ex2f(m_ref - m_new);     // m_ref = -inf on the first tile -> 0
@@ -695,583 +690,6 @@ attn_fwd_db_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant_
         bq.w = pack_bf16x2(__uint_as_float(r[14]) * inv_l, __uint_as_float(r[15]) * inv_l);
         *reinterpret_cast<uint4*>(orow + c * 16) = a;
         *reinterpret_cast<uint4*>(orow + c * 16 + 8) = bq;
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == W_MMA) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, p.tmem_cols);
-  }
-}
-
-
-// =================================================================================================
-// Ping-pong variant (EXPERIMENT, opt-in through dbg_flags bit12; not yet run on hardware — written at the end of round 1
-// from the reading of the stamps in profiles/r01_attention_experiments.md, session 5).
-//
-// The shipped kernel keeps two CTAs per SM so that one CTA's bookkeeping (wait for S, P store, fence, arrive) can hide under
-// the other's exponentials.  The stamps say it does not happen: two streams that contend for the one MUFU progress at equal
-// speed, reach their bookkeeping together and idle together (1029 + ~380 cycles per tile instead of ~1024).  Here the
-// alternation is explicit: ONE CTA per SM owns two query tiles (256 rows) of one (batch, head); softmax warpgroup A
-// (warps 0..3) works on tile 0, warpgroup B (warps 4..7) on tile 1, and two named barriers pass the "exponential turn"
-// back and forth (FlashAttention-3's ping-pong, applied to the MUFU): while A computes the exponentials of its KV tile j,
-// B stores P_j, arrives, and waits for its next S; then they swap.  K/V tiles are loaded ONCE for both query tiles.
-// TMEM: S_A[2] | S_B[2] | O_A | O_B = 4 x 64 + 2 x dp <= 512 columns (dp <= 64: the S = 4096, d = 40 -> 48 layers).
-// KV tile 64, P through tensor memory (TS-form PV).  Same numerics as attn_fwd_db_kernel<64, true>.
-// =================================================================================================
-constexpr int ATT_PP_THREADS = 320;     // 8 softmax warps + TMA producer + MMA issuer
-
-__device__ __forceinline__ void named_bar_sync(int id, int count) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-__device__ __forceinline__ void named_bar_arrive(int id, int count) {
-  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-
-__global__ void __launch_bounds__(ATT_PP_THREADS, 1)
-attn_fwd_pp_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnKernelParams p) {
-  constexpr int KV = 64;
-  constexpr int NST_MAX = 4;
-  const int NST = p.kv_stages;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int dchunks = p.dp >> 4;
-  const uint32_t q_tile_bytes = (uint32_t)dchunks * ATT_BLOCK_Q * 32u;
-  constexpr uint32_t kv_chunk_bytes = KV * 32u;
-  const uint32_t kv_tile_bytes = (uint32_t)dchunks * kv_chunk_bytes;
-  const uint32_t sQ = smem_base;                                            // Q tile 0, Q tile 1
-  const uint32_t sKV = sQ + 2 * q_tile_bytes;                               // stage s: K then V
-  const uint32_t bar_base = sKV + NST * 2 * kv_tile_bytes;
-  const uint32_t q_full = bar_base;
-  auto s_full = [&](int g, int i) { return bar_base + 8u + 8u * (2 * g + i); };          // 4
-  auto p_full = [&](int g, int i) { return bar_base + 40u + 8u * (2 * g + i); };         // 4
-  auto o_done = [&](int g, int i) { return bar_base + 72u + 8u * (2 * g + i); };         // 4
-  auto kv_full = [&](int st) { return bar_base + 104u + 8u * st; };
-  auto kv_empty = [&](int st) { return bar_base + 104u + 8u * (NST_MAX + st); };
-  const uint32_t tmem_ptr_smem = bar_base + 104u + 8u * (2 * NST_MAX);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int qt2 = blockIdx.x, head = blockIdx.y, b = blockIdx.z;            // qt2: pair of query tiles
-  const int n_tiles = p.n_kv_tiles;
-  constexpr int W_TMA = 8, W_MMA = 9;                                        // control warps above the softmax warps
-
-  if (warp == W_TMA && lane == 0) {
-    tma_prefetch_desc(&maps.q);
-    tma_prefetch_desc(&maps.k);
-    tma_prefetch_desc(&maps.v);
-    mbar_init(q_full, 1);
-    for (int g = 0; g < 2; ++g)
-      for (int i = 0; i < 2; ++i) {
-        mbar_init(s_full(g, i), 1);
-        mbar_init(p_full(g, i), 128);
-        mbar_init(o_done(g, i), 1);
-      }
-    for (int st = 0; st < NST; ++st) {
-      mbar_init(kv_full(st), 1);
-      mbar_init(kv_empty(st), 1);
-    }
-    fence_mbar_init();
-    fence_proxy_async_smem();
-  }
-  if (warp == W_MMA) tmem_alloc(tmem_ptr_smem, p.tmem_cols);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
-  auto tmem_S = [&](int g, int i) { return tmem_base + (uint32_t)((2 * g + i) * KV); };
-  auto tmem_Og = [&](int g) { return tmem_base + (uint32_t)(4 * KV) + (uint32_t)(g * p.dp); };
-
-  if (warp == W_TMA) {
-    // ---------------- TMA producer: both Q tiles once, K/V tiles through the ring (shared by both query tiles) ----------------
-    if (elect_one()) {
-      mbar_expect_tx(q_full, 2 * q_tile_bytes);
-      for (int g = 0; g < 2; ++g)
-        for (int c = 0; c < dchunks; ++c)
-          tma_load_3d(&maps.q, sQ + (uint32_t)g * q_tile_bytes + (uint32_t)c * ATT_BLOCK_Q * 32u, q_full,
-                      p.q_col0 + head * p.dp + c * 16, (2 * qt2 + g) * ATT_BLOCK_Q, b);
-    }
-    __syncwarp();
-    int st = 0;
-    uint32_t ph = 0;
-    for (int j = 0; j < n_tiles; ++j) {
-      mbar_wait(kv_empty(st), ph ^ 1u);
-      if (elect_one()) {
-        const uint32_t sK = sKV + (uint32_t)st * 2 * kv_tile_bytes;
-        const uint32_t sV = sK + kv_tile_bytes;
-        mbar_expect_tx(kv_full(st), 2 * kv_tile_bytes);
-        for (int c = 0; c < dchunks; ++c)
-          tma_load_3d(&maps.k, sK + (uint32_t)c * kv_chunk_bytes, kv_full(st), p.k_col0 + head * p.dp + c * 16, j * KV, b);
-        for (int c = 0; c < dchunks; ++c)
-          tma_load_3d(&maps.v, sV + (uint32_t)c * kv_chunk_bytes, kv_full(st), p.v_col0 + head * p.dp + c * 16, j * KV, b);
-      }
-      __syncwarp();
-      if (++st == NST) { st = 0; ph ^= 1u; }
-    }
-  } else if (warp == W_MMA) {
-    // ---------------- MMA issuer: QK for both query tiles per K/V stage, PV as each group's P arrives ----------------
-    const uint32_t idesc_qk = make_idesc_f16(ATT_BLOCK_Q, (uint32_t)KV, true, 0, 0);
-    const uint32_t idesc_pv = make_idesc_f16(ATT_BLOCK_Q, (uint32_t)p.dp, true, 0, 1);
-    const uint64_t desc_q0 = make_smem_desc(sQ, 16, 256, SWZ_32B);
-    const uint64_t desc_k0 = make_smem_desc(sKV, 16, 256, SWZ_32B);
-    const uint64_t desc_v0 = make_smem_desc(sKV + kv_tile_bytes, KV * 32u, 256, SWZ_32B);
-    const uint32_t stage_step = (2 * kv_tile_bytes) >> 4;
-    const uint32_t q_step = q_tile_bytes >> 4;
-    auto issue_qk = [&](int g, int jj) {          // S[g][jj & 1] = Q_g K_jj^T   (K/V stage jj % NST must be full)
-      if (elect_one()) {
-        const uint64_t dk = desc_k0 + (uint64_t)((uint32_t)(jj % NST) * stage_step);
-        const uint64_t dq = desc_q0 + (uint64_t)((uint32_t)g * q_step);
-        for (int c = 0; c < dchunks; ++c)
-          umma_f16_ss(tmem_S(g, jj & 1), dq + (uint64_t)(c * (ATT_BLOCK_Q * 32 / 16)), dk + (uint64_t)(c * (int)(kv_chunk_bytes >> 4)),
-                      idesc_qk, c != 0);
-        umma_commit(s_full(g, jj & 1));
-      }
-      __syncwarp();
-    };
-    auto wait_kv = [&](int jj) {
-      mbar_wait(kv_full(jj % NST), (uint32_t)(jj / NST) & 1u);
-      tc_fence_after();
-    };
-    mbar_wait(q_full, 0);
-    wait_kv(0);
-    issue_qk(0, 0);
-    issue_qk(1, 0);
-    if (n_tiles > 1) {
-      wait_kv(1);
-      issue_qk(0, 1);
-      issue_qk(1, 1);
-    }
-    for (int j = 0; j < n_tiles; ++j) {
-      const int bi = j & 1;
-      const int st = j % NST;
-      if (j + 2 < n_tiles) wait_kv(j + 2);
-      for (int g = 0; g < 2; ++g) {
-        mbar_wait(p_full(g, bi), (uint32_t)(j >> 1) & 1u);      // P_g[bi] written, S_g[bi] consumed
-        tc_fence_after();
-        if (elect_one()) {
-          const uint64_t dv = desc_v0 + (uint64_t)((uint32_t)st * stage_step);
-#pragma unroll
-          for (int k = 0; k < KV / 16; ++k)
-            umma_f16_ts(tmem_Og(g), tmem_S(g, bi) + (uint32_t)(8 * k), dv + (uint64_t)(k * (512 / 16)), idesc_pv, (j | k) != 0);
-          umma_commit(o_done(g, bi));
-          if (g == 1) umma_commit(kv_empty(st));                 // both groups' MMAs on this K/V stage are issued
-        }
-        __syncwarp();
-        if (j + 2 < n_tiles) issue_qk(g, j + 2);                 // overwrites S_g[bi] after PV_g(j) (in-order tensor pipe)
-      }
-    }
-  } else {
-    // ---------------- softmax warpgroups A (warps 0..3, query tile 0) and B (warps 4..7, query tile 1) ----------------
-    const int g = warp >> 2;
-    const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;
-    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    const int q_row = (2 * qt2 + g) * ATT_BLOCK_Q + row;
-    float m_ref = -INFINITY, l = 0.f;
-    // named barriers 1 + g: "group g may use the MUFU".  B hands the first turn to A.
-    const int my_turn = 1 + g, other_turn = 2 - g;
-    if (g == 1) named_bar_arrive(other_turn, 256);
-    for (int j = 0; j < n_tiles; ++j) {
-      const int bi = j & 1;
-      const uint32_t tS = tmem_S(g, bi) + lane_addr;
-      mbar_wait(s_full(g, bi), (uint32_t)(j >> 1) & 1u);
-      tc_fence_after();
-      named_bar_sync(my_turn, 256);                               // ---- my exponential turn starts ----
-      const int kv_valid = min(KV, p.Skv - j * KV);
-      uint32_t sreg[KV];
-      uint32_t pw[KV / 2];
-      bool careful = (kv_valid != KV) || (j == 0);
-      float mx = -INFINITY;
-      if (!careful) {
-        float m8[8], l8[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { m8[i] = -INFINITY; l8[i] = 0.f; }
-        tmem_ld_32x32b_x32(tS, *reinterpret_cast<uint32_t(*)[32]>(&sreg[0]));
-#pragma unroll
-        for (int c = 0; c < KV / 32; ++c) {
-          tmem_ld_wait();
-          if (c + 1 < KV / 32)
-            tmem_ld_32x32b_x32(tS + (uint32_t)((c + 1) * 32), *reinterpret_cast<uint32_t(*)[32]>(&sreg[(c + 1) * 32]));
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            float pv[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float sv = __uint_as_float(sreg[c * 32 + h * 16 + i]);
-              m8[i & 7] = fmaxf(m8[i & 7], sv);
-              pv[i] = ex2f(fmaf(sv, p.scale_log2, -m_ref));
-              l8[i & 7] += pv[i];
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) pw[(c * 2 + h) * 8 + i] = pack_bf16x2(pv[2 * i], pv[2 * i + 1]);
-          }
-        }
-        const float tsum = ((l8[0] + l8[1]) + (l8[2] + l8[3])) + ((l8[4] + l8[5]) + (l8[6] + l8[7]));
-        mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7]))) * p.scale_log2;
-        careful = __any_sync(0xffffffffu, mx > m_ref + 8.0f);
-        if (!careful) l += tsum;
-      } else {
-#pragma unroll
-        for (int c = 0; c < KV / 32; ++c)
-          tmem_ld_32x32b_x32(tS + (uint32_t)(c * 32), *reinterpret_cast<uint32_t(*)[32]>(&sreg[c * 32]));
-        tmem_ld_wait();
-        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-        for (int i = 0; i < KV; ++i)
-          if (i < kv_valid) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(sreg[i]));
-        mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * p.scale_log2;
-      }
-      if (careful) {
-        const bool need = mx > m_ref + 8.0f;
-        if (__any_sync(0xffffffffu, need)) {
-          const float m_new = need ? mx : m_ref;
-          const float alpha = ex2f(m_ref - m_new);
-          if (j > 0) {
-            mbar_wait(o_done(g, (j - 1) & 1), (uint32_t)((j - 1) >> 1) & 1u);
-            tc_fence_after();
-            for (int c = 0; c < dchunks; ++c) {
-              uint32_t r[16];
-              tmem_ld_32x32b_x16(tmem_Og(g) + lane_addr + (uint32_t)(c * 16), r);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-              tmem_st_32x32b_x16(tmem_Og(g) + lane_addr + (uint32_t)(c * 16), r);
-            }
-            tmem_st_wait();
-          }
-          l *= alpha;
-          m_ref = m_new;
-        }
-        float l4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int c = 0; c < KV / 16; ++c) {
-          float pv[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float e = ex2f(fmaf(__uint_as_float(sreg[c * 16 + i]), p.scale_log2, -m_ref));
-            pv[i] = (c * 16 + i < kv_valid) ? e : 0.f;
-            l4[i & 3] += pv[i];
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) pw[c * 8 + i] = pack_bf16x2(pv[2 * i], pv[2 * i + 1]);
-        }
-        l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
-      }
-      // ---- my turn ends: the other group computes while I store P and wait for my next S ----
-      if (!(g == 1 && j == n_tiles - 1)) named_bar_arrive(other_turn, 256);
-#pragma unroll
-      for (int c = 0; c < KV / 64; ++c)
-        tmem_st_32x32b_x32(tS + (uint32_t)(c * 32), *reinterpret_cast<uint32_t(*)[32]>(&pw[c * 32]));
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(p_full(g, bi));
-    }
-    // ---- epilogue: O / l -> bf16 ----
-    mbar_wait(o_done(g, (n_tiles - 1) & 1), (uint32_t)((n_tiles - 1) >> 1) & 1u);
-    tc_fence_after();
-    const float inv_l = 1.0f / l;
-    __nv_bfloat16* orow = p.out + (size_t)b * p.out_batch_stride + (size_t)q_row * p.out_ld + p.out_col0 + head * p.dp;
-    for (int c = 0; c < dchunks; ++c) {
-      uint32_t r[16];
-      tmem_ld_32x32b_x16(tmem_Og(g) + lane_addr + (uint32_t)(c * 16), r);
-      tmem_ld_wait();
-      if (q_row < p.Sq) {
-        uint4 a, bq;
-        a.x = pack_bf16x2(__uint_as_float(r[0]) * inv_l, __uint_as_float(r[1]) * inv_l);
-        a.y = pack_bf16x2(__uint_as_float(r[2]) * inv_l, __uint_as_float(r[3]) * inv_l);
-        a.z = pack_bf16x2(__uint_as_float(r[4]) * inv_l, __uint_as_float(r[5]) * inv_l);
-        a.w = pack_bf16x2(__uint_as_float(r[6]) * inv_l, __uint_as_float(r[7]) * inv_l);
-        bq.x = pack_bf16x2(__uint_as_float(r[8]) * inv_l, __uint_as_float(r[9]) * inv_l);
-        bq.y = pack_bf16x2(__uint_as_float(r[10]) * inv_l, __uint_as_float(r[11]) * inv_l);
-        bq.z = pack_bf16x2(__uint_as_float(r[12]) * inv_l, __uint_as_float(r[13]) * inv_l);
-        bq.w = pack_bf16x2(__uint_as_float(r[14]) * inv_l, __uint_as_float(r[15]) * inv_l);
-        *reinterpret_cast<uint4*>(orow + c * 16) = a;
-        *reinterpret_cast<uint4*>(orow + c * 16 + 8) = bq;
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == W_MMA) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, p.tmem_cols);
-  }
-}
-
-
-// =================================================================================================
-// Split-KV variant of the double-buffered kernel (block_kv == 64, dp <= 64) — an EXPERIMENT, not the default (see
-// dfb_attention below).  ncu of attn_fwd_db_kernel showed neither the MUFU (63 %) nor the issue slots (57 %)
-// saturated, which suggested latency-bound exponential chains with two softmax warps per scheduler.
-// Here EIGHT softmax warps per CTA (four per scheduler with two CTAs per SM) each own 32 of the 64 columns of
-// every score tile:  warps 0-3 (half a) columns [0,32), warps 4-7 (half b) columns [32,64) of the same 128 rows.
-// The halves are independent online-softmax streams over disjoint key subsets — own reference max, own row sum,
-// own accumulator O_a / O_b in tensor memory — so the main loop has no cross-warp communication at all; the
-// two partial results are merged once in the epilogue:
-//     O = (2^(m_a-m) O_a + 2^(m_b-m) O_b) / (2^(m_a-m) l_a + 2^(m_b-m) l_b),   m = max(m_a, m_b).
-// TMEM columns: S[0] 64 | S[1] 64 | O_a dp | O_b dp  (<= 256: two CTAs per SM).  P_x (bf16) overwrites the first
-// 16 columns of its own half of the score buffer and feeds the TS-form PV MMA.
-//   warps 0..7 softmax, warp 8 TMA producer, warp 9 MMA issuer (control warps at the highest ids).
-// =================================================================================================
-constexpr int ATT_SPLIT_THREADS = 320;
-
-__global__ void __launch_bounds__(ATT_SPLIT_THREADS, 2)
-attn_fwd_split_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnKernelParams p) {
-  constexpr int KV = 64, HK = 32;
-  constexpr int NST_MAX = 3;
-  const int NST = p.kv_stages;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int dchunks = p.dp >> 4;
-  const uint32_t q_bytes = (uint32_t)dchunks * ATT_BLOCK_Q * 32u;
-  constexpr uint32_t kv_chunk_bytes = KV * 32u;
-  const uint32_t kv_tile_bytes = (uint32_t)dchunks * kv_chunk_bytes;
-  const uint32_t sQ = smem_base;
-  const uint32_t sKV = sQ + q_bytes;                                         // stage s: K then V
-  const uint32_t sML = sKV + NST * 2 * kv_tile_bytes;                        // (m, l) of half b: [128][2] floats
-  const uint32_t bar_base = sML + ATT_BLOCK_Q * 8u;
-  const uint32_t q_full = bar_base;
-  auto s_full = [&](int i) { return bar_base + 8u + 8u * i; };
-  auto p_full = [&](int i, int h) { return bar_base + 24u + 8u * (2 * i + h); };
-  auto o_done = [&](int i) { return bar_base + 56u + 8u * i; };
-  auto kv_full = [&](int s) { return bar_base + 72u + 8u * s; };
-  auto kv_empty = [&](int s) { return bar_base + 72u + 8u * (NST_MAX + s); };
-  const uint32_t tmem_ptr_smem = bar_base + 72u + 8u * (2 * NST_MAX);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
-  const int n_tiles = p.n_kv_tiles;
-  constexpr int W_TMA = 8, W_MMA = 9;
-
-  if (warp == W_TMA && lane == 0) {
-    tma_prefetch_desc(&maps.q);
-    tma_prefetch_desc(&maps.k);
-    tma_prefetch_desc(&maps.v);
-    mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(s_full(i), 1);
-      mbar_init(p_full(i, 0), 128);
-      mbar_init(p_full(i, 1), 128);
-      mbar_init(o_done(i), 1);
-    }
-    for (int s = 0; s < NST; ++s) {
-      mbar_init(kv_full(s), 1);
-      mbar_init(kv_empty(s), 1);
-    }
-    fence_mbar_init();
-    fence_proxy_async_smem();
-  }
-  if (warp == W_MMA) tmem_alloc(tmem_ptr_smem, p.tmem_cols);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
-  const uint32_t tmem_O0 = tmem_base + 2u * KV;                              // O_a, then O_b at + dp
-
-  if (warp == W_TMA) {
-    // ---------------- TMA producer ----------------
-    if (elect_one()) {
-      mbar_expect_tx(q_full, q_bytes);
-      for (int c = 0; c < dchunks; ++c)
-        tma_load_3d(&maps.q, sQ + (uint32_t)c * ATT_BLOCK_Q * 32u, q_full, p.q_col0 + head * p.dp + c * 16,
-                    qt * ATT_BLOCK_Q, b);
-    }
-    __syncwarp();
-    int st = 0;
-    uint32_t ph = 0;
-    for (int j = 0; j < n_tiles; ++j) {
-      mbar_wait(kv_empty(st), ph ^ 1u);
-      if (elect_one()) {
-        const uint32_t sK = sKV + (uint32_t)st * 2 * kv_tile_bytes;
-        const uint32_t sV = sK + kv_tile_bytes;
-        mbar_expect_tx(kv_full(st), 2 * kv_tile_bytes);
-        for (int c = 0; c < dchunks; ++c)
-          tma_load_3d(&maps.k, sK + (uint32_t)c * kv_chunk_bytes, kv_full(st), p.k_col0 + head * p.dp + c * 16, j * KV, b);
-        for (int c = 0; c < dchunks; ++c)
-          tma_load_3d(&maps.v, sV + (uint32_t)c * kv_chunk_bytes, kv_full(st), p.v_col0 + head * p.dp + c * 16, j * KV, b);
-      }
-      __syncwarp();
-      if (++st == NST) { st = 0; ph ^= 1u; }
-    }
-  } else if (warp == W_MMA) {
-    // ---------------- MMA issuer (warp-uniform, one elected lane issues) ----------------
-    const uint32_t idesc_qk = make_idesc_f16(ATT_BLOCK_Q, (uint32_t)KV, true, 0, 0);
-    const uint32_t idesc_pv = make_idesc_f16(ATT_BLOCK_Q, (uint32_t)p.dp, true, 0, 1);
-    const uint64_t desc_q0 = make_smem_desc(sQ, 16, 256, SWZ_32B);
-    const uint64_t desc_k0 = make_smem_desc(sKV, 16, 256, SWZ_32B);
-    const uint64_t desc_v0 = make_smem_desc(sKV + kv_tile_bytes, KV * 32u, 256, SWZ_32B);
-    const uint32_t stage_step = (2 * kv_tile_bytes) >> 4;
-    auto issue_qk = [&](int jj) {                 // S[jj & 1] = Q K_jj^T
-      const int st = jj % NST;
-      mbar_wait(kv_full(st), (uint32_t)(jj / NST) & 1u);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint64_t dk = desc_k0 + (uint64_t)((uint32_t)st * stage_step);
-        const uint32_t tS = tmem_base + (uint32_t)(jj & 1) * KV;
-        for (int c = 0; c < dchunks; ++c)
-          umma_f16_ss(tS, desc_q0 + (uint64_t)(c * (ATT_BLOCK_Q * 32 / 16)), dk + (uint64_t)(c * (int)(kv_chunk_bytes >> 4)),
-                      idesc_qk, c != 0);
-        umma_commit(s_full(jj & 1));
-      }
-      __syncwarp();
-    };
-    mbar_wait(q_full, 0);
-    issue_qk(0);
-    if (n_tiles > 1) issue_qk(1);
-    for (int j = 0; j < n_tiles; ++j) {
-      const int bi = j & 1;
-      const int st = j % NST;
-      const uint64_t dv = desc_v0 + (uint64_t)((uint32_t)st * stage_step);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        mbar_wait(p_full(bi, h), (uint32_t)(j >> 1) & 1u);      // P_h of tile j written over its half of S[bi]
-        tc_fence_after();
-        if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < HK / 16; ++k)
-            umma_f16_ts(tmem_O0 + (uint32_t)(h * p.dp), tmem_base + (uint32_t)bi * KV + (uint32_t)(h * HK + 8 * k),
-                        dv + (uint64_t)((h * (HK / 16) + k) * (512 / 16)), idesc_pv, (j | k) != 0);
-          if (h == 1) {
-            umma_commit(o_done(bi));
-            umma_commit(kv_empty(st));
-          }
-        }
-        __syncwarp();
-      }
-      if (j + 2 < n_tiles) issue_qk(j + 2);
-    }
-  } else {
-    // ---------------- softmax warps: half = warp / 4 owns score columns [32 half, 32 half + 32) ----------------
-    const int half = warp >> 2;
-    const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;
-    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    const int q_row = qt * ATT_BLOCK_Q + row;
-    const uint32_t tO = tmem_O0 + (uint32_t)(half * p.dp) + lane_addr;
-    float m_ref = -INFINITY, l = 0.f;
-    for (int j = 0; j < n_tiles; ++j) {
-      const int bi = j & 1;
-      const uint32_t tS = tmem_base + (uint32_t)bi * KV + (uint32_t)(half * HK) + lane_addr;
-      mbar_wait(s_full(bi), (uint32_t)(j >> 1) & 1u);
-      tc_fence_after();
-      int kv_valid = p.Skv - j * KV - half * HK;
-      kv_valid = kv_valid < 0 ? 0 : (kv_valid > HK ? HK : kv_valid);
-      uint32_t sreg[HK];
-      uint32_t pw[HK / 2];
-      bool careful = (kv_valid != HK) || (j == 0);
-      float mx = -INFINITY;
-      tmem_ld_32x32b_x16(tS, *reinterpret_cast<uint32_t(*)[16]>(&sreg[0]));
-      if (!careful) {
-        // optimistic pass: exponentials against the running reference max while the second 16 columns load
-        float m8[8], l8[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { m8[i] = -INFINITY; l8[i] = 0.f; }
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          tmem_ld_wait();
-          if (c == 0) tmem_ld_32x32b_x16(tS + 16u, *reinterpret_cast<uint32_t(*)[16]>(&sreg[16]));
-          float pv[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float sv = __uint_as_float(sreg[c * 16 + i]);
-            m8[i & 7] = fmaxf(m8[i & 7], sv);
-            pv[i] = ex2f(fmaf(sv, p.scale_log2, -m_ref));
-            l8[i & 7] += pv[i];
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) pw[c * 8 + i] = pack_bf16x2(pv[2 * i], pv[2 * i + 1]);
-        }
-        mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7]))) * p.scale_log2;
-        careful = __any_sync(0xffffffffu, mx > m_ref + 8.0f);
-        if (!careful) l += ((l8[0] + l8[1]) + (l8[2] + l8[3])) + ((l8[4] + l8[5]) + (l8[6] + l8[7]));
-      } else {
-        tmem_ld_32x32b_x16(tS + 16u, *reinterpret_cast<uint32_t(*)[16]>(&sreg[16]));
-        tmem_ld_wait();
-        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-        for (int i = 0; i < HK; ++i)
-          if (i < kv_valid) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(sreg[i]));
-        mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * p.scale_log2;
-      }
-      if (careful) {
-        // new reference max for this half: rescale O_half (needs every earlier PV retired) and l, redo from registers
-        const bool need = mx > m_ref + 8.0f;
-        if (__any_sync(0xffffffffu, need)) {
-          const float m_new = need ? mx : m_ref;
-          const float alpha = ex2f(m_ref - m_new);     // m_ref = -inf on the first tile -> 0
-          if (j > 0) {
-            mbar_wait(o_done((j - 1) & 1), (uint32_t)((j - 1) >> 1) & 1u);
-            tc_fence_after();
-            for (int c = 0; c < dchunks; ++c) {
-              uint32_t r[16];
-              tmem_ld_32x32b_x16(tO + (uint32_t)(c * 16), r);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-              tmem_st_32x32b_x16(tO + (uint32_t)(c * 16), r);
-            }
-            tmem_st_wait();
-          }
-          l *= alpha;
-          m_ref = m_new;
-        }
-        float l4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int c = 0; c < HK / 16; ++c) {
-          float pv[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float e = ex2f(fmaf(__uint_as_float(sreg[c * 16 + i]), p.scale_log2, -m_ref));
-            pv[i] = (c * 16 + i < kv_valid) ? e : 0.f;
-            l4[i & 3] += pv[i];
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) pw[c * 8 + i] = pack_bf16x2(pv[2 * i], pv[2 * i + 1]);
-        }
-        l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
-      }
-      // P_half (bf16, two per column) over the first 16 columns of this half of the score buffer
-      tmem_st_32x32b_x16(tS, *reinterpret_cast<uint32_t(*)[16]>(&pw[0]));
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(p_full(bi, half));
-    }
-    // ---- epilogue: merge the two halves, O / l -> bf16 ----
-    mbar_wait(o_done((n_tiles - 1) & 1), (uint32_t)((n_tiles - 1) >> 1) & 1u);
-    tc_fence_after();
-    if (half == 1) {
-      asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(sML + (uint32_t)row * 8u), "f"(m_ref), "f"(l) : "memory");
-    }
-    asm volatile("bar.sync 1, 256;" ::: "memory");          // the 8 softmax warps only
-    if (half == 0) {
-      float m_b, l_b;
-      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(m_b), "=f"(l_b) : "r"(sML + (uint32_t)row * 8u));
-      const float m = fmaxf(m_ref, m_b);
-      const float wa = ex2f(m_ref - m), wb = ex2f(m_b - m);
-      const float inv = 1.0f / fmaf(wa, l, wb * l_b);
-      const float ca = wa * inv, cb = wb * inv;
-      __nv_bfloat16* orow = p.out + (size_t)b * p.out_batch_stride + (size_t)q_row * p.out_ld + p.out_col0 + head * p.dp;
-      for (int c = 0; c < dchunks; ++c) {
-        uint32_t ra[16], rb[16];
-        tmem_ld_32x32b_x16(tO + (uint32_t)(c * 16), ra);
-        tmem_ld_32x32b_x16(tO + (uint32_t)(p.dp + c * 16), rb);
-        tmem_ld_wait();
-        if (q_row < p.Sq) {
-          uint32_t w[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            w[i] = pack_bf16x2(fmaf(__uint_as_float(ra[2 * i]), ca, __uint_as_float(rb[2 * i]) * cb),
-                               fmaf(__uint_as_float(ra[2 * i + 1]), ca, __uint_as_float(rb[2 * i + 1]) * cb));
-          *reinterpret_cast<uint4*>(orow + c * 16) = make_uint4(w[0], w[1], w[2], w[3]);
-          *reinterpret_cast<uint4*>(orow + c * 16 + 8) = make_uint4(w[4], w[5], w[6], w[7]);
-        }
       }
     }
   }
@@ -1513,7 +931,32 @@ attn_short_kv_kernel(const __grid_constant__ AttnMaps maps, const __grid_constan
 
 }  // namespace dfb
 
+#include "dfb_attn_sa.cuh"
+#include "dfb_attn_sa8.cuh"
+
 using namespace dfb;
+
+// Share of the exponentials attn_fwd_sa_kernel computes on the FMA pipe (of every 16).  DFB_ATTN_POLY = 0 | 2 | 4 overrides
+// the built-in choice (measured on B200, profiles/r02_attention_sa_*.log).
+static int attn_env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+static int attn_poly_default(bool ones) {
+  static int env = -2;
+  if (env == -2) {
+    const char* e = getenv("DFB_ATTN_POLY");
+    env = e ? atoi(e) : -1;
+    if (env != -1 && env != 0 && env != 2 && env != 4) env = -1;
+  }
+  if (env >= 0) return env;
+  return ones ? DFB_ATTN_POLY_ONES_DEFAULT : DFB_ATTN_POLY_DEFAULT;
+}
+
+extern "C" size_t dfb_attention_ws_bytes(int B, int heads, int Sq) {
+  return (size_t)4 * (size_t)B * (size_t)heads * (size_t)((Sq + ATT_BLOCK_Q - 1) / ATT_BLOCK_Q);
+}
 
 extern "C" int dfb_attention(const dfb_attn_params* a, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -1548,26 +991,38 @@ extern "C" int dfb_attention(const dfb_attn_params* a, void* stream_) {
   kp.out = (__nv_bfloat16*)a->out;
   kp.out_ld = a->out_ld; kp.out_col0 = a->out_col0;
   kp.out_batch_stride = (long long)a->Sq * a->out_ld;
-  // split-KV kernel (8 softmax warps, two independent halves; dp <= 64): measured 5 % SLOWER than the 4-softmax-warp
-  // double-buffered kernel (1836 vs 1744 cycles per 128x128 tile per SM, profiles/r01_attention_experiments.md) — more
-  // warps do not help because the tile time is set by the MUFU and the TMEM read port, not by issue latency.  Kept
-  // behind dbg_flags bit5 with its parity tests as the record of that experiment.
-  const bool use_split = use_db && bkv == 64 && a->dp <= 64 && (a->dbg_flags & 16) == 0 && (a->dbg_flags & 32) != 0;
   // short-KV kernel (one key tile, K/V resident, query tiles streamed): cross-attention.  dbg_flags bit6 disables it.
   const bool use_short = !causal && !use_db && a->Skv <= bkv && 2 * (bkv + a->dp) <= 512 && a->Sq > ATT_BLOCK_Q && (a->dbg_flags & (8 | 64)) == 0;
-  // ping-pong kernel (one CTA per SM, two query tiles, two softmax warpgroups alternating on the MUFU): opt-in experiment,
-  // dbg_flags bit12; see attn_fwd_pp_kernel.
-  const bool use_pp = use_db && !use_split && bkv == 64 && a->dp <= 64 && a->Sq > ATT_BLOCK_Q && (a->dbg_flags & 16) == 0 &&
-                      (a->dbg_flags & 4096) != 0;
-  uint32_t need_cols = use_short ? (uint32_t)(2 * (bkv + a->dp))
-                       : use_pp  ? (uint32_t)(4 * bkv + 2 * a->dp)
-                                 : (uint32_t)((use_db ? 2 : 1) * bkv + (use_split ? 2 : 1) * a->dp), cols = 32;
+  // attn_fwd_sa_kernel (dfb_attn_sa.cuh): the double-buffered kernel with P in tensor memory, reworked for the long
+  // self-attention layers — softmax denominator from the P V MMA (ones column of V, `ones_col`), part of the exponentials
+  // on the FMA pipe, TMEM loads prefetched across tiles.  dbg_flags bit12 keeps the round-1 kernel (A/B runs);
+  // bits 13-14 choose the polynomial share: 1 -> none, 2 -> 2 of 16, 3 -> 4 of 16, 0 -> default (DFB_ATTN_POLY or built-in).
+  const bool use_sa = use_db && bkv == 64 && (a->dbg_flags & (16 | 4096)) == 0;
+  const bool sa_ones = use_sa && a->ones_col > 0;
+  DFB_REQUIRE(a->ones_col >= 0 && a->ones_col <= a->dp, "dfb_attention: ones_col must be 0 (none) or 1 + a column of the padded head");
+  int sa_poly = 0;
+  if (use_sa) {
+    const int sel = (a->dbg_flags >> 13) & 3;
+    sa_poly = sel == 1 ? 0 : sel == 2 ? 2 : sel == 3 ? 4 : attn_poly_default(sa_ones);
+  }
+  kp.l_col = sa_ones ? a->ones_col - 1 : 0;
+  // attn_fwd_sa8_kernel (dfb_attn_sa8.cuh): eight softmax warps per CTA, static reference maximum, overflow flagged into the
+  // caller's workspace and redone by attn_fwd_sa_kernel<.., REDO>.  Needs the ones column, room for three score buffers
+  // (dp <= 64) and the workspace; dbg_flags bit15 / DFB_ATTN_SA8=0 keep the 4-warp kernel.
+  const bool use_sa8 = sa_ones && 3 * bkv + a->dp <= 256 && a->workspace != nullptr && (a->dbg_flags & 32768) == 0 &&
+                       attn_env_int("DFB_ATTN_SA8", 1) != 0;
+  kp.redo_flags = (int*)a->workspace;
+  // three score buffers where they still leave room for two CTAs per SM (3 * 64 + dp <= 256 columns: dp <= 64)
+  kp.s_ring = (use_sa && 3 * bkv + a->dp <= 256 && (use_sa8 || attn_env_int("DFB_ATTN_S_RING", 3) >= 3)) ? 3 : 2;
+  uint32_t need_cols = use_short ? (uint32_t)(2 * (bkv + a->dp)) : use_sa ? (uint32_t)(kp.s_ring * bkv + a->dp)
+                                                                         : (uint32_t)((use_db ? 2 : 1) * bkv + a->dp), cols = 32;
   while (cols < need_cols) cols <<= 1;
   DFB_REQUIRE(cols <= 512, "dfb_attention: block_kv + dp exceeds TMEM");
   kp.tmem_cols = cols;
   kp.v_lbo = a->dbg_v_lbo > 0 ? (uint32_t)a->dbg_v_lbo : (uint32_t)bkv * 32u;
   kp.v_sbo = a->dbg_v_sbo > 0 ? (uint32_t)a->dbg_v_sbo : 256u;
   kp.timeline = (long long*)a->dbg_timeline;
+  kp.tl_second = num_sms();
   kp.causal = causal ? 1 : 0;
 
   AttnMaps maps;
@@ -1599,19 +1054,21 @@ extern "C" int dfb_attention(const dfb_attn_params* a, void* stream_) {
   size_t smem;
   if (use_db) {
     // 3 K/V stages when two CTAs still fit per SM with them, else 2
-    const size_t fixed = 1024 + (size_t)dch * ATT_BLOCK_Q * 32 + (p_tmem ? 0 : 2 * (size_t)(bkv / 16) * ATT_BLOCK_Q * 32) + 256 +
-                         (use_split ? (size_t)ATT_BLOCK_Q * 8 : 0);
+    const size_t fixed = 1024 + (size_t)dch * ATT_BLOCK_Q * 32 + (p_tmem ? 0 : 2 * (size_t)(bkv / 16) * ATT_BLOCK_Q * 32) + 256;
     const size_t stage = (size_t)2 * dch * bkv * 32;
     kp.kv_stages = (fixed + 3 * stage + 1024 <= (size_t)113 * 1024 || fixed + 2 * stage + 1024 > (size_t)113 * 1024) ? 3 : 2;
-    smem = fixed + (size_t)kp.kv_stages * stage;
+    if (use_sa) {
+      // deeper ring: the TMA of tile j + NST - 1 is issued when PV_{j-1} retires, i.e. NST - 2 tile periods before QK needs it
+      int want = attn_env_int("DFB_ATTN_KV_STAGES", 6);
+      if (want > 8) want = 8;
+      while (want > kp.kv_stages && fixed + (size_t)want * stage + 1024 > (size_t)113 * 1024) --want;
+      if (want > kp.kv_stages) kp.kv_stages = want;
+    }
+    smem = fixed + (size_t)kp.kv_stages * stage + (use_sa8 ? 1536 : 0);
   } else {
     smem = 1024 + (size_t)dch * ATT_BLOCK_Q * 32 + (size_t)(bkv / 16) * ATT_BLOCK_Q * 32 + (size_t)ATT_STAGES * 2 * dch * bkv * 32 + 128;
   }
   const int n_qtiles = (a->Sq + ATT_BLOCK_Q - 1) / ATT_BLOCK_Q;
-  if (use_pp) {
-    kp.kv_stages = 4;       // >= 3 required: QK(j + 2) is issued before the stage of tile j is released
-    smem = 1024 + 2 * (size_t)dch * ATT_BLOCK_Q * 32 + (size_t)kp.kv_stages * 2 * dch * bkv * 32 + 256;
-  }
   if (use_short) {
     smem = 1024 + 2 * (size_t)dch * ATT_BLOCK_Q * 32 + (size_t)2 * dch * bkv * 32 + 256;
     // query tiles per CTA: amortise the per-CTA set-up, but keep >= ~4 CTAs per SM slot for load balance
@@ -1633,24 +1090,32 @@ extern "C" int dfb_attention(const dfb_attn_params* a, void* stream_) {
     DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_db_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_db_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_db_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_db_kernel<64, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_db_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_short_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_sa_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_sa_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_sa_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_sa_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_sa_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_sa_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_sa_kernel<true, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_sa8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     attr_set[dev] = true;
   }
   dim3 grid((a->Sq + ATT_BLOCK_Q - 1) / ATT_BLOCK_Q, a->heads, a->B);
   if (use_short) {
     dim3 gshort((n_qtiles + kp.q_tiles - 1) / kp.q_tiles, a->heads, a->B);
     attn_short_kv_kernel<<<gshort, ATT_THREADS, smem, stream>>>(maps, kp);
-  } else if (use_pp) {
-    dim3 gpp((n_qtiles + 1) / 2, a->heads, a->B);
-    attn_fwd_pp_kernel<<<gpp, ATT_PP_THREADS, smem, stream>>>(maps, kp);
-  } else if (use_split)
-    attn_fwd_split_kernel<<<grid, ATT_SPLIT_THREADS, smem, stream>>>(maps, kp);
-  else if (use_db && bkv == 64 && p_tmem && (a->dbg_flags & 128))
-    attn_fwd_db_kernel<64, true, true><<<grid, ATT_THREADS, smem, stream>>>(maps, kp);
+  } else if (use_sa8) {
+    attn_fwd_sa8_kernel<<<grid, ATT_SA8_THREADS, smem, stream>>>(maps, kp);
+    DFB_CHECK_CUDA(cudaGetLastError());
+    attn_fwd_sa_kernel<true, 0, true><<<grid, ATT_THREADS, smem, stream>>>(maps, kp);     // flagged tiles only (normally none)
+  } else if (use_sa) {
+#define DFB_SA_LAUNCH(O_, P_) attn_fwd_sa_kernel<O_, P_><<<grid, ATT_THREADS, smem, stream>>>(maps, kp)
+    if (sa_ones) { if (sa_poly == 4) DFB_SA_LAUNCH(true, 4); else if (sa_poly == 2) DFB_SA_LAUNCH(true, 2); else DFB_SA_LAUNCH(true, 0); }
+    else { if (sa_poly == 4) DFB_SA_LAUNCH(false, 4); else if (sa_poly == 2) DFB_SA_LAUNCH(false, 2); else DFB_SA_LAUNCH(false, 0); }
+#undef DFB_SA_LAUNCH
+  }
   else if (use_db && bkv == 64 && p_tmem)
     attn_fwd_db_kernel<64, true><<<grid, ATT_THREADS, smem, stream>>>(maps, kp);
   else if (use_db && bkv == 64)

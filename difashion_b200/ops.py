@@ -251,10 +251,13 @@ def pad16(d: int) -> int:
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, heads: int, dp: int,
               scale: float, q_col0: int = 0, k_col0: int = 0, v_col0: int = 0, out_col0: int = 0,
               block_kv: int = 0, dbg_v_lbo: int = 0, dbg_v_sbo: int = 0, dbg_flags: int = 0, dbg_timeline: Optional[torch.Tensor] = None,
-              causal: bool = False) -> torch.Tensor:
+              causal: bool = False, ones_col: Optional[int] = None, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
     """softmax(Q K^T * scale) V per (batch, head); q/k/v/out are bf16 ``[B, S, ld]`` views whose head
     ``h`` lives in columns ``[col0 + h*dp, col0 + (h+1)*dp)`` (``dp`` = head dim padded to 16).  ``causal``: key j is
-    visible to query i only when j <= i (CLIP text encoder)."""
+    visible to query i only when j <= i (CLIP text encoder).  ``ones_col`` = c: the caller promises that column c of every
+    padded head of ``v`` holds 1.0 (``AttnPack.b_qkv`` writes it through the projection's bias), so the long-sequence kernel
+    takes the softmax denominator from the P V product (see ``dfb_attn_params.ones_col``).  ``workspace``: caller-owned
+    int32 scratch of ``attention_ws_elems(B, heads, Sq)`` elements (``dfb_attn_params.workspace``: the 8-softmax-warp kernel)."""
     from ._lib import AttnParams
     p = AttnParams()
     for t in (q, k, v, out):
@@ -270,6 +273,11 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
     p.dbg_flags = dbg_flags
     p.dbg_timeline = _ptr(dbg_timeline)
     p.causal = 1 if causal else 0
+    p.ones_col = 0 if ones_col is None else int(ones_col) + 1
+    if workspace is not None:
+        assert workspace.dtype == torch.int32 and workspace.is_cuda and workspace.is_contiguous()
+        assert workspace.numel() >= attention_ws_elems(q.shape[0], heads, q.shape[1])
+        p.workspace = workspace.data_ptr()
     e0 = _prof_begin()
     if q.dtype == torch.float32:
         check(_lib.load().dfb_attention_f32(C.byref(p), _stream()), "dfb_attention_f32")
@@ -279,6 +287,11 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
         _prof_end(e0, "attention", 4.0 * q.shape[0] * heads * q.shape[1] * k.shape[1] * dp, (q.shape[0], heads, q.shape[1], k.shape[1], dp))
     _count(1)
     return out
+
+
+def attention_ws_elems(b: int, heads: int, sq: int) -> int:
+    """int32 elements of the scratch ``attention(workspace=...)`` takes (one flag per 128-query tile of every (batch, head))."""
+    return b * heads * ((sq + 127) // 128)
 
 
 # ----------------------------------------------------------------------------------------------

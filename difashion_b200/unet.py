@@ -518,11 +518,12 @@ class B200UNet2DConditionModel(nn.Module):
         self._tap(name + ".ln1", ln[:Mp])
         if fast:
             qkv = ws.get("qkv", (B, S, 3 * a1.cp), self._op_dtype)
-            ops.gemm([ln[:Mp]], a1.w_qkv, 3 * a1.cp, out=qkv.view(M, 3 * a1.cp)[:Mp])
+            ops.gemm([ln[:Mp]], a1.w_qkv, 3 * a1.cp, out=qkv.view(M, 3 * a1.cp)[:Mp], bias=a1.b_qkv)
             self._tap(name + ".qkv", qkv[:Bp])
             att = ws.get("att", (B, S, a1.cp), self._op_dtype)
             ops.attention(qkv[:Bp, :, :a1.cp], qkv[:Bp, :, a1.cp:2 * a1.cp], qkv[:Bp, :, 2 * a1.cp:], att[:Bp], heads=a1.heads,
-                          dp=a1.dp, scale=a1.scale)
+                          dp=a1.dp, scale=a1.scale, ones_col=a1.ones_col,
+                          workspace=ws.get("att_flags", (ops.attention_ws_elems(B, a1.heads, S),), torch.int32))
             self._tap(name + ".att1", att[:Bp])
             ops.gemm([att.view(M, a1.cp)[:Mp]], a1.w_o, C, out=h[:Mp], bias=a1.b_o, residual=h[:Mp])
         else:

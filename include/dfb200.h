@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define DFB200_ABI_VERSION 5
+#define DFB200_ABI_VERSION 6
 
 #define DFB_OK 0
 #define DFB_ERR_INVALID (-1)
@@ -135,11 +135,22 @@ typedef struct dfb_attn_params {
   float scale;            /* softmax scale (true head_dim ** -0.5)                          */
   int32_t block_kv;       /* KV tile (multiple of 16, <= 128); 0 = automatic                */
   int32_t dbg_v_lbo, dbg_v_sbo; /* 0 = default; test hooks for the V descriptor strides     */
-  int32_t dbg_flags;      /* 0 = default; tuning hooks: bit1 one CTA per SM, bit3 single-buffer kernel, bit4 P via smem, bit5 split-KV kernel, bit6 no short-KV kernel, bit7 "no max" fast path (experiment), bits 8-11 query tiles per CTA of the short-KV kernel */
+  int32_t dbg_flags;      /* 0 = default; tuning hooks: bit1 one CTA per SM, bit3 single-buffer kernel, bit4 P via smem, bit6 no short-KV kernel, bits 8-11 query tiles per CTA of the short-KV kernel, bit12 round-1 double-buffered kernel instead of attn_fwd_sa_kernel, bits 13-14 share of the exponentials on the FMA pipe (1 none, 2 = 2/16, 3 = 4/16), bit15 no 8-softmax-warp kernel */
   void* dbg_timeline;     /* NULL, or device buffer of >= 4096 int64: clock64 stamps of CTA (0,0,0) (tuning)  */
   int32_t causal;         /* 1: key j is visible to query i only when j <= i (CLIPTextModel's causal mask,
                              DiFashion/models/difashion.py:339-353); 0 everywhere in the UNet              */
+  int32_t ones_col;       /* 0: none.  c + 1: the caller promises V[:, head*dp + c] == 1.0 for every key row and head (a padding
+                             column of the padded head, written by the q|k|v projection's bias): the long-sequence
+                             self-attention kernel then takes the softmax denominator from O[:, c] — accumulated by the P V
+                             MMA from the same bf16 probabilities as the numerator — and out[:, head*dp + c] comes back as 1.
+                             Kernels that keep their own running sum ignore it.                                  */
+  void* workspace;        /* NULL, or caller-owned device scratch of >= dfb_attention_ws_bytes(B, heads, Sq) bytes (no
+                             initialisation needed): lets the self-attention path with ones_col use the 8-softmax-warp kernel,
+                             which flags tiles whose scores overflow its static reference maximum there; a second launch on
+                             the same stream recomputes flagged tiles exactly.                                     */
 } dfb_attn_params;
+
+size_t dfb_attention_ws_bytes(int B, int heads, int Sq);
 
 int dfb_attention(const dfb_attn_params* p, void* stream);
 /* fp32 verification path: q/k/v/out fp32, same layout conventions (dp <= 160), expf softmax on the CUDA cores. */

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_library_loads_and_exports_every_declared_symbol():
     from difashion_b200 import _lib
     lib = _lib.load()
-    assert lib.dfb_abi_version() == 5
+    assert lib.dfb_abi_version() == 6
     header = open(os.path.join(ROOT, "include", "dfb200.h")).read()
     declared = set(re.findall(r"\b(dfb_[a-z0-9_]+)\s*\(", header))
     assert declared, "no declarations parsed"
