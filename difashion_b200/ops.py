@@ -285,7 +285,10 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
         check(_lib.load().dfb_attention(C.byref(p), _stream()), "dfb_attention")
     if e0 is not None:
         _prof_end(e0, "attention", 4.0 * q.shape[0] * heads * q.shape[1] * k.shape[1] * dp, (q.shape[0], heads, q.shape[1], k.shape[1], dp))
-    _count(1)
+    # the 8-softmax-warp self-attention path is two launches (kernel + the redo pass over flagged tiles); same condition as the host side
+    two = (workspace is not None and ones_col is not None and q.dtype == torch.bfloat16 and k.shape[1] > 128 and 192 + dp <= 256
+           and not causal and (dbg_flags & (8 | 16 | 4096 | 32768)) == 0 and block_kv in (0, 64))
+    _count(2 if two else 1)
     return out
 
 

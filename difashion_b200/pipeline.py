@@ -415,8 +415,10 @@ def gather_item_rows(local: Optional[torch.Tensor], counts: Sequence[int], row_s
     gathered = torch.empty(world * pad, *row_shape, dtype=torch.float32, device=device)
     if dist.get_backend(group) == "nccl":
         dist.all_gather_into_tensor(gathered, buf, group=group)
-    else:                                   # gloo (CPU tests)
-        dist.all_gather(list(gathered.view(world, pad, *row_shape).unbind(0)), buf, group=group)
+    else:                                   # gloo (CPU tests; GPU tests with both ranks on one device): staged through the host
+        host = [torch.empty(pad, *row_shape, dtype=torch.float32) for _ in range(world)]
+        dist.all_gather(host, buf.cpu(), group=group)
+        gathered.copy_(torch.cat(host, 0))
     if all(c == pad for c in counts):
         return gathered
     return torch.cat([gathered[r * pad:r * pad + c] for r, c in enumerate(counts)], 0)

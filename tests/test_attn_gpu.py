@@ -167,7 +167,8 @@ def test_self_attention_kernel_ones_column_and_polynomial_exponentials(B, H, S, 
     # no further from fp64 than it
     e = {n: rel_l2(g, ref) for n, g in outs.items()}
     assert e["sa+ones"] < 1.5 * e["sa"] + 1e-4 and e["sa+ones+poly4"] < 1.5 * e["sa"] + 1e-4 and e["sa8"] < 1.5 * e["sa"] + 1e-4, e
-    assert int(wsp.min()) >= 0 and int(wsp.max()) <= 1          # every tile wrote its flag; (k_ramp cases may overflow -> redo)
+    if (skv or S) > 128:        # (up to 128 keys are one tile of the single-buffer kernel: the 8-warp kernel is not involved)
+        assert int(wsp.min()) >= 0 and int(wsp.max()) <= 1          # every tile wrote its flag; (k_ramp cases may overflow -> redo)
 
 
 def test_eight_warp_kernel_flags_overflow_and_the_redo_pass_fixes_it():

@@ -318,3 +318,53 @@ def test_postprocess_uint8_rounding():
     u = postprocess_uint8(x)
     assert u.shape == (1, 1, 7, 3) and u.dtype.name == "uint8"
     assert u[0, 0, :, 0].tolist() == [0, 0, 0, 128, 128, 255, 255]          # 0.5/255 -> 0 and 127.5 -> 128: half to even
+
+
+# ------------------------------------------------------------------------------------------ oracle pinning kit
+def _golden(name):
+    import os
+    p = os.path.join(os.path.dirname(__file__), "golden", name)
+    if not os.path.exists(p):
+        pytest.skip(f"{name} not present: run tools/dump_diffusers_golden.py where diffusers==0.18.2 is installed "
+                    "(the oracle is 'parity unpinned' until then, DESIGN.md §2)")
+    return torch.load(p)
+
+
+def test_oracle_matches_diffusers_golden_vectors():
+    """Consumes tests/golden/diffusers_{unet,schedulers,vae}.pt (written by tools/dump_diffusers_golden.py from the REAL
+    diffusers 0.18.2 classes): the oracle restatements must reproduce them at 1e-5.  Skips while the files are absent."""
+    from oracle.schedulers_oracle import OracleDDIMScheduler, OraclePNDMScheduler
+    from oracle.unet_oracle import OracleUNet2DConditionModel, UNetConfig
+    from oracle.vae_oracle import OracleVAE, VAEConfig
+    from tests.util import rel_l2
+    g = _golden("diffusers_unet.pt")
+    for name, case in g["cases"].items():
+        c = case["config"]
+        cfg = UNetConfig(sample_size=c["sample_size"], in_channels=c["in_channels"], out_channels=c["out_channels"],
+                         block_out_channels=tuple(c["block_out_channels"]), cross_attention_dim=c["cross_attention_dim"],
+                         attention_head_dim=tuple(c["attention_head_dim"]) if isinstance(c["attention_head_dim"], list) else c["attention_head_dim"],
+                         use_linear_projection=c["use_linear_projection"])
+        m = OracleUNet2DConditionModel(cfg).eval()
+        m.load_state_dict(case["state_dict"], strict=True)                     # same key names, same shapes
+        with torch.no_grad():
+            assert rel_l2(m(case["x"], torch.tensor(case["t"]), case["ctx"]), case["y"]) < 1e-5, name
+            assert rel_l2(m(case["x"], torch.tensor(case["t_vec"]), case["ctx"]), case["y_vec_t"]) < 1e-5, name
+    s = _golden("diffusers_schedulers.pt")
+    for key, cls in (("ddim", OracleDDIMScheduler), ("pndm", OraclePNDMScheduler)):
+        for n in (6, 50):
+            ref = s[f"{key}_{n}"]
+            sch = cls()
+            sch.set_timesteps(n)
+            assert torch.equal(torch.as_tensor(sch.timesteps), ref["timesteps"]) and float(sch.init_noise_sigma) == ref["init_noise_sigma"]
+            x = s["x0"].clone()
+            for i, t in enumerate(sch.timesteps):
+                x = sch.step(s["eps"][i], t, x)[0]
+                assert rel_l2(x, ref["traj"][i]) < 1e-5, (key, n, i)
+    v = _golden("diffusers_vae.pt")
+    c = v["config"]
+    vae = OracleVAE(VAEConfig(block_out_channels=tuple(c["block_out_channels"]), layers_per_block=c["layers_per_block"],
+                              norm_num_groups=c["norm_num_groups"], scaling_factor=c["scaling_factor"], sample_size=c["sample_size"]),
+                    with_encoder=True).eval()
+    vae.load_state_dict(v["state_dict"], strict=True)
+    assert rel_l2(vae.encode_moments(v["img"])[0], v["mode"]) < 1e-5
+    assert rel_l2(vae.decode(v["z"]), v["dec"]) < 1e-5

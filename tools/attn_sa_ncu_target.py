@@ -9,6 +9,7 @@ qkv = torch.randn(B, 4096, 3 * 384, generator=g).bfloat16().cuda()
 qkv.view(B, 4096, 3, 8, 48)[..., 40:] = 0
 qkv.view(B, 4096, 3, 8, 48)[:, :, 2, :, 40] = 1.0
 o = torch.empty(B, 4096, 384, dtype=torch.bfloat16, device="cuda")
-for flags, ones in ((1 << 13, 40), (1 << 13, 40), (3 << 13, 40)):
-    ops.attention(qkv[..., :384], qkv[..., 384:768], qkv[..., 768:], o, heads=8, dp=48, scale=40 ** -0.5, dbg_flags=flags, ones_col=ones)
+wsp = torch.empty(ops.attention_ws_elems(B, 8, 4096), dtype=torch.int32, device="cuda")
+for flags, ones, w in ((1 << 13, 40, None), (1 << 13, 40, None), (0, 40, wsp)):
+    ops.attention(qkv[..., :384], qkv[..., 384:768], qkv[..., 768:], o, heads=8, dp=48, scale=40 ** -0.5, dbg_flags=flags, ones_col=ones, workspace=w)
 torch.cuda.synchronize()
