@@ -29,6 +29,9 @@ constexpr int ATT_BLOCK_Q = 128;
 #ifndef DFB_ATTN_POLY_DEFAULT
 #define DFB_ATTN_POLY_DEFAULT 0
 #endif
+#ifndef DFB_ATTN_SA8_POLY_DEFAULT
+#define DFB_ATTN_SA8_POLY_DEFAULT 2      // measured on B200: 2.903 (none) / 2.864 (2 of 16) / 3.017 (4) / 3.463 ms (8) at B = 64, S = 4096, d = 40
+#endif
 constexpr int ATT_THREADS = 192;
 constexpr int ATT_STAGES = 2;
 
@@ -997,7 +1000,8 @@ extern "C" int dfb_attention(const dfb_attn_params* a, void* stream_) {
   // self-attention layers — softmax denominator from the P V MMA (ones column of V, `ones_col`), part of the exponentials
   // on the FMA pipe, TMEM loads prefetched across tiles.  dbg_flags bit12 keeps the round-1 kernel (A/B runs);
   // bits 13-14 choose the polynomial share: 1 -> none, 2 -> 2 of 16, 3 -> 4 of 16, 0 -> default (DFB_ATTN_POLY or built-in).
-  const bool use_sa = use_db && bkv == 64 && (a->dbg_flags & (16 | 4096)) == 0;
+  // (DFB_ATTN_R01=1: round 1's double-buffered kernel everywhere — the A/B partner in profiles/r02_attention_step_ab.json)
+  const bool use_sa = use_db && bkv == 64 && (a->dbg_flags & (16 | 4096)) == 0 && attn_env_int("DFB_ATTN_R01", 0) == 0;
   const bool sa_ones = use_sa && a->ones_col > 0;
   DFB_REQUIRE(a->ones_col >= 0 && a->ones_col <= a->dp, "dfb_attention: ones_col must be 0 (none) or 1 + a column of the padded head");
   int sa_poly = 0;
@@ -1099,7 +1103,10 @@ extern "C" int dfb_attention(const dfb_attn_params* a, void* stream_) {
     DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_sa_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_sa_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_sa_kernel<true, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_sa8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_sa8_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_sa8_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_sa8_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_sa8_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     attr_set[dev] = true;
   }
   dim3 grid((a->Sq + ATT_BLOCK_Q - 1) / ATT_BLOCK_Q, a->heads, a->B);
@@ -1107,7 +1114,14 @@ extern "C" int dfb_attention(const dfb_attn_params* a, void* stream_) {
     dim3 gshort((n_qtiles + kp.q_tiles - 1) / kp.q_tiles, a->heads, a->B);
     attn_short_kv_kernel<<<gshort, ATT_THREADS, smem, stream>>>(maps, kp);
   } else if (use_sa8) {
-    attn_fwd_sa8_kernel<<<grid, ATT_SA8_THREADS, smem, stream>>>(maps, kp);
+    // share of the exponentials on the FMA pipe: dbg_flags bits 13-14 (1 none, 2 = 2/16, 3 = 4/16), DFB_ATTN_SA8_POLY = 0|2|4|8, or built-in
+    int poly8 = attn_env_int("DFB_ATTN_SA8_POLY", DFB_ATTN_SA8_POLY_DEFAULT);
+    const int sel8 = (a->dbg_flags >> 13) & 3;
+    if (sel8) poly8 = sel8 == 1 ? 0 : sel8 == 2 ? 2 : 4;
+    if (poly8 == 8) attn_fwd_sa8_kernel<8><<<grid, ATT_SA8_THREADS, smem, stream>>>(maps, kp);
+    else if (poly8 == 4) attn_fwd_sa8_kernel<4><<<grid, ATT_SA8_THREADS, smem, stream>>>(maps, kp);
+    else if (poly8 == 2) attn_fwd_sa8_kernel<2><<<grid, ATT_SA8_THREADS, smem, stream>>>(maps, kp);
+    else attn_fwd_sa8_kernel<0><<<grid, ATT_SA8_THREADS, smem, stream>>>(maps, kp);
     DFB_CHECK_CUDA(cudaGetLastError());
     attn_fwd_sa_kernel<true, 0, true><<<grid, ATT_THREADS, smem, stream>>>(maps, kp);     // flagged tiles only (normally none)
   } else if (use_sa) {

@@ -29,6 +29,10 @@ namespace dfb {
 
 constexpr int ATT_SA8_THREADS = 320;      // 8 softmax warps + TMA producer + MMA issuer
 
+// POLY: of every 16 exponentials of the full-tile path, POLY are computed on the FMA pipe (ex2_poly3, dfb_attn_sa.cuh).  With four
+// softmax warps per scheduler the loop is MUFU-queue-bound (ncu: mio_throttle is its top stall), which is the regime where
+// moving work to the idle FMA pipe can pay (it did not with one or two warps per scheduler).
+template <int POLY>
 __global__ void __launch_bounds__(ATT_SA8_THREADS, 2)
 attn_fwd_sa8_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnKernelParams p) {
   constexpr int KV = ATT_SA_KV;
@@ -197,7 +201,9 @@ attn_fwd_sa8_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
           for (int i = 0; i < 16; ++i) {
             const float sv = __uint_as_float(sreg[h * 16 + i]);
             m4[i & 3] = fmaxf(m4[i & 3], sv);
-            pv[i] = ex2f(fmaf(sv, p.scale_log2, -m_ref));
+            const float x = fmaf(sv, p.scale_log2, -m_ref);
+            const bool on_fma = POLY > 0 && ((i + 1) % (16 / (POLY > 0 ? POLY : 1))) == 0;
+            pv[i] = on_fma ? ex2_poly3(x) : ex2f(x);
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i) pw[h * 8 + i] = pack_bf16x2(pv[2 * i], pv[2 * i + 1]);

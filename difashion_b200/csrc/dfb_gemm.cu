@@ -447,12 +447,34 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
               gs0 += __shfl_xor_sync(0xffffffffu, gs0, o); gq0 += __shfl_xor_sync(0xffffffffu, gq0, o);
               gs1 += __shfl_xor_sync(0xffffffffu, gs1, o); gq1 += __shfl_xor_sync(0xffffffffu, gq1, o);
             }
-            if (lane < 8 && lane_ok && row0 < p.M)
-              *reinterpret_cast<float4*>(p.gn_partial + ((size_t)(row0 >> 5) * (size_t)(p.N >> 1) + (size_t)(col >> 1)) * 2) =
-                  make_float4(gs0, gq0, gs1, gq1);
+            if (lane < 8 && lane_ok && row0 < p.M) {
+              size_t blk = (size_t)(row0 >> 5);
+              if constexpr (MODE == EPI_OUT_F32) {
+                if (p.up_w > 0)      // upsample phase: this phase's blocks of image `img` sit at [img * 4 * up_blk + phase * up_blk, ...)
+                  blk = (blk / (size_t)p.up_blk) * (size_t)(4 * p.up_blk) + (size_t)((2 * p.up_a + p.up_b) * p.up_blk) + blk % (size_t)p.up_blk;
+              }
+              *reinterpret_cast<float4*>(p.gn_partial + (blk * (size_t)(p.N >> 1) + (size_t)(col >> 1)) * 2) = make_float4(gs0, gq0, gs1, gq1);
+            }
           }
           const int mrow = row0 + rsub;
           if constexpr ((MODE & EPI_OUT_F32) != 0) {
+            if constexpr (MODE == EPI_OUT_F32) {
+              if (p.up_w > 0) {
+                // fused upsample phase (a, b): row (img * H + i) * W + j of the low-resolution grid -> pixel (2i + a, 2j + b) of
+                // the [B, 2H, 2W, N] output (W is a power of two: conv tiles need 128 % W == 0)
+                const int sh = 31 - __clz(p.up_w);
+#pragma unroll
+                for (int itr = 0; itr < 8; ++itr) {
+                  const int m = mrow + itr * 4;
+                  if (lane_ok && (full_rows || m < p.M)) {
+                    const size_t orow = ((size_t)(2 * (m >> sh) + p.up_a) << (sh + 1)) + (size_t)(2 * (m & (p.up_w - 1)) + p.up_b);
+                    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + orow * p.out_ld + col) = x[itr];
+                  }
+                }
+                __syncwarp();
+                continue;
+              }
+            }
             float* op = reinterpret_cast<float*>(p.out) + (size_t)mrow * p.out_ld + col;
             const size_t ostep = (size_t)4 * p.out_ld;
             if (full_rows) {
@@ -900,7 +922,9 @@ extern "C" int dfb_gemm(const dfb_gemm_params* q, void* stream_) {
 
   // epilogue specialisation
   int mode = EPI_GENERIC;
-  const bool simple = kp.vec_ok && (q->N % 4) == 0 && kp.act == 0 && q->up2x == 0 && (q->residual == nullptr || kp.res_fp32) &&
+  // (an upsample phase takes the specialised path in its one shape: fp32 output, bias only, optional GroupNorm partials)
+  const bool up_ok = q->up2x == 0 || (kp.out_fp32 && q->residual == nullptr && q->rowbias == nullptr && !kp.geglu && (q->W & (q->W - 1)) == 0);
+  const bool simple = kp.vec_ok && (q->N % 4) == 0 && kp.act == 0 && up_ok && (q->residual == nullptr || kp.res_fp32) &&
                       (q->bias == nullptr || (reinterpret_cast<uintptr_t>(q->bias) & 15) == 0) &&
                       (q->rowbias == nullptr || (kp.rows_per_batch % 32 == 0 && (q->rowbias_ld % 4) == 0 &&
                                                  (reinterpret_cast<uintptr_t>(q->rowbias) & 15) == 0));

@@ -151,7 +151,8 @@ def test_self_attention_kernel_ones_column_and_polynomial_exponentials(B, H, S, 
     wsp = torch.full((ops.attention_ws_elems(B, H, S),), -7, dtype=torch.int32, device="cuda")
     for name, flags, ones, w in (("db", 4096, None, None), ("sa", 1 << 13, None, None), ("sa+ones", 1 << 13, d, None),
                                  ("sa+ones+poly2", 2 << 13, d, None), ("sa+ones+poly4", 3 << 13, d, None), ("sa+poly4", 3 << 13, None, None),
-                                 ("sa8", 0, d, wsp), ("default", 0, d, None)):
+                                 ("sa8", 1 << 13, d, wsp), ("sa8+poly2", 2 << 13, d, wsp), ("sa8+poly4", 3 << 13, d, wsp), ("sa8 default", 0, d, wsp),
+                                 ("default", 0, d, None)):
         out = torch.full((B, S, H * dp), float("nan"), dtype=torch.bfloat16, device="cuda")
         ops.attention(qp, kp, vp, out, heads=H, dp=dp, scale=d ** -0.5, dbg_flags=flags, ones_col=ones, workspace=w)
         torch.cuda.synchronize()

@@ -48,7 +48,9 @@ def run(flags, ones, w=None, reps=5):
 
 
 variants = [("round-1 double-buffered (dbg bit12)", 4096, None, None), ("sa", 1 << 13, None, None), ("sa + ones", 1 << 13, 40, None),
-            ("sa8 (8 softmax warps) + redo launch", 0, 40, wsp)]
+            ("sa8 (8 softmax warps) + redo launch", 1 << 13, 40, wsp), ("sa8 + poly 2/16", 2 << 13, 40, wsp), ("sa8 + poly 4/16", 3 << 13, 40, wsp)]
+os.environ["DFB_ATTN_SA8_POLY"] = "8"
+variants.append(("sa8 + poly 8/16", 0, 40, wsp))
 for rnd in range(3):
     for name, flags, ones, w in variants:
         ms = run(flags, ones, w)

@@ -38,7 +38,9 @@ def run():
 
 
 def family(name: str) -> str:
-    for key, fam in (("gemm_tcgen05", "gemm_tcgen05_kernel"), ("attn_fwd_db", "attn_fwd_db_kernel"), ("attn_fwd", "attn_fwd_kernel"),
+    for key, fam in (("gemm_tcgen05", "gemm_tcgen05_kernel"), ("attn_fwd_sa8", "attn_fwd_sa8_kernel (S=4096 self-attention)"),
+                     ("attn_fwd_sa", "attn_fwd_sa_kernel (other self-attention + redo pass)"), ("attn_short_kv", "attn_short_kv_kernel (cross-attention)"),
+                     ("attn_fwd_db", "attn_fwd_db_kernel"), ("attn_fwd", "attn_fwd_kernel"), ("cast_rows", "cast"),
                      ("groupnorm_apply", "groupnorm_apply"), ("groupnorm_finalize", "groupnorm_finalize"), ("layernorm", "layernorm"),
                      ("cfg_step", "cfg_step"), ("mutual", "mutual_*"), ("upsample", "upsample2x"), ("space_to_depth", "space_to_depth")):
         if key in name:
