@@ -325,8 +325,14 @@ using namespace dfb;
 static int launch_gn_apply(const float* src0, int c0, int ld0, const float* src1, int c1, int ld1, int B, int hw, int groups,
                            const float* stats, const float* gamma, const float* beta, int silu, void* out, int out_dtype,
                            int ld_out, void* raw_out, int ld_raw, cudaStream_t stream) {
-  // ~16 CTAs per SM over (B x pixel chunks)
-  int ach = (num_sms() * 16 + B - 1) / B;
+  // ~16 CTAs per SM over (B x pixel chunks); DFB_GN_CTAS_PER_SM overrides (tuning hook, read once)
+  static int ctas_per_sm = 0;
+  if (ctas_per_sm == 0) {
+    const char* e = getenv("DFB_GN_CTAS_PER_SM");
+    ctas_per_sm = e ? atoi(e) : 16;
+    if (ctas_per_sm < 1) ctas_per_sm = 16;
+  }
+  int ach = (num_sms() * ctas_per_sm + B - 1) / B;
   if (ach > hw) ach = hw;
   if (ach < 1) ach = 1;
   const int appb = (hw + ach - 1) / ach;
