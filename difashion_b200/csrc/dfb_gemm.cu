@@ -35,6 +35,7 @@ constexpr int GEMM_TMEM_COLS = 512;
 struct GemmMaps {
   CUtensorMap a[2];
   CUtensorMap b;
+  CUtensorMap c;     // bf16 output, box = one epilogue chunk (32 rows x 32 columns, or x 16 GEGLU outputs): TMA-store epilogue
 };
 
 struct GemmKernelParams {
@@ -57,7 +58,20 @@ struct GemmKernelParams {
   float* gn_partial;   // optional GroupNorm partial statistics of the fp32 output
   int up_w, up_a, up_b, up_blk;   // up_w > 0: phase (up_a, up_b) of a fused nearest-2x upsample + 3x3 conv; rows are scattered into
                                   // the [B, 2H, 2W, N] output (up_w = W of the input, up_blk = H*W/32 partial blocks per image)
+  int tma_out;                    // bf16 output written with cp.async.bulk.tensor stores through maps.c (modes 0 and GEGLU)
 };
+
+// TMA store of one staged chunk (shared -> global, bulk async-group completion); issued by one lane
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+               "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {      // at most N of this thread's bulk groups still READING shared memory
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
 
 // Epilogue specialisations (compile-time, so the hot epilogue loop carries no runtime flag tests and the
 // kernel image stays small enough for the instruction cache); EPI_GENERIC keeps every option at run time.
@@ -293,6 +307,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
       }
     };
     int it = 0;
+    int tma_chunk = 0;                          // TMA-store epilogue: staging tile parity of this warp
     const uint32_t tempty_leader0 = CTA2 ? mapa_shared(tempty_bar(0), 0) : 0u;     // the leader's tmem_empty barriers
     for (int item = unit0; item < num_items; item += n_units, ++it) {
       const int mt = item_mt(item);
@@ -333,6 +348,28 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
               o[j] = a * gelu_sigmoid_f(g);
             }
           }
+          if constexpr (!kGeneric) {
+            if (p.tma_out) {
+              // TMA-store epilogue: this row's 16 bf16 outputs (32 bytes) go into a [32 rows][32 B] tile with the 32-byte swizzle
+              // (conflict-free 16-byte stores), one lane issues the bulk tensor store; two tiles per warp alternate, so the store
+              // of chunk i drains while chunk i + 1 is computed.  Half the shared-memory traffic of the transposing path and no
+              // LDS / STG in the warp's instruction stream; rows >= M and columns >= N/2 are clipped by the tensor map.
+              const uint32_t dst0 = stg + (uint32_t)(tma_chunk & 1) * 1024u;
+              if (lane == 0) tma_store_wait_read<1>();
+              __syncwarp();
+              const uint32_t rowb = dst0 + (uint32_t)lane * 32u;
+              const uint32_t sw = (uint32_t)((lane >> 2) & 1) << 4;
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + (0u ^ sw)), "r"(pack_bf16x2(o[0], o[1])), "r"(pack_bf16x2(o[2], o[3])),
+                           "r"(pack_bf16x2(o[4], o[5])), "r"(pack_bf16x2(o[6], o[7])) : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + (16u ^ sw)), "r"(pack_bf16x2(o[8], o[9])), "r"(pack_bf16x2(o[10], o[11])),
+                           "r"(pack_bf16x2(o[12], o[13])), "r"(pack_bf16x2(o[14], o[15])) : "memory");
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) tma_store_2d(&maps.c, dst0, n0 >> 1, row0);
+              ++tma_chunk;
+              continue;
+            }
+          }
           // staging tile [32 rows][64 B], 64-byte swizzle
 #pragma unroll
           for (int u2 = 0; u2 < 4; ++u2) {
@@ -365,6 +402,40 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
           }
           __syncwarp();
           continue;
+        }
+        if constexpr (MODE == 0) {
+          if (p.tma_out) {
+            // TMA-store epilogue for the bf16-output, bias-only GEMMs (q|k|v, q, K/V projections): thread = accumulator row, its
+            // 32 columns (64 bytes) staged with the 64-byte swizzle, one bulk tensor store per chunk (see the GEGLU path)
+            float4 bv[8];
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + n0);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4)
+              bv[j4] = (p.bias && n0 + 4 * j4 < p.N) ? __ldg(bp + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!waited) { mbar_wait(tfull_bar(as), aphase); tc_fence_after(); waited = true; }
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(taddr0 + (uint32_t)(c * 32), r);
+            tmem_ld_wait();
+            const uint32_t dst0 = stg + (uint32_t)(tma_chunk & 1) * 2048u;
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
+            const uint32_t rowb = dst0 + (uint32_t)lane * 64u;
+            const uint32_t sw = (uint32_t)((lane >> 1) & 3);
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const float4 b0 = bv[2 * q4], b1 = bv[2 * q4 + 1];
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + (((uint32_t)q4 ^ sw) << 4)),
+                           "r"(pack_bf16x2(__uint_as_float(r[8 * q4 + 0]) + b0.x, __uint_as_float(r[8 * q4 + 1]) + b0.y)),
+                           "r"(pack_bf16x2(__uint_as_float(r[8 * q4 + 2]) + b0.z, __uint_as_float(r[8 * q4 + 3]) + b0.w)),
+                           "r"(pack_bf16x2(__uint_as_float(r[8 * q4 + 4]) + b1.x, __uint_as_float(r[8 * q4 + 5]) + b1.y)),
+                           "r"(pack_bf16x2(__uint_as_float(r[8 * q4 + 6]) + b1.z, __uint_as_float(r[8 * q4 + 7]) + b1.w)) : "memory");
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) tma_store_2d(&maps.c, dst0, n0, row0);
+            ++tma_chunk;
+            continue;
+          }
         }
         if constexpr (!kGeneric) {
           // ---- specialised epilogue (aligned, N % 4 == 0, no activation): straight-line code.  lane -> 4 columns
@@ -663,6 +734,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
         else mbar_arrive(tempty_bar(as));
       }
     }
+    // TMA-store epilogue: wait for this lane's bulk stores to COMPLETE (not only to have read shared memory) before the CTA
+    // retires: the next kernel on the stream reads what they write
+    if (p.tma_out && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -673,6 +747,16 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
     if constexpr (CTA2) tmem_dealloc_pair(tmem_base, GEMM_TMEM_COLS);
     else tmem_dealloc(tmem_base, GEMM_TMEM_COLS);
   }
+}
+
+// DFB_GEMM_TMA_STORE=0 disables the TMA-store epilogue (read once)
+static bool tma_store_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DFB_GEMM_TMA_STORE");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v != 0;
 }
 
 // tuning hook: DFB_GEMM_STAGES=<n> caps the smem ring depth (read once)
@@ -938,6 +1022,18 @@ extern "C" int dfb_gemm(const dfb_gemm_params* q, void* stream_) {
             mode == (EPI_OUT_F32 | EPI_ROWBIAS)))
         mode = EPI_GENERIC;
     }
+  }
+  // TMA-store epilogue (cp.async.bulk.tensor shared -> global) for the bf16-output GEMMs: bias-only (mode 0: q|k|v, q, K/V
+  // projections) and GEGLU.  DFB_GEMM_TMA_STORE=0 keeps the transposing st.global epilogue.
+  kp.tma_out = 0;
+  if ((mode == 0 || mode == EPI_GEGLU) && !kp.out_fp32 && q->up2x == 0 && tma_store_enabled()) {
+    const int n_out = kp.geglu ? q->N / 2 : q->N;
+    uint64_t dims[2] = {(uint64_t)n_out, (uint64_t)q->M};
+    uint64_t str[1] = {(uint64_t)q->out_ld * 2};
+    uint32_t box[2] = {kp.geglu ? 16u : 32u, 32u};
+    int rc = make_tmap(&maps.c, q->out, 2, 2, dims, str, box, kp.geglu ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc != DFB_OK) return rc;
+    kp.tma_out = 1;
   }
   const int num_tiles = kp.n_tiles_m * kp.n_tiles_n;
   int grid = num_tiles < num_sms() ? num_tiles : num_sms();
