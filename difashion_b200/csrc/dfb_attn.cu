@@ -29,6 +29,9 @@ constexpr int ATT_BLOCK_Q = 128;
 #ifndef DFB_ATTN_POLY_DEFAULT
 #define DFB_ATTN_POLY_DEFAULT 0
 #endif
+#ifndef DFB_ATTN_SA8_TILES_DEFAULT
+#define DFB_ATTN_SA8_TILES_DEFAULT 1      // measured on B200 (B = 64, S = 4096, d = 40): column split 2.905 ms, tile split 2.783 ms
+#endif
 #ifndef DFB_ATTN_SA8_POLY_DEFAULT
 #define DFB_ATTN_SA8_POLY_DEFAULT 2      // measured on B200: 2.903 (none) / 2.864 (2 of 16) / 3.017 (4) / 3.463 ms (8) at B = 64, S = 4096, d = 40
 #endif
@@ -1107,6 +1110,9 @@ extern "C" int dfb_attention(const dfb_attn_params* a, void* stream_) {
     DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_sa8_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_sa8_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_sa8_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_sa8_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_sa8_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_sa8_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     attr_set[dev] = true;
   }
   dim3 grid((a->Sq + ATT_BLOCK_Q - 1) / ATT_BLOCK_Q, a->heads, a->B);
@@ -1115,10 +1121,17 @@ extern "C" int dfb_attention(const dfb_attn_params* a, void* stream_) {
     attn_short_kv_kernel<<<gshort, ATT_THREADS, smem, stream>>>(maps, kp);
   } else if (use_sa8) {
     // share of the exponentials on the FMA pipe: dbg_flags bits 13-14 (1 none, 2 = 2/16, 3 = 4/16), DFB_ATTN_SA8_POLY = 0|2|4|8, or built-in
-    int poly8 = attn_env_int("DFB_ATTN_SA8_POLY", DFB_ATTN_SA8_POLY_DEFAULT);
+    const bool tiles8 = attn_env_int("DFB_ATTN_SA8_TILES", DFB_ATTN_SA8_TILES_DEFAULT) != 0;
+    // (the polynomial share pays only with the column split: 2.867 vs 2.905 ms; with the tile split 2.821 vs 2.783)
+    int poly8 = attn_env_int("DFB_ATTN_SA8_POLY", tiles8 ? 0 : DFB_ATTN_SA8_POLY_DEFAULT);
     const int sel8 = (a->dbg_flags >> 13) & 3;
     if (sel8) poly8 = sel8 == 1 ? 0 : sel8 == 2 ? 2 : 4;
-    if (poly8 == 8) attn_fwd_sa8_kernel<8><<<grid, ATT_SA8_THREADS, smem, stream>>>(maps, kp);
+    // DFB_ATTN_SA8_TILES = 1 (default): the warps of a lane quarter alternate TILES instead of splitting every tile's columns
+    if (tiles8) {
+      if (poly8 == 4) attn_fwd_sa8_kernel<4, true><<<grid, ATT_SA8_THREADS, smem, stream>>>(maps, kp);
+      else if (poly8 == 2) attn_fwd_sa8_kernel<2, true><<<grid, ATT_SA8_THREADS, smem, stream>>>(maps, kp);
+      else attn_fwd_sa8_kernel<0, true><<<grid, ATT_SA8_THREADS, smem, stream>>>(maps, kp);
+    } else if (poly8 == 8) attn_fwd_sa8_kernel<8><<<grid, ATT_SA8_THREADS, smem, stream>>>(maps, kp);
     else if (poly8 == 4) attn_fwd_sa8_kernel<4><<<grid, ATT_SA8_THREADS, smem, stream>>>(maps, kp);
     else if (poly8 == 2) attn_fwd_sa8_kernel<2><<<grid, ATT_SA8_THREADS, smem, stream>>>(maps, kp);
     else attn_fwd_sa8_kernel<0><<<grid, ATT_SA8_THREADS, smem, stream>>>(maps, kp);

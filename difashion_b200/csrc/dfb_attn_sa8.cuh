@@ -32,7 +32,14 @@ constexpr int ATT_SA8_THREADS = 320;      // 8 softmax warps + TMA producer + MM
 // POLY: of every 16 exponentials of the full-tile path, POLY are computed on the FMA pipe (ex2_poly3, dfb_attn_sa.cuh).  With four
 // softmax warps per scheduler the loop is MUFU-queue-bound (ncu: mio_throttle is its top stall), which is the regime where
 // moving work to the idle FMA pipe can pay (it did not with one or two warps per scheduler).
-template <int POLY>
+// TILES: how the two warps of a lane quarter divide the work.  false: the two 32-column halves of EVERY score tile (lock-step:
+// both wait for the same S, both arrive on the same P).  true: ALTERNATE TILES — warp h takes all 64 columns (two 32-column
+// passes) of tiles j = h (mod 2).  The two warps of a quarter sit on the same scheduler (TMEM lane quarter = warp id mod 4 =
+// scheduler), so in the column split a scheduler sees only two independent streams (one per CTA) of two lock-stepped warps each;
+// with the tile split it sees four streams that are a tile apart by construction, with half as many barrier operations per score.
+// The static reference maximum is what allows it: consecutive tiles of a row are handled by different warps with no hand-over.
+// (Three warps per lane quarter, one per buffer of the score ring, measured no faster: 2.85 vs 2.78 ms — profiles/r02_attention_sa8_tile_split.log.)
+template <int POLY, bool TILES = false>
 __global__ void __launch_bounds__(ATT_SA8_THREADS, 2)
 attn_fwd_sa8_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnKernelParams p) {
   constexpr int KV = ATT_SA_KV;
@@ -62,7 +69,8 @@ attn_fwd_sa8_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
   const int lane = threadIdx.x & 31;
   const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
   const int n_tiles = p.n_kv_tiles;
-  constexpr int W_TMA = 8, W_MMA = 9;
+  constexpr int NW = 2;                    // softmax warps per lane quarter
+  constexpr int W_TMA = 4 * NW, W_MMA = 4 * NW + 1;
 
   if (warp == W_TMA && lane == 0) {
     tma_prefetch_desc(&maps.q);
@@ -71,7 +79,7 @@ attn_fwd_sa8_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
     mbar_init(q_full, 1);
     for (int i = 0; i < NS; ++i) {
       mbar_init(s_full(i), 1);
-      mbar_init(p_full(i), 256);
+      mbar_init(p_full(i), TILES ? 128 : 256);
       mbar_init(o_done(i), 1);
     }
     for (int s = 0; s < NST; ++s) {
@@ -149,8 +157,8 @@ attn_fwd_sa8_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
         const uint64_t dv = desc_v0 + (uint64_t)((uint32_t)st * stage_step);
         const uint32_t tP = tmem_base + (uint32_t)sb * KV;
 #pragma unroll
-        for (int k = 0; k < KV / 16; ++k)                  // keys 16k .. 16k+15: P columns 8k (k < 2) or 32 + 8(k - 2)
-          umma_f16_ts(tmem_O, tP + (uint32_t)(k < 2 ? 8 * k : 32 + 8 * (k - 2)), dv + (uint64_t)(k * (512 / 16)), idesc_pv, (j | k) != 0);
+        for (int k = 0; k < KV / 16; ++k)                  // keys 16k .. 16k+15: P columns 8k (k < 2) or 32 + 8(k - 2); tile split: 8k
+          umma_f16_ts(tmem_O, tP + (uint32_t)((TILES || k < 2) ? 8 * k : 32 + 8 * (k - 2)), dv + (uint64_t)(k * (512 / 16)), idesc_pv, (j | k) != 0);
         umma_commit(o_done(sb));
         umma_commit(kv_empty(st));
       }
@@ -169,6 +177,86 @@ attn_fwd_sa8_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
     const uint32_t col0 = (uint32_t)half * 32u;           // score columns [col0, col0 + 32); P goes to [col0, col0 + 16)
     float m_ref = 0.f;
     bool overflow = false;
+    if constexpr (TILES) {
+      // ---- tile split: warp `half` handles tiles half, half + 2, ...; 32 columns at a time (registers) ----
+      {
+        // reference maximum = maximum of the row's FIRST tile, found by warp 0 of the quarter, read by warp 1
+        if (half == 0) {
+          mbar_wait(s_full(0), 0);
+          tc_fence_after();
+          float mh = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t sreg[32];
+            tmem_ld_32x32b_x32(tmem_base + lane_addr + (uint32_t)(c * 32), sreg);
+            tmem_ld_wait();
+            const int kv_valid = min(32, p.Skv - c * 32);
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < kv_valid) mh = fmaxf(mh, __uint_as_float(sreg[i]));
+          }
+          m_ref = mh * p.scale_log2;
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(mx_smem + (uint32_t)row * 4u), "f"(m_ref) : "memory");
+        }
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + quarter), "n"(32 * NW) : "memory");     // the warps of this lane quarter
+        if (half != 0) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(m_ref) : "r"(mx_smem + (uint32_t)row * 4u) : "memory");
+      }
+      int sb = half;                     // score buffer and barrier phase of tile j = half, half + NW, ...
+      uint32_t sph = 0;
+      for (int j = half; j < n_tiles; j += NW) {
+        const uint32_t tS = tmem_base + (uint32_t)sb * KV + lane_addr;
+        mbar_wait(s_full(sb), sph);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t sreg[32];
+          tmem_ld_32x32b_x32(tS + (uint32_t)(c * 32), sreg);
+          tmem_ld_wait();
+          const int kv_valid = min(32, p.Skv - j * KV - c * 32);
+          uint32_t pw[16];
+          if (kv_valid == 32) {
+            float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              float pv[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float sv = __uint_as_float(sreg[h * 16 + i]);
+                m4[i & 3] = fmaxf(m4[i & 3], sv);
+                const float x = fmaf(sv, p.scale_log2, -m_ref);
+                const bool on_fma = POLY > 0 && ((i + 1) % (16 / (POLY > 0 ? POLY : 1))) == 0;
+                pv[i] = on_fma ? ex2_poly3(x) : ex2f(x);
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) pw[h * 8 + i] = pack_bf16x2(pv[2 * i], pv[2 * i + 1]);
+            }
+            const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * p.scale_log2;
+            overflow |= mx > m_ref + 100.0f;
+          } else {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              float pv[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float x = fmaf(__uint_as_float(sreg[h * 16 + i]), p.scale_log2, -m_ref);
+                const bool ok = h * 16 + i < kv_valid;
+                overflow |= ok && x > 100.0f;
+                pv[i] = ok ? ex2f(x) : 0.f;
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) pw[h * 8 + i] = pack_bf16x2(pv[2 * i], pv[2 * i + 1]);
+            }
+          }
+          // P of keys 32c .. 32c+31 -> columns [16c, 16c + 16) of the score buffer (score columns < 32(c + 1) are consumed)
+          tmem_st_32x32b_x16(tS + (uint32_t)(c * 16), pw);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(p_full(sb));
+        sb += NW;
+        if (sb >= NS) { sb -= NS; sph ^= 1u; }
+      }
+    } else {
     int sb = 0;
     uint32_t sph = 0;
     for (int j = 0; j < n_tiles; ++j) {
@@ -231,6 +319,7 @@ attn_fwd_sa8_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
       mbar_arrive(p_full(sb));
       if (++sb == NS) { sb = 0; sph ^= 1u; }
     }
+    }
     if (__any_sync(0xffffffffu, overflow) && lane == 0)
       asm volatile("st.shared.u32 [%0], %1;" ::"r"(flag_smem), "r"(1u) : "memory");
     // ---- epilogue: O / O[:, l_col] -> bf16; the two halves split the 16-column output chunks ----
@@ -249,7 +338,7 @@ attn_fwd_sa8_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
     }
     const float inv_l = 1.0f / l;
     __nv_bfloat16* orow = p.out + (size_t)b * p.out_batch_stride + (size_t)q_row * p.out_ld + p.out_col0 + head * p.dp;
-    for (int c = half; c < dchunks; c += 2) {
+    for (int c = half; c < dchunks; c += NW) {
       uint32_t r[16];
       tmem_ld_32x32b_x16(tmem_O + lane_addr + (uint32_t)(c * 16), r);
       tmem_ld_wait();

@@ -1,5 +1,7 @@
 """GPU parity of the tcgen05 flash-attention kernel vs plain softmax(QK^T*scale)V in fp64 on the same
 bf16 operands.  Tolerance rel-L2 <= 1e-2 (P and the output are rounded to bf16; measured ~3e-3)."""
+import os
+
 import pytest
 import torch
 
@@ -152,10 +154,14 @@ def test_self_attention_kernel_ones_column_and_polynomial_exponentials(B, H, S, 
     for name, flags, ones, w in (("db", 4096, None, None), ("sa", 1 << 13, None, None), ("sa+ones", 1 << 13, d, None),
                                  ("sa+ones+poly2", 2 << 13, d, None), ("sa+ones+poly4", 3 << 13, d, None), ("sa+poly4", 3 << 13, None, None),
                                  ("sa8", 1 << 13, d, wsp), ("sa8+poly2", 2 << 13, d, wsp), ("sa8+poly4", 3 << 13, d, wsp), ("sa8 default", 0, d, wsp),
-                                 ("default", 0, d, None)):
+                                 ("sa8 tile split", 1 << 13, d, wsp), ("sa8 tile split + poly2", 2 << 13, d, wsp), ("default", 0, d, None)):
         out = torch.full((B, S, H * dp), float("nan"), dtype=torch.bfloat16, device="cuda")
-        ops.attention(qp, kp, vp, out, heads=H, dp=dp, scale=d ** -0.5, dbg_flags=flags, ones_col=ones, workspace=w)
-        torch.cuda.synchronize()
+        os.environ["DFB_ATTN_SA8_TILES"] = "1" if "tile split" in name else "0"
+        try:
+            ops.attention(qp, kp, vp, out, heads=H, dp=dp, scale=d ** -0.5, dbg_flags=flags, ones_col=ones, workspace=w)
+            torch.cuda.synchronize()
+        finally:
+            os.environ.pop("DFB_ATTN_SA8_TILES", None)
         o = out.reshape(B, S, H, dp)
         got = o[..., :d].reshape(B, S, H * d)
         assert rel_l2(got, ref) < 1e-2, err_report(got.reshape(-1, H * d), ref.reshape(-1, H * d), f"attn {name}")

@@ -15,7 +15,7 @@ qkv = torch.randn(B, 4096, 3 * 384, generator=g).bfloat16().cuda()
 qkv.view(B, 4096, 3, 8, 48)[..., 40:] = 0
 qkv.view(B, 4096, 3, 8, 48)[:, :, 2, :, 40] = 1.0
 o = torch.empty(B, 4096, 384, dtype=torch.bfloat16, device="cuda")
-tiles = B * 8 * 32 * 32 / 148
+tiles_per_sm = B * 8 * 32 * 32 / 148
 
 
 def run(flags, ones, reps=5):
@@ -47,12 +47,12 @@ def run(flags, ones, w=None, reps=5):
     return e0.elapsed_time(e1) / reps
 
 
-variants = [("round-1 double-buffered (dbg bit12)", 4096, None, None), ("sa", 1 << 13, None, None), ("sa + ones", 1 << 13, 40, None),
-            ("sa8 (8 softmax warps) + redo launch", 1 << 13, 40, wsp), ("sa8 + poly 2/16", 2 << 13, 40, wsp), ("sa8 + poly 4/16", 3 << 13, 40, wsp)]
-os.environ["DFB_ATTN_SA8_POLY"] = "8"
-variants.append(("sa8 + poly 8/16", 0, 40, wsp))
+variants = [("round-1 double-buffered (dbg bit12)", 4096, None, None, "0"), ("sa + ones", 1 << 13, 40, None, "0"),
+            ("sa8 column split", 1 << 13, 40, wsp, "0"), ("sa8 column split + poly 2/16", 2 << 13, 40, wsp, "0"),
+            ("sa8 TILE split", 1 << 13, 40, wsp, "1"), ("sa8 TILE split + poly 2/16", 2 << 13, 40, wsp, "1")]
 for rnd in range(3):
-    for name, flags, ones, w in variants:
+    for name, flags, ones, w, tiles in variants:
+        os.environ["DFB_ATTN_SA8_TILES"] = tiles[0]
         ms = run(flags, ones, w)
-        print(f"{name:40s} {ms:8.3f} ms  {4.0 * B * 8 * 4096 * 4096 * 40 / ms / 1e9:8.1f} TFLOP/s (d = 40)  {ms * 1e-3 / tiles * 1e9:7.1f} ns per 128x128 tile per SM", flush=True)
+        print(f"{name:40s} {ms:8.3f} ms  {4.0 * B * 8 * 4096 * 4096 * 40 / ms / 1e9:8.1f} TFLOP/s (d = 40)  {ms * 1e-3 / tiles_per_sm * 1e9:7.1f} ns per 128x128 tile per SM", flush=True)
 print("flags raised:", int(wsp.sum()))
