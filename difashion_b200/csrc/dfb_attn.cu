@@ -59,6 +59,8 @@ struct AttnKernelParams {
   int s_ring;                     // attn_fwd_sa_kernel: score / probability buffers in tensor memory (2 or 3)
   int tl_second;                  // attn_fwd_sa_kernel tuning hook: linear index of the second CTA that writes stamps
   int* redo_flags;                // attn_fwd_sa8_kernel -> attn_fwd_sa_kernel<.., REDO>: one flag per CTA (caller's workspace)
+  int dbg_delay;                  // test hooks of attn_fwd_sa8_kernel (dbg_flags bits 16-19): bit0 slow MMA issuer, bit1 slow TMA producer, bit2 / bit3 the softmax warps of the odd / even tiles lag
+  int n_q_tiles;                  // query tiles per (batch, head) = grid.x of the per-tile kernels (the REDO kernel scans that many flags)
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -1019,6 +1021,8 @@ extern "C" int dfb_attention(const dfb_attn_params* a, void* stream_) {
   const bool use_sa8 = sa_ones && 3 * bkv + a->dp <= 256 && a->workspace != nullptr && (a->dbg_flags & 32768) == 0 &&
                        attn_env_int("DFB_ATTN_SA8", 1) != 0;
   kp.redo_flags = (int*)a->workspace;
+  kp.n_q_tiles = (a->Sq + ATT_BLOCK_Q - 1) / ATT_BLOCK_Q;
+  kp.dbg_delay = (a->dbg_flags >> 16) & 15;
   // three score buffers where they still leave room for two CTAs per SM (3 * 64 + dp <= 256 columns: dp <= 64)
   kp.s_ring = (use_sa && 3 * bkv + a->dp <= 256 && (use_sa8 || attn_env_int("DFB_ATTN_S_RING", 3) >= 3)) ? 3 : 2;
   uint32_t need_cols = use_short ? (uint32_t)(2 * (bkv + a->dp)) : use_sa ? (uint32_t)(kp.s_ring * bkv + a->dp)
@@ -1136,7 +1140,8 @@ extern "C" int dfb_attention(const dfb_attn_params* a, void* stream_) {
     else if (poly8 == 2) attn_fwd_sa8_kernel<2><<<grid, ATT_SA8_THREADS, smem, stream>>>(maps, kp);
     else attn_fwd_sa8_kernel<0><<<grid, ATT_SA8_THREADS, smem, stream>>>(maps, kp);
     DFB_CHECK_CUDA(cudaGetLastError());
-    attn_fwd_sa_kernel<true, 0, true><<<grid, ATT_THREADS, smem, stream>>>(maps, kp);     // flagged tiles only (normally none)
+    // flagged tiles only (normally none): one CTA per (batch, head) scans that head's flags
+    attn_fwd_sa_kernel<true, 0, true><<<dim3(1, grid.y, grid.z), ATT_THREADS, smem, stream>>>(maps, kp);
   } else if (use_sa) {
 #define DFB_SA_LAUNCH(O_, P_) attn_fwd_sa_kernel<O_, P_><<<grid, ATT_THREADS, smem, stream>>>(maps, kp)
     if (sa_ones) { if (sa_poly == 4) DFB_SA_LAUNCH(true, 4); else if (sa_poly == 2) DFB_SA_LAUNCH(true, 2); else DFB_SA_LAUNCH(true, 0); }

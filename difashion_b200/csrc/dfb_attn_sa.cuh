@@ -34,15 +34,12 @@ __device__ __forceinline__ float ex2_poly3(float x) {
 
 constexpr int ATT_SA_KV = 64;
 
-// REDO: the exact fallback behind attn_fwd_sa8_kernel (dfb_attn_sa8.cuh) — a CTA exits at once unless the 8-warp kernel
-// flagged its tile (a score overflowed the static reference maximum).
-template <bool ONES, int POLY, bool REDO = false>
-__global__ void __launch_bounds__(ATT_THREADS, 2)
-attn_fwd_sa_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnKernelParams p) {
+// One 128-query tile `qt` of (batch blockIdx.z, head blockIdx.y).  RERUN: the CTA may run several tiles one after the other
+// (the REDO kernel below): tensor memory is allocated without giving up the allocation permit and the mbarriers are
+// invalidated at the end so that the next tile can initialise them again.
+template <bool ONES, int POLY, bool RERUN>
+__device__ __forceinline__ void attn_sa_tile(const AttnMaps& maps, const AttnKernelParams& p, const int qt) {
   constexpr int KV = ATT_SA_KV;
-  if constexpr (REDO) {
-    if (p.redo_flags[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] == 0) return;
-  }
   constexpr int NST_MAX = 8;               // K/V ring depth (TMA issued that many tiles ahead)
   constexpr int NS_MAX = 3;                // score / probability ring in tensor memory
   const int NST = p.kv_stages;
@@ -68,7 +65,7 @@ attn_fwd_sa_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant_
   // warp ids: the issue arbiter favours them)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  const int head = blockIdx.y, b = blockIdx.z;
   const int n_tiles = p.n_kv_tiles;
   constexpr int W_TMA = 4, W_MMA = 5;
 
@@ -89,7 +86,10 @@ attn_fwd_sa_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant_
     fence_mbar_init();
     fence_proxy_async_smem();
   }
-  if (warp == W_MMA) tmem_alloc(tmem_ptr_smem, p.tmem_cols);
+  if (warp == W_MMA) {
+    if constexpr (RERUN) tmem_alloc_keep_permit(tmem_ptr_smem, p.tmem_cols);
+    else tmem_alloc(tmem_ptr_smem, p.tmem_cols);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -99,7 +99,7 @@ attn_fwd_sa_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant_
   // tuning hook: stamps of two CTAs — linear block 0 and block `tl_second` (= number of SMs: with two CTAs per SM the block
   // scheduler places it next to block 0) — 2048 int64 each, the SM id in the last slot
   const int lin_block = (int)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
-  const int tl_slot = p.timeline == nullptr ? -1 : (lin_block == 0 ? 0 : (lin_block == p.tl_second ? 1 : -1));
+  const int tl_slot = (RERUN || p.timeline == nullptr) ? -1 : (lin_block == 0 ? 0 : (lin_block == p.tl_second ? 1 : -1));
   const bool tl_cta = tl_slot >= 0;
   long long* const tl = tl_cta ? p.timeline + 2048 * tl_slot : nullptr;
 
@@ -343,6 +343,38 @@ attn_fwd_sa_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant_
   if (warp == W_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+  if constexpr (RERUN) {
+    if (warp == W_TMA && lane == 0) {
+      mbar_inval(q_full);
+      for (int i = 0; i < NS; ++i) { mbar_inval(s_full(i)); mbar_inval(p_full(i)); mbar_inval(o_done(i)); }
+      for (int st = 0; st < NST; ++st) { mbar_inval(kv_full(st)); mbar_inval(kv_empty(st)); }
+    }
+    __syncthreads();
+  }
+}
+
+// REDO: the exact fallback behind attn_fwd_sa8_kernel (dfb_attn_sa8.cuh) — launched right behind it on a grid of ONE CTA
+// per (batch, head) (a CTA per query tile, exiting at once unless flagged, cost 0.3 - 0.4 ms per launch at 49 k - 65 k CTAs:
+// profiles/r02_ncu_launches_step_v2.csv).  The CTA reads the flags of its `n_q_tiles` query tiles 32 at a time (every warp
+// loads the same words, so the ballot is CTA-uniform) and recomputes the flagged tiles one after the other — normally none.
+template <bool ONES, int POLY, bool REDO = false>
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attn_fwd_sa_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnKernelParams p) {
+  if constexpr (REDO) {
+    const int* flags = p.redo_flags + (size_t)(blockIdx.z * gridDim.y + blockIdx.y) * (size_t)p.n_q_tiles;
+    const int lane = threadIdx.x & 31;
+    for (int q0 = 0; q0 < p.n_q_tiles; q0 += 32) {
+      const int f = q0 + lane < p.n_q_tiles ? flags[q0 + lane] : 0;
+      uint32_t mask = __ballot_sync(0xffffffffu, f != 0);
+      while (mask) {
+        const int qt = q0 + __ffs((int)mask) - 1;
+        mask &= mask - 1u;
+        attn_sa_tile<ONES, POLY, true>(maps, p, qt);
+      }
+    }
+  } else {
+    attn_sa_tile<ONES, POLY, false>(maps, p, (int)blockIdx.x);
   }
 }
 

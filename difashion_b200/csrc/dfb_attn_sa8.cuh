@@ -110,6 +110,7 @@ attn_fwd_sa8_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
     uint32_t ph = 0;
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(kv_empty(st), ph ^ 1u);
+      if (p.dbg_delay & 2) __nanosleep(3000);             // test hook: a slow TMA producer
       if (elect_one()) {
         const uint32_t sK = sKV + (uint32_t)st * 2 * kv_tile_bytes;
         const uint32_t sV = sK + kv_tile_bytes;
@@ -152,6 +153,7 @@ attn_fwd_sa8_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
     uint32_t sph = 0;
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(p_full(sb), sph);                         // both halves of P written over S[sb]
+      if (p.dbg_delay & 1) __nanosleep(4000);             // test hook: a slow MMA issuer
       tc_fence_after();
       if (elect_one()) {
         const uint64_t dv = desc_v0 + (uint64_t)((uint32_t)st * stage_step);
@@ -206,6 +208,8 @@ attn_fwd_sa8_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
       for (int j = half; j < n_tiles; j += NW) {
         const uint32_t tS = tmem_base + (uint32_t)sb * KV + lane_addr;
         mbar_wait(s_full(sb), sph);
+        if ((p.dbg_delay & 4) && half == 1) __nanosleep(5000);      // test hook: the softmax warps of the odd tiles lag
+        if ((p.dbg_delay & 8) && half == 0) __nanosleep(5000);      //            ... of the even tiles
         tc_fence_after();
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
@@ -262,6 +266,8 @@ attn_fwd_sa8_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
     for (int j = 0; j < n_tiles; ++j) {
       const uint32_t tS = tmem_base + (uint32_t)sb * KV + lane_addr + col0;
       mbar_wait(s_full(sb), sph);
+      if ((p.dbg_delay & 4) && half == 1) __nanosleep(5000);
+      if ((p.dbg_delay & 8) && half == 0) __nanosleep(5000);
       tc_fence_after();
       uint32_t sreg[32];
       tmem_ld_32x32b_x32(tS, sreg);
@@ -323,8 +329,19 @@ attn_fwd_sa8_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant
     if (__any_sync(0xffffffffu, overflow) && lane == 0)
       asm volatile("st.shared.u32 [%0], %1;" ::"r"(flag_smem), "r"(1u) : "memory");
     // ---- epilogue: O / O[:, l_col] -> bf16; the two halves split the 16-column output chunks ----
-    int sb_last = (n_tiles - 1) % NS;
-    mbar_wait(o_done(sb_last), (uint32_t)((n_tiles - 1) / NS) & 1u);
+    const int sb_last = (n_tiles - 1) % NS;
+    const uint32_t ph_last = (uint32_t)((n_tiles - 1) / NS) & 1u;
+    if constexpr (TILES) {
+      // A parity wait is only right when the barrier is exactly one phase behind.  The warp that does NOT own the last tile
+      // has consumed S(n - 2) only, which says nothing about P V(n - 4) — the previous phase of o_done(sb_last) — having
+      // retired: with a slow MMA issuer the wait below passed one phase early and O was read with the last tiles missing
+      // (found with compute-sanitizer's timing, tools/attn_race_probe.py; reproduced by the dbg_delay hook in
+      // tests/test_attn_gpu.py).  S(n - 1) complete => Q K^T(n - 1) retired => P V(n - 4), issued before it, retired.
+#ifndef DFB_SA8_NO_EPILOGUE_FIX      // (A/B builds only: shows that the robustness test catches the missing wait)
+      mbar_wait(s_full(sb_last), ph_last);
+#endif
+    }
+    mbar_wait(o_done(sb_last), ph_last);
     tc_fence_after();
     float l;
     {

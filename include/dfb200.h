@@ -135,7 +135,7 @@ typedef struct dfb_attn_params {
   float scale;            /* softmax scale (true head_dim ** -0.5)                          */
   int32_t block_kv;       /* KV tile (multiple of 16, <= 128); 0 = automatic                */
   int32_t dbg_v_lbo, dbg_v_sbo; /* 0 = default; test hooks for the V descriptor strides     */
-  int32_t dbg_flags;      /* 0 = default; tuning hooks: bit1 one CTA per SM, bit3 single-buffer kernel, bit4 P via smem, bit6 no short-KV kernel, bits 8-11 query tiles per CTA of the short-KV kernel, bit12 round-1 double-buffered kernel instead of attn_fwd_sa_kernel, bits 13-14 share of the exponentials on the FMA pipe (1 none, 2 = 2/16, 3 = 4/16), bit15 no 8-softmax-warp kernel */
+  int32_t dbg_flags;      /* 0 = default; tuning hooks: bit1 one CTA per SM, bit3 single-buffer kernel, bit4 P via smem, bit6 no short-KV kernel, bits 8-11 query tiles per CTA of the short-KV kernel, bit12 round-1 double-buffered kernel instead of attn_fwd_sa_kernel, bits 13-14 share of the exponentials on the FMA pipe (1 none, 2 = 2/16, 3 = 4/16), bit15 no 8-softmax-warp kernel, bits 16-19 timing perturbation of the 8-softmax-warp kernel for the robustness tests (slow MMA issuer / TMA producer / odd- / even-tile softmax warps) */
   void* dbg_timeline;     /* NULL, or device buffer of >= 4096 int64: clock64 stamps of CTA (0,0,0) (tuning)  */
   int32_t causal;         /* 1: key j is visible to query i only when j <= i (CLIPTextModel's causal mask,
                              DiFashion/models/difashion.py:339-353); 0 everywhere in the UNet              */

@@ -204,6 +204,65 @@ def test_eight_warp_kernel_flags_overflow_and_the_redo_pass_fixes_it():
     assert int(wsp.max()) == 0
 
 
+@pytest.mark.parametrize("S", [1024, 1088, 1152, 192])
+@pytest.mark.parametrize("tiles", ["1", "0"])
+def test_eight_warp_kernel_does_not_depend_on_the_relative_speed_of_its_warps(S, tiles, monkeypatch):
+    """Timing robustness of attn_fwd_sa8_kernel: dbg_flags bits 16-19 make the MMA issuer, the TMA producer or the softmax
+    warps of the odd / even tiles sleep microseconds per tile.  Every combination must reproduce the unperturbed output bit
+    for bit.  (With the tile split, the warp that does not own the last key tile once passed the final o_done parity wait a
+    phase early when the MMA issuer lagged — compute-sanitizer's timing found it; 16 / 17 / 18 / 3 key tiles cover both
+    owners of the last tile and both parities.)"""
+    from difashion_b200 import ops
+    monkeypatch.setenv("DFB_ATTN_SA8_TILES", tiles)
+    B, H, d = 1, 2, 40
+    q, k, v, qp, kp, vp, dp = _ones_case(B, S, H, d, seed=S)
+    ref = _ref(q, k, v, H, d, d ** -0.5)
+    wsp = torch.full((ops.attention_ws_elems(B, H, S),), -7, dtype=torch.int32, device="cuda")
+    outs = []
+    for delay in (0, 1, 2, 4, 8, 1 | 4, 1 | 8, 2 | 4, 1 | 2 | 8):
+        out = torch.full((B, S, H * dp), float("nan"), dtype=torch.bfloat16, device="cuda")
+        ops.attention(qp, kp, vp, out, heads=H, dp=dp, scale=d ** -0.5, dbg_flags=delay << 16, ones_col=d, workspace=wsp)
+        torch.cuda.synchronize()
+        assert int(wsp.min()) == 0 and int(wsp.max()) == 0
+        outs.append(out)
+        assert torch.equal(out, outs[0]), f"delay mask {delay}: differs from the unperturbed launch"
+    got = outs[0].reshape(B, S, H, dp)[..., :d].reshape(B, S, H * d)
+    assert rel_l2(got, ref) < 1e-2
+
+
+def test_redo_pass_scans_more_than_32_query_tiles_and_recomputes_only_the_flagged_ones():
+    """The redo launch runs ONE CTA per (batch, head), which reads that head's per-tile flags 32 at a time and recomputes the
+    flagged tiles one after the other (tensor memory and barriers set up again per tile).  34 query tiles; only the queries of
+    tiles 3 and 33 of head 1 score ~ +190 log2-units against one late key: exactly those two flags, exact result everywhere."""
+    from difashion_b200 import ops
+    B, S, H, d = 1, 34 * 128, 2, 40
+    q, k, v, qp, kp, vp, dp = _ones_case(B, S, H, d, seed=11)
+    u = torch.zeros(d)
+    u[0] = 1.0
+    qq, kk = q.float().cpu().view(B, S, H, d), k.float().cpu().view(B, S, H, d)
+    kk[0, 1000, 1] = 30.0 * u                                    # one late key of head 1 ...
+    for t in (3, 33):
+        qq[0, t * 128:(t + 1) * 128, 1] = 28.0 * u               # ... that the queries of tiles 3 and 33 align with: 840 * 0.158 * 1.4427
+    q, k = qq.view(B, S, H * d).bfloat16().cuda(), kk.view(B, S, H * d).bfloat16().cuda()
+    qp, kp = _pad_heads(q, H, d, dp).contiguous(), _pad_heads(k, H, d, dp).contiguous()
+    wsp = torch.full((ops.attention_ws_elems(B, H, S),), -7, dtype=torch.int32, device="cuda")
+    out = torch.full((B, S, H * dp), float("nan"), dtype=torch.bfloat16, device="cuda")
+    ops.attention(qp, kp, vp, out, heads=H, dp=dp, scale=d ** -0.5, ones_col=d, workspace=wsp)
+    torch.cuda.synchronize()
+    flags = wsp[:B * H * 34].view(B, H, 34).cpu()
+    want = torch.zeros(B, H, 34, dtype=torch.int32)
+    want[0, 1, 3] = want[0, 1, 33] = 1
+    assert torch.equal(flags, want), flags
+    ref = _ref(q, k, v, H, d, d ** -0.5)
+    got = out.reshape(B, S, H, dp)[..., :d].reshape(B, S, H * d)
+    per_tile = ((got.double() - ref).view(B, 34, 128, H, d).pow(2).sum((2, 4)) / ref.view(B, 34, 128, H, d).pow(2).sum((2, 4))).sqrt()[0]
+    worst = [(int(i) // H, int(i) % H, float(per_tile.flatten()[i])) for i in per_tile.flatten().argsort(descending=True)[:6]]
+    assert torch.isfinite(got.float()).all() and rel_l2(got, ref) < 1e-2, f"worst (query tile, head, rel-L2): {worst}"
+    for t in (3, 33):                                              # the recomputed tiles on their own
+        sl = slice(t * 128, (t + 1) * 128)
+        assert rel_l2(got[:, sl, d:], ref[:, sl, d:]) < 1e-2
+
+
 def test_self_attention_kernel_is_deterministic_and_batch_invariant():
     from difashion_b200 import ops
     q, k, v, qp, kp, vp, dp = _ones_case(3, 1024, 8, 40, seed=9)
