@@ -64,8 +64,12 @@ def _ncu_traffic():
     """DRAM bytes per launch of the tcgen05 GEMM/conv kernel (dram__bytes_read.sum + dram__bytes_write.sum summed over the
     185 launches of one step / 185) from the newest committed ncu capture of tools/step_traffic.py, or None."""
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_step_traffic_v*.json")),
-                   key=lambda f: int(f.rsplit("_v", 1)[1].split(".")[0]))
+    import re
+
+    def key(f):         # (round, version): r02_step_traffic_v2 is newer than r01_step_traffic_v17
+        m = re.search(r"r(\d+)_step_traffic_v(\d+)", os.path.basename(f))
+        return (int(m.group(1)), int(m.group(2))) if m else (-1, -1)
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_step_traffic_v*.json")), key=key)
     if not files:
         return None, None
     with open(files[-1]) as f:
