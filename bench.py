@@ -412,7 +412,7 @@ def main():
                       "ms_per_step": att_ms, "achieved": att_alg / (att_ms / 1e3) / 1e12 if att_ms else None,
                       "achieved_executed_padded_d": att_exec_flops / (att_ms / 1e3) / 1e12 if att_ms else None, "unit": "TFLOP/s",
                       "frac_of_burst": att_alg / (att_ms / 1e3) / 1e12 / peaks["burst"] if att_ms else None,
-                      "bound": "MUFU (16 ex2/clk/SM) for S=4096, d=40: 1024 cycles per 128x128 score tile pair"},
+                      "bound": "MUFU (16 ex2/clk/SM: 1024 cycles per 128x128 score tile at S=4096, d=40) plus the TMEM loads / stores of S and P on the same MIO port (~380 cycles): DESIGN 5a"},
         "step_achieved": step_tflops, "step_frac": step_tflops / peaks["sustained"], "step_frac_of_burst": step_tflops / peaks["burst"],
     }
     if args.profile_step and rank == 0:
