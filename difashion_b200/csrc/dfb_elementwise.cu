@@ -281,16 +281,31 @@ __global__ void __launch_bounds__(256) space_to_depth_kernel(const float* __rest
   const int cq = C >> 2;
   const long long total = (long long)B * H * W * cq;
   const int H2 = H >> 1, W2 = W >> 1;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % cq) << 2;
-    long long r = i / cq;
-    const int w = (int)(r % W); r /= W;
-    const int h = (int)(r % H);
-    const int b = (int)(r / H);
-    const float4 v = ldg4(in + (((size_t)b * H + h) * W + w) * C + c);
-    const int plane = (h & 1) * 2 + (w & 1);
-    store4(out + ((((size_t)b * H2 + (h >> 1)) * W2 + (w >> 1)) * 4 + plane) * C + c, v.x, v.y, v.z, v.w);
+  // four independent 16-byte loads in flight per thread (one per grid stride): with a single one the kernel sat at 3.9 TB/s of
+  // tensor bytes (ncu launch list, 0.28 ms for the 64x64x320 tensor), exposed DRAM latency per iteration
+  constexpr int U = 4;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < total; i0 += U * stride) {
+    float4 v[U];
+    size_t dst[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      dst[u] = (size_t)-1;
+      if (i < total) {
+        const int c = (int)(i % cq) << 2;
+        long long r = i / cq;
+        const int w = (int)(r % W); r /= W;
+        const int h = (int)(r % H);
+        const int b = (int)(r / H);
+        v[u] = ldg4(in + (((size_t)b * H + h) * W + w) * C + c);
+        const int plane = (h & 1) * 2 + (w & 1);
+        dst[u] = ((((size_t)b * H2 + (h >> 1)) * W2 + (w >> 1)) * 4 + plane) * C + c;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (dst[u] != (size_t)-1) store4(out + dst[u], v[u].x, v[u].y, v[u].z, v[u].w);
   }
 }
 
