@@ -719,13 +719,19 @@ attn_fwd_db_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant_
 // software pipeline:
 //   TMA warp     : K/V once; Q tiles through a 2-slot ring
 //   MMA warp     : S[i&1] = Q_i K^T (issued one tile ahead);  O[i&1] = P_i V   (P from tensor memory, TS form)
-//   softmax warps: tile i: two passes over S[i&1] in TMEM (max, then exponentials; P over the score columns),
-//                  then the epilogue of tile i-1 (O[(i-1)&1] / l -> bf16) while PV_i runs.
+//   softmax warps: EIGHT — warps w and w + 4 share TMEM lane quarter w & 3 and alternate query tiles (warp h owns slot h of the
+//                  S / O double buffers: tiles i = h, h + 2, ...), so each scheduler interleaves four of these latency-bound
+//                  chains (two CTAs per SM) instead of two: 0.527 -> 0.458 ms at 256 rows x 64x64, 0.261 -> 0.229 at 32x32
+//                  (profiles/r02_cross_attention_eight_warps.log).  Tile i: the epilogue of the warp's previous tile i - 2
+//                  (O[h] / l -> bf16; its P V retired a tile ago), then two passes over S[h] in TMEM (max, then
+//                  exponentials; P over the score columns).  Same arithmetic per row as the four-warp form: same bits.
+//                  (Two 16-column TMEM loads per wait instead of one: slower, 0.582 ms, like the one-pass form below.)
 // TMEM columns: S[0], S[1] (block_kv each), O[0], O[1] (dp each).
 // =================================================================================================
 // (Holding the 80-column score row in registers — one TMEM pass instead of two — measured 4 % slower: 0.284 vs 0.272 ms
 // at B=128; the two-pass form is kept.)
-__global__ void __launch_bounds__(ATT_THREADS, 2)
+constexpr int ATT_SHORT_THREADS = 320;      // 8 softmax warps + TMA producer + MMA issuer
+__global__ void __launch_bounds__(ATT_SHORT_THREADS, 2)
 attn_short_kv_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -753,7 +759,7 @@ attn_short_kv_kernel(const __grid_constant__ AttnMaps maps, const __grid_constan
   const int n_qtiles = (p.Sq + ATT_BLOCK_Q - 1) / ATT_BLOCK_Q;
   const int qt0 = blockIdx.x * p.q_tiles;
   const int nt = min(p.q_tiles, n_qtiles - qt0);          // query tiles of this CTA (>= 1)
-  constexpr int W_TMA = 4, W_MMA = 5;
+  constexpr int W_TMA = 8, W_MMA = 9;
 
   if (warp == W_TMA && lane == 0) {
     tma_prefetch_desc(&maps.q);
@@ -841,6 +847,7 @@ attn_short_kv_kernel(const __grid_constant__ AttnMaps maps, const __grid_constan
   } else {
     // ---------------- softmax + epilogue warps ----------------
     const int quarter = warp & 3;
+    const int half = warp >> 2;                   // this warp's slot of the S / O double buffers: tiles half, half + 2, ...
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const int kv_chunks = bkv >> 4;
@@ -867,9 +874,12 @@ attn_short_kv_kernel(const __grid_constant__ AttnMaps maps, const __grid_constan
       tc_fence_before();
       mbar_arrive(o_empty(sl));
     };
-    for (int i = 0; i < nt; ++i) {
+    int i_last = -1;
+    for (int i = half; i < nt; i += 2) {
       const int sl = i & 1;
       const uint32_t tS = tmem_base + (uint32_t)(sl * bkv) + lane_addr;
+      if (i >= 2) epilogue(i - 2, l_prev);        // this warp's previous tile: frees O[sl] for P V of tile i
+      i_last = i;
       mbar_wait(s_full(sl), (uint32_t)(i >> 1) & 1u);
       tc_fence_after();
       float l = 0.f;
@@ -923,10 +933,9 @@ attn_short_kv_kernel(const __grid_constant__ AttnMaps maps, const __grid_constan
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(p_full(sl));
-      if (i >= 1) epilogue(i - 1, l_prev);        // overlaps PV_i
       l_prev = l;
     }
-    epilogue(nt - 1, l_prev);
+    if (i_last >= 0) epilogue(i_last, l_prev);
   }
 
   tc_fence_before();
@@ -1122,7 +1131,7 @@ extern "C" int dfb_attention(const dfb_attn_params* a, void* stream_) {
   dim3 grid((a->Sq + ATT_BLOCK_Q - 1) / ATT_BLOCK_Q, a->heads, a->B);
   if (use_short) {
     dim3 gshort((n_qtiles + kp.q_tiles - 1) / kp.q_tiles, a->heads, a->B);
-    attn_short_kv_kernel<<<gshort, ATT_THREADS, smem, stream>>>(maps, kp);
+    attn_short_kv_kernel<<<gshort, ATT_SHORT_THREADS, smem, stream>>>(maps, kp);
   } else if (use_sa8) {
     // share of the exponentials on the FMA pipe: dbg_flags bits 13-14 (1 none, 2 = 2/16, 3 = 4/16), DFB_ATTN_SA8_POLY = 0|2|4|8, or built-in
     const bool tiles8 = attn_env_int("DFB_ATTN_SA8_TILES", DFB_ATTN_SA8_TILES_DEFAULT) != 0;
