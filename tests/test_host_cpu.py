@@ -410,3 +410,16 @@ def test_output_wire_format(tmp_path):
     assert torch.equal(back[9][102]["outfits"], torch.tensor([11, 0, 7, 9]))
     merge_and_save_images([mk() for _ in range(5)], str(tmp_path / "m.jpg"))
     assert Image.open(str(tmp_path / "m.jpg")).size == (96, 96)      # 3 columns, white background
+
+
+def test_bench_picks_the_newest_step_traffic_capture_by_round_then_version(tmp_path, monkeypatch):
+    """`roofline.traffic` comes from the newest committed ncu capture: r02_..._v3 is newer than r01_..._v17 (a plain version sort
+    once picked the round-1 file)."""
+    import json
+    import bench
+    prof = tmp_path / "profiles"
+    prof.mkdir()
+    for name, val in (("r01_step_traffic_v17.json", 1.0), ("r02_step_traffic_v2.json", 2.0), ("r02_step_traffic_v3.json", 3.0)):
+        (prof / name).write_text(json.dumps({"families": {"gemm_tcgen05_kernel": {"dram_bytes_per_launch": val}}}))
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    assert bench._ncu_traffic() == (3.0, "r02_step_traffic_v3.json")
