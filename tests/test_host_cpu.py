@@ -423,3 +423,11 @@ def test_bench_picks_the_newest_step_traffic_capture_by_round_then_version(tmp_p
         (prof / name).write_text(json.dumps({"families": {"gemm_tcgen05_kernel": {"dram_bytes_per_launch": val}}}))
     monkeypatch.setattr(bench, "ROOT", str(tmp_path))
     assert bench._ncu_traffic() == (3.0, "r02_step_traffic_v3.json")
+
+
+def test_graft_entry_build_passes_on_cpu():
+    """The driver's "does it build" check: nvcc for sm_100a (cached objects make it seconds), the package imports, the ABI version
+    of the built library equals include/dfb200.h's (a hard-coded number once went stale when the ABI moved to 6), every exported
+    symbol resolves."""
+    import __graft_entry__
+    __graft_entry__.build()
